@@ -1,0 +1,207 @@
+/*
+ * mdconv_b200.h -- C ABI of libmdconv_b200.so: deformable / modulated-deformable convolution
+ * forward + backward (2D and 3D) for NVIDIA B200 (sm_100a).
+ *
+ * This is the drop-in boundary for the reference's extension module MDCONV_CUDA
+ * (CHONSPQX/modulated-deform-conv).  The reference binds eight C++ functions taking at::Tensor
+ * handles through pybind11; here the same eight entry points exist with plain device pointers,
+ * sizes and a CUDA stream, so any host language can bind them (ctypes, cgo, JNI, N-API ...).
+ * The Python module `MDCONV_CUDA.py` shipped in this repo is such a binding and keeps the
+ * reference's positional signatures.
+ *
+ * Reference interface each entry replaces (paths under the reference repo):
+ *   deform_conv2d_forward_cuda              src/deformable_conv.cu:117-123
+ *   deform_conv2d_backward_cuda             src/deformable_conv.cu:327-333
+ *   modulated_deform_conv2d_forward_cuda    src/mdeformable_conv.cu:120-126
+ *   modulated_deform_conv2d_backward_cuda   src/mdeformable_conv.cu:361-366
+ *   deform_conv3d_forward_cuda              src/deformable_conv3d.cu:160-167
+ *   deform_conv3d_backward_cuda             src/deformable_conv3d.cu:434-442
+ *   modulated_deform_conv3d_forward_cuda    src/mdeformable_conv3d.cu:170-177
+ *   modulated_deform_conv3d_backward_cuda   src/mdeformable_conv3d.cu:443-451
+ *   (pybind registration: src/mdeformable_conv.cu:460-465, src/warp.cpp:1-19)
+ *
+ * Conventions
+ *   - All tensor pointers are DEVICE pointers to dense, contiguous tensors in the reference's
+ *     layouts:  input [B,C,H,W(,L)], weight [Co,C/g,kh,kw(,kl)], bias [Co] (NULL when
+ *     with_bias == 0), offset [B, dg*nd*K, Ho,Wo(,Lo)] (per deformable group, per tap: h,w(,l)),
+ *     mask [B, dg*K, Ho,Wo(,Lo)], output / grad_output [B,Co,Ho,Wo(,Lo)]; every gradient has
+ *     the shape of its primal.  K = kh*kw(*kl);  out = (in + 2*pad - (dil*(k-1)+1))/stride + 1.
+ *   - All tensors of one call share one dtype (MDCONV_F32 / F16 / BF16 / F64).
+ *   - Nothing is allocated inside: the caller passes a workspace of at least
+ *     mdconv_workspace_bytes() bytes (device memory, 256-byte aligned).
+ *   - Work is enqueued on `stream` (a cudaStream_t; NULL = default stream) of the CURRENT device
+ *     and the call returns without synchronising.
+ *   - Outputs are fully overwritten (gradients are zero-initialised by the callee).
+ *   - `in_step` is accepted for signature compatibility and ignored: no column buffer exists,
+ *     so results never depend on it (the reference chunks the batch by gcd(B, in_step),
+ *     src/config.h:43-60).
+ *   - Return value: 0 on success, otherwise an MDCONV_ERR_* code (mdconv_status_string()).
+ *     Unlike the reference (which printf()s launch errors and returns 0), launch failures are
+ *     reported.
+ */
+#ifndef MDCONV_B200_H_
+#define MDCONV_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDCONV_B200_ABI_VERSION 1
+
+enum mdconv_dtype { MDCONV_F32 = 0, MDCONV_F16 = 1, MDCONV_BF16 = 2, MDCONV_F64 = 3 };
+
+enum mdconv_status {
+  MDCONV_OK = 0,
+  MDCONV_ERR_BAD_GEOMETRY = 1,   /* nd, sizes, divisibility, empty output */
+  MDCONV_ERR_NULL_POINTER = 2,
+  MDCONV_ERR_WORKSPACE = 3,      /* workspace too small or misaligned */
+  MDCONV_ERR_DTYPE = 4,
+  MDCONV_ERR_CUDA = 5,           /* a CUDA runtime / launch error (see mdconv_last_cuda_error) */
+  MDCONV_ERR_TOO_LARGE = 6       /* a tensor exceeds 2^31-1 elements */
+};
+
+/* Gradient rule at exactly-integer sampling coordinates (the reference's two behaviours):
+ * A = modulated 2D (src/mdeformable_conv.cu:259-315), B = plain 2D and both 3D ops
+ * (src/deformable_conv.cu:254-261, src/mdeformable_conv3d.cu:340-342). */
+enum mdconv_grad_rule { MDCONV_RULE_A = 0, MDCONV_RULE_B = 1 };
+
+/* Kernel family selection (mostly for tests and benchmarks). */
+enum mdconv_path {
+  MDCONV_PATH_AUTO = 0,     /* tcgen05 path when the shape/dtype qualifies, else generic */
+  MDCONV_PATH_GENERIC = 1,  /* fused SIMT implicit-GEMM kernels, every dtype/shape */
+  MDCONV_PATH_TENSOR = 2    /* tcgen05/TMEM path; MDCONV_ERR_BAD_GEOMETRY if it does not qualify */
+};
+
+typedef struct mdconv_geom {
+  int32_t nd;                 /* 2 or 3 */
+  int32_t batch, c_in, c_out;
+  int32_t in_size[3];         /* H, W, L  (L ignored for nd == 2) */
+  int32_t kernel[3];
+  int32_t stride[3];
+  int32_t pad[3];
+  int32_t dilation[3];
+  int32_t groups;
+  int32_t deformable_groups;
+  int32_t dtype;              /* enum mdconv_dtype */
+  int32_t modulated;          /* 1: mask tensor present */
+  int32_t grad_rule;          /* enum mdconv_grad_rule */
+  int32_t with_bias;
+  int32_t path;               /* enum mdconv_path */
+} mdconv_geom_t;
+
+int mdconv_abi_version(void);
+const char* mdconv_status_string(int status);
+/* Text of the last CUDA error seen by this thread ("" if none). */
+const char* mdconv_last_cuda_error(void);
+
+/* out[0..nd) = output spatial size.  Returns MDCONV_ERR_BAD_GEOMETRY if any is < 1. */
+int mdconv_out_size(const mdconv_geom_t* g, int32_t out[3]);
+
+/* Bytes of device workspace mdconv_forward / mdconv_backward need for this geometry. */
+size_t mdconv_workspace_bytes(const mdconv_geom_t* g, int backward);
+
+/* Which path AUTO would take for this geometry: MDCONV_PATH_GENERIC or MDCONV_PATH_TENSOR. */
+int mdconv_selected_path(const mdconv_geom_t* g, int backward);
+
+/* Number of kernel launches the last forward/backward call of this thread enqueued. */
+int mdconv_last_launch_count(void);
+
+int mdconv_forward(const mdconv_geom_t* g, const void* input, const void* weight, const void* bias,
+                   const void* offset, const void* mask, void* output, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* Any of grad_bias / grad_mask may be NULL (with_bias == 0 / modulated == 0). */
+int mdconv_backward(const mdconv_geom_t* g, const void* input, const void* weight, const void* offset,
+                    const void* mask, const void* grad_output, void* grad_input, void* grad_weight,
+                    void* grad_bias, void* grad_offset, void* grad_mask, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+/* ---- The reference's eight entry points, C ABI form --------------------------------------
+ * Argument order follows the reference signatures; tensor handles become device pointers and the
+ * sizes the reference read from the tensors are passed explicitly (batch, channels, spatial
+ * sizes, channels_out).  Trailing (dtype, workspace, workspace_bytes, stream) are new. */
+
+int deform_conv2d_forward_cuda(
+    const void* input, const void* weight, const void* bias, const void* offset, void* output,
+    int batch, int channels, int height, int width, int channels_out,
+    int kernel_h, int kernel_w, int stride_h, int stride_w, int pad_h, int pad_w,
+    int dilation_h, int dilation_w, int group, int deformable_group, int in_step, int with_bias,
+    int dtype, void* workspace, size_t workspace_bytes, void* stream);
+
+int deform_conv2d_backward_cuda(
+    const void* input, const void* weight, const void* bias, const void* offset,
+    void* grad_input, void* grad_weight, void* grad_bias, void* grad_offset, const void* grad_output,
+    int batch, int channels, int height, int width, int channels_out,
+    int kernel_h, int kernel_w, int stride_h, int stride_w, int pad_h, int pad_w,
+    int dilation_h, int dilation_w, int group, int deformable_group, int in_step, int with_bias,
+    int dtype, void* workspace, size_t workspace_bytes, void* stream);
+
+int modulated_deform_conv2d_forward_cuda(
+    const void* input, const void* weight, const void* bias, const void* offset, const void* mask,
+    void* output,
+    int batch, int channels, int height, int width, int channels_out,
+    int kernel_h, int kernel_w, int stride_h, int stride_w, int pad_h, int pad_w,
+    int dilation_h, int dilation_w, int group, int deformable_group, int in_step, int with_bias,
+    int dtype, void* workspace, size_t workspace_bytes, void* stream);
+
+int modulated_deform_conv2d_backward_cuda(
+    const void* input, const void* weight, const void* bias, const void* offset, const void* mask,
+    const void* grad_output,
+    void* grad_input, void* grad_offset, void* grad_mask, void* grad_weight, void* grad_bias,
+    int batch, int channels, int height, int width, int channels_out,
+    int kernel_h, int kernel_w, int stride_h, int stride_w, int pad_h, int pad_w,
+    int dilation_h, int dilation_w, int group, int deformable_group, int in_step, int with_bias,
+    int dtype, void* workspace, size_t workspace_bytes, void* stream);
+
+int deform_conv3d_forward_cuda(
+    const void* input, const void* weight, const void* bias, const void* offset, void* output,
+    int batch, int channels, int height, int width, int length, int channels_out,
+    int kernel_h, int kernel_w, int kernel_l, int stride_h, int stride_w, int stride_l,
+    int pad_h, int pad_w, int pad_l, int dilation_h, int dilation_w, int dilation_l,
+    int group, int deformable_group, int in_step, int with_bias,
+    int dtype, void* workspace, size_t workspace_bytes, void* stream);
+
+int deform_conv3d_backward_cuda(
+    const void* input, const void* weight, const void* bias, const void* offset,
+    void* grad_input, void* grad_weight, void* grad_bias, void* grad_offset, const void* grad_output,
+    int batch, int channels, int height, int width, int length, int channels_out,
+    int kernel_h, int kernel_w, int kernel_l, int stride_h, int stride_w, int stride_l,
+    int pad_h, int pad_w, int pad_l, int dilation_h, int dilation_w, int dilation_l,
+    int group, int deformable_group, int in_step, int with_bias,
+    int dtype, void* workspace, size_t workspace_bytes, void* stream);
+
+int modulated_deform_conv3d_forward_cuda(
+    const void* input, const void* weight, const void* bias, const void* offset, const void* mask,
+    void* output,
+    int batch, int channels, int height, int width, int length, int channels_out,
+    int kernel_h, int kernel_w, int kernel_l, int stride_h, int stride_w, int stride_l,
+    int pad_h, int pad_w, int pad_l, int dilation_h, int dilation_w, int dilation_l,
+    int group, int deformable_group, int in_step, int with_bias,
+    int dtype, void* workspace, size_t workspace_bytes, void* stream);
+
+int modulated_deform_conv3d_backward_cuda(
+    const void* input, const void* weight, const void* bias, const void* offset, const void* mask,
+    void* grad_input, void* grad_weight, void* grad_bias, void* grad_offset, void* grad_mask,
+    const void* grad_output,
+    int batch, int channels, int height, int width, int length, int channels_out,
+    int kernel_h, int kernel_w, int kernel_l, int stride_h, int stride_w, int stride_l,
+    int pad_h, int pad_w, int pad_l, int dilation_h, int dilation_w, int dilation_l,
+    int group, int deformable_group, int in_step, int with_bias,
+    int dtype, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Workspace size for the legacy-named entry points (same meaning as mdconv_workspace_bytes). */
+size_t mdconv_legacy_workspace_bytes(int nd, int modulated, int backward, int batch, int channels,
+                                     int height, int width, int length, int channels_out,
+                                     int kernel_h, int kernel_w, int kernel_l,
+                                     int stride_h, int stride_w, int stride_l,
+                                     int pad_h, int pad_w, int pad_l,
+                                     int dilation_h, int dilation_w, int dilation_l,
+                                     int group, int deformable_group, int with_bias, int dtype);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDCONV_B200_H_ */

@@ -1,0 +1,324 @@
+"""MDCONV_CUDA -- drop-in for the reference's pybind11 extension module of the same name.
+
+The reference builds ``MDCONV_CUDA`` from src/*.cu with torch's CUDAExtension (setup.py:36-40) and
+registers ``*_forward_cuda`` / ``*_backward_cuda`` (src/mdeformable_conv.cu:460-465; the other six
+registrations are commented out in src/warp.cpp:1-19 on HEAD).  This module exposes all eight names
+with the reference's positional signatures, but is a thin ctypes binding over the C ABI of
+``lib/libmdconv_b200.so`` (include/mdconv_b200.h): torch supplies device memory and the current
+stream, every kernel is this repo's sm_100a code.
+
+There is NO fallback: if the shared library is missing the import fails, and CPU tensors are
+rejected -- the product path never computes on the host.
+
+Error behaviour mirrors the reference: non-contiguous tensors and kernel/channel mismatches raise
+RuntimeError (TORCH_CHECK / AT_ERROR in src/mdeformable_conv.cu:127-148); additionally dtype/device
+mismatches and CUDA launch failures raise RuntimeError instead of being printed and ignored
+(src/mdeformable_conv.cu:113-117).
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.environ.get("MDCONV_B200_LIB", os.path.join(_HERE, "lib", "libmdconv_b200.so"))
+if not os.path.exists(_LIB_PATH):
+    raise ImportError(
+        f"MDCONV_CUDA: {_LIB_PATH} not found -- build it with `python __graft_entry__.py build` "
+        "(or `make -C modulated-deform-conv_b200/csrc`).  There is no CPU/eager fallback.")
+_lib = ctypes.CDLL(_LIB_PATH)
+
+_vp, _i, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
+
+
+class _Geom(ctypes.Structure):
+    """struct mdconv_geom (include/mdconv_b200.h)."""
+    _fields_ = [("nd", ctypes.c_int32), ("batch", ctypes.c_int32), ("c_in", ctypes.c_int32),
+                ("c_out", ctypes.c_int32), ("in_size", ctypes.c_int32 * 3), ("kernel", ctypes.c_int32 * 3),
+                ("stride", ctypes.c_int32 * 3), ("pad", ctypes.c_int32 * 3), ("dilation", ctypes.c_int32 * 3),
+                ("groups", ctypes.c_int32), ("deformable_groups", ctypes.c_int32), ("dtype", ctypes.c_int32),
+                ("modulated", ctypes.c_int32), ("grad_rule", ctypes.c_int32), ("with_bias", ctypes.c_int32),
+                ("path", ctypes.c_int32)]
+
+
+_lib.mdconv_abi_version.restype = _i
+_lib.mdconv_status_string.restype = ctypes.c_char_p
+_lib.mdconv_status_string.argtypes = [_i]
+_lib.mdconv_last_cuda_error.restype = ctypes.c_char_p
+_lib.mdconv_last_launch_count.restype = _i
+_lib.mdconv_workspace_bytes.restype = _sz
+_lib.mdconv_workspace_bytes.argtypes = [ctypes.POINTER(_Geom), _i]
+_lib.mdconv_selected_path.restype = _i
+_lib.mdconv_selected_path.argtypes = [ctypes.POINTER(_Geom), _i]
+_lib.mdconv_out_size.restype = _i
+_lib.mdconv_out_size.argtypes = [ctypes.POINTER(_Geom), ctypes.POINTER(ctypes.c_int32)]
+_lib.mdconv_forward.restype = _i
+_lib.mdconv_forward.argtypes = [ctypes.POINTER(_Geom)] + [_vp] * 7 + [_sz, _vp]
+_lib.mdconv_backward.restype = _i
+_lib.mdconv_backward.argtypes = [ctypes.POINTER(_Geom)] + [_vp] * 11 + [_sz, _vp]
+
+_TAIL = [_i, _vp, _sz, _vp]  # dtype, workspace, workspace_bytes, stream
+_G2 = [_i] * 17              # batch, channels, H, W, Cout, kh,kw, sh,sw, ph,pw, dh,dw, g, dg, in_step, with_bias
+_G3 = [_i] * 22              # batch, channels, H, W, L, Cout, 12 geometry ints, g, dg, in_step, with_bias
+for _name, _nptr, _geo in (("deform_conv2d_forward_cuda", 5, _G2), ("deform_conv2d_backward_cuda", 9, _G2),
+                           ("modulated_deform_conv2d_forward_cuda", 6, _G2),
+                           ("modulated_deform_conv2d_backward_cuda", 11, _G2),
+                           ("deform_conv3d_forward_cuda", 5, _G3), ("deform_conv3d_backward_cuda", 9, _G3),
+                           ("modulated_deform_conv3d_forward_cuda", 6, _G3),
+                           ("modulated_deform_conv3d_backward_cuda", 11, _G3)):
+    _f = getattr(_lib, _name)
+    _f.restype = _i
+    _f.argtypes = [_vp] * _nptr + _geo + _TAIL
+_lib.mdconv_legacy_workspace_bytes.restype = _sz
+_lib.mdconv_legacy_workspace_bytes.argtypes = [_i] * 25
+
+if _lib.mdconv_abi_version() != 1:
+    raise ImportError("MDCONV_CUDA: libmdconv_b200.so ABI version mismatch")
+
+_DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2, torch.float64: 3}
+
+# Kernel-family override for tests / benchmarks: 0 auto, 1 generic SIMT, 2 tcgen05 (error if n/a).
+_path_override = int(os.environ.get("MDCONV_B200_PATH", "0"))
+
+
+def set_path(path: int) -> None:
+    """0 = auto (default), 1 = force the generic SIMT kernels, 2 = force the tcgen05 path."""
+    global _path_override
+    _path_override = int(path)
+
+
+def last_launch_count() -> int:
+    """Kernel launches enqueued by the most recent forward/backward call on this thread."""
+    return int(_lib.mdconv_last_launch_count())
+
+
+def library_path() -> str:
+    return _LIB_PATH
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = _lib.mdconv_status_string(rc).decode()
+        if rc == 5:
+            msg += ": " + _lib.mdconv_last_cuda_error().decode()
+        raise RuntimeError(f"{what}: {msg}")
+
+
+def _ptr(t):
+    return None if t is None or t.numel() == 0 else ctypes.c_void_p(t.data_ptr())
+
+
+def _validate(named, weight, kernel, group, nd):
+    """The reference's entry checks (src/mdeformable_conv.cu:127-148 and twins)."""
+    first = named[0][1]
+    for name, t in named:
+        if not t.is_contiguous():
+            raise RuntimeError(f"{name} tensor has to be contiguous")
+        if not t.is_cuda:
+            raise RuntimeError(f"{name} tensor has to be a CUDA tensor (no CPU path)")
+        if t.numel() and (t.dtype != first.dtype or t.device != first.device):
+            raise RuntimeError(f"{name} tensor dtype/device differs from input ({t.dtype}, {t.device})")
+    if first.dtype not in _DTYPES:
+        raise RuntimeError(f"unsupported dtype {first.dtype}")
+    if first.dim() != nd + 2 or weight.dim() != nd + 2:
+        raise RuntimeError(f"expected {nd + 2}-d input and weight")
+    if tuple(weight.shape[2:]) != tuple(kernel):
+        raise RuntimeError("Input shape and kernel shape wont match: ({} vs {}).".format(
+            " x ".join(map(str, kernel)), " x ".join(map(str, weight.shape[2:]))))
+    if first.shape[1] != weight.shape[1] * group:
+        raise RuntimeError("Input shape and kernel channels wont match: ({} vs {}).".format(
+            first.shape[1], weight.shape[1] * group))
+
+
+def _geom(input, weight, kernel, stride, pad, dil, group, dgroup, modulated, with_bias):
+    nd = input.dim() - 2
+    g = _Geom()
+    g.nd, g.batch, g.c_in, g.c_out = nd, input.shape[0], input.shape[1], weight.shape[0]
+    for a in range(3):
+        g.in_size[a] = input.shape[2 + a] if a < nd else 1
+        g.kernel[a] = kernel[a] if a < nd else 1
+        g.stride[a] = stride[a] if a < nd else 1
+        g.pad[a] = pad[a] if a < nd else 0
+        g.dilation[a] = dil[a] if a < nd else 1
+    g.groups, g.deformable_groups = group, dgroup
+    g.dtype = _DTYPES[input.dtype]
+    g.modulated = 1 if modulated else 0
+    g.grad_rule = 0 if (nd == 2 and modulated) else 1
+    g.with_bias = 1 if with_bias else 0
+    g.path = _path_override
+    return g
+
+
+def _out_shape(g, input, weight):
+    out = (ctypes.c_int32 * 3)()
+    _check(_lib.mdconv_out_size(ctypes.byref(g), out), "output size")
+    return (input.shape[0], weight.shape[0]) + tuple(out[a] for a in range(g.nd))
+
+
+def _expect(t, shape, name):
+    if tuple(t.shape) != tuple(shape):
+        raise RuntimeError(f"{name} has shape {tuple(t.shape)}, expected {tuple(shape)}")
+
+
+def _workspace(g, backward, device):
+    n = int(_lib.mdconv_workspace_bytes(ctypes.byref(g), 1 if backward else 0))
+    if n == 0:
+        return None, 0
+    return torch.empty(n, dtype=torch.uint8, device=device), n
+
+
+def _forward(input, weight, bias, offset, mask, output, kernel, stride, pad, dil, group, dgroup, with_bias):
+    nd = len(kernel)
+    modulated = mask is not None
+    named = [("input", input), ("weight", weight), ("bias", bias), ("offset", offset)]
+    if modulated:
+        named.append(("mask", mask))
+    if output is not None:
+        named.append(("output", output))
+    _validate(named, weight, kernel, group, nd)
+    g = _geom(input, weight, kernel, stride, pad, dil, group, dgroup, modulated, with_bias)
+    shape = _out_shape(g, input, weight)
+    K = 1
+    for k in kernel:
+        K *= k
+    _expect(offset, (input.shape[0], dgroup * nd * K) + shape[2:], "offset")
+    if modulated:
+        _expect(mask, (input.shape[0], dgroup * K) + shape[2:], "mask")
+    if with_bias:
+        _expect(bias, (weight.shape[0],), "bias")
+    with torch.cuda.device(input.device):
+        if output is None:
+            output = torch.empty(shape, dtype=input.dtype, device=input.device)
+        else:
+            _expect(output, shape, "output")
+        ws, n = _workspace(g, False, input.device)
+        stream = torch.cuda.current_stream().cuda_stream
+        rc = _lib.mdconv_forward(ctypes.byref(g), _ptr(input), _ptr(weight), _ptr(bias) if with_bias else None,
+                                 _ptr(offset), _ptr(mask), _ptr(output), _ptr(ws), n, ctypes.c_void_p(stream))
+    _check(rc, "mdconv_forward")
+    return output
+
+
+def _backward(input, weight, bias, offset, mask, grad_output, grads, kernel, stride, pad, dil, group, dgroup,
+              with_bias):
+    """grads: None (allocate and return) or dict of caller-owned tensors (out-param style)."""
+    nd = len(kernel)
+    modulated = mask is not None
+    named = [("input", input), ("weight", weight), ("bias", bias), ("offset", offset)]
+    if modulated:
+        named.append(("mask", mask))
+    named.append(("grad_output", grad_output))
+    if grads is not None:
+        named += [(k, v) for k, v in grads.items() if v is not None]
+    _validate(named, weight, kernel, group, nd)
+    g = _geom(input, weight, kernel, stride, pad, dil, group, dgroup, modulated, with_bias)
+    _expect(grad_output, _out_shape(g, input, weight), "grad_output")
+    with torch.cuda.device(input.device):
+        if grads is None:
+            grads = {"grad_input": torch.empty_like(input), "grad_offset": torch.empty_like(offset),
+                     "grad_mask": torch.empty_like(mask) if modulated else None,
+                     "grad_weight": torch.empty_like(weight),
+                     "grad_bias": torch.empty_like(bias) if with_bias else torch.zeros_like(bias)}
+        else:
+            _expect(grads["grad_input"], input.shape, "grad_input")
+            _expect(grads["grad_offset"], offset.shape, "grad_offset")
+            _expect(grads["grad_weight"], weight.shape, "grad_weight")
+            if modulated:
+                _expect(grads["grad_mask"], mask.shape, "grad_mask")
+        ws, n = _workspace(g, True, input.device)
+        stream = torch.cuda.current_stream().cuda_stream
+        rc = _lib.mdconv_backward(ctypes.byref(g), _ptr(input), _ptr(weight), _ptr(offset), _ptr(mask),
+                                  _ptr(grad_output), _ptr(grads["grad_input"]), _ptr(grads["grad_weight"]),
+                                  _ptr(grads["grad_bias"]) if with_bias else None, _ptr(grads["grad_offset"]),
+                                  _ptr(grads.get("grad_mask")) if modulated else None, _ptr(ws), n,
+                                  ctypes.c_void_p(stream))
+    _check(rc, "mdconv_backward")
+    return grads
+
+
+# ---- the eight reference entry points ------------------------------------------------------------
+
+def deform_conv2d_forward_cuda(input, weight, bias, offset, output, kernel_h, kernel_w, stride_h, stride_w,
+                               pad_h, pad_w, dilation_h, dilation_w, group, deformable_group, in_step, with_bias):
+    """reference: src/deformable_conv.cu:117-196 (out-param, returns 0).  Unlike the reference for
+    gcd(batch, in_step) > 1 (SURVEY B-1), the caller's ``output`` always receives the correct result."""
+    _forward(input, weight, bias, offset, None, output, (kernel_h, kernel_w), (stride_h, stride_w),
+             (pad_h, pad_w), (dilation_h, dilation_w), group, deformable_group, with_bias)
+    return 0
+
+
+def deform_conv2d_backward_cuda(input, weight, bias, offset, grad_input, grad_weight, grad_bias, grad_offset,
+                                grad_output, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h,
+                                dilation_w, group, deformable_group, in_step, with_bias):
+    """reference: src/deformable_conv.cu:327-431."""
+    _backward(input, weight, bias, offset, None, grad_output,
+              {"grad_input": grad_input, "grad_weight": grad_weight, "grad_bias": grad_bias,
+               "grad_offset": grad_offset},
+              (kernel_h, kernel_w), (stride_h, stride_w), (pad_h, pad_w), (dilation_h, dilation_w), group,
+              deformable_group, with_bias)
+    return 0
+
+
+def modulated_deform_conv2d_forward_cuda(input, weight, bias, offset, mask, kernel_h, kernel_w, stride_h,
+                                         stride_w, pad_h, pad_w, dilation_h, dilation_w, group, deformable_group,
+                                         in_step, with_bias):
+    """reference: src/mdeformable_conv.cu:120-194 (returns the output tensor)."""
+    return _forward(input, weight, bias, offset, mask, None, (kernel_h, kernel_w), (stride_h, stride_w),
+                    (pad_h, pad_w), (dilation_h, dilation_w), group, deformable_group, with_bias)
+
+
+def modulated_deform_conv2d_backward_cuda(input, weight, bias, offset, mask, grad_output, kernel_h, kernel_w,
+                                          stride_h, stride_w, pad_h, pad_w, dilation_h, dilation_w, group,
+                                          deformable_group, in_step, with_bias):
+    """reference: src/mdeformable_conv.cu:361-458 (returns the 5-tuple
+    grad_input, grad_offset, grad_mask, grad_weight, grad_bias)."""
+    g = _backward(input, weight, bias, offset, mask, grad_output, None, (kernel_h, kernel_w),
+                  (stride_h, stride_w), (pad_h, pad_w), (dilation_h, dilation_w), group, deformable_group,
+                  with_bias)
+    return g["grad_input"], g["grad_offset"], g["grad_mask"], g["grad_weight"], g["grad_bias"]
+
+
+def deform_conv3d_forward_cuda(input, weight, bias, offset, output, kernel_h, kernel_w, kernel_l, stride_h,
+                               stride_w, stride_l, pad_h, pad_w, pad_l, dilation_h, dilation_w, dilation_l,
+                               group, deformable_group, in_step, with_bias):
+    """reference: src/deformable_conv3d.cu:160-256."""
+    _forward(input, weight, bias, offset, None, output, (kernel_h, kernel_w, kernel_l),
+             (stride_h, stride_w, stride_l), (pad_h, pad_w, pad_l), (dilation_h, dilation_w, dilation_l), group,
+             deformable_group, with_bias)
+    return 0
+
+
+def deform_conv3d_backward_cuda(input, weight, bias, offset, grad_input, grad_weight, grad_bias, grad_offset,
+                                grad_output, kernel_h, kernel_w, kernel_l, stride_h, stride_w, stride_l, pad_h,
+                                pad_w, pad_l, dilation_h, dilation_w, dilation_l, group, deformable_group,
+                                in_step, with_bias):
+    """reference: src/deformable_conv3d.cu:434-561."""
+    _backward(input, weight, bias, offset, None, grad_output,
+              {"grad_input": grad_input, "grad_weight": grad_weight, "grad_bias": grad_bias,
+               "grad_offset": grad_offset},
+              (kernel_h, kernel_w, kernel_l), (stride_h, stride_w, stride_l), (pad_h, pad_w, pad_l),
+              (dilation_h, dilation_w, dilation_l), group, deformable_group, with_bias)
+    return 0
+
+
+def modulated_deform_conv3d_forward_cuda(input, weight, bias, offset, mask, output, kernel_h, kernel_w, kernel_l,
+                                         stride_h, stride_w, stride_l, pad_h, pad_w, pad_l, dilation_h,
+                                         dilation_w, dilation_l, group, deformable_group, in_step, with_bias):
+    """reference: src/mdeformable_conv3d.cu:170-262."""
+    _forward(input, weight, bias, offset, mask, output, (kernel_h, kernel_w, kernel_l),
+             (stride_h, stride_w, stride_l), (pad_h, pad_w, pad_l), (dilation_h, dilation_w, dilation_l), group,
+             deformable_group, with_bias)
+    return 0
+
+
+def modulated_deform_conv3d_backward_cuda(input, weight, bias, offset, mask, grad_input, grad_weight, grad_bias,
+                                          grad_offset, grad_mask, grad_output, kernel_h, kernel_w, kernel_l,
+                                          stride_h, stride_w, stride_l, pad_h, pad_w, pad_l, dilation_h,
+                                          dilation_w, dilation_l, group, deformable_group, in_step, with_bias):
+    """reference: src/mdeformable_conv3d.cu:443-586."""
+    _backward(input, weight, bias, offset, mask, grad_output,
+              {"grad_input": grad_input, "grad_weight": grad_weight, "grad_bias": grad_bias,
+               "grad_offset": grad_offset, "grad_mask": grad_mask},
+              (kernel_h, kernel_w, kernel_l), (stride_h, stride_w, stride_l), (pad_h, pad_w, pad_l),
+              (dilation_h, dilation_w, dilation_l), group, deformable_group, with_bias)
+    return 0
