@@ -1,0 +1,437 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the deformable-conv hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg4]
+
+A step = one forward + backward of ModulatedDeformConv2d over one batch of synthetic input
+(cfg2: N=32 per GPU, C=256->256, 56x56, k3 s1 p1 dg1, fp16 -- the configuration the metric is quoted
+on).  N>1 is launched by torchrun, one rank per GPU: the batch is sharded per rank (weak scaling,
+32 samples per GPU) and the only exchange is ONE NCCL all-reduce of [grad_weight || grad_bias].
+Rank 0 prints ONE JSON line.
+
+`--impl reference`: the reference publishes no CPU implementation, so this arm times the CPU
+restatement of its algorithm (oracle/, C + OpenMP, all host threads) on a bounded sample of the
+same workload (one sample per step).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (os.path.join(ROOT, "modulated-deform-conv_b200"), ROOT):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+METRIC = "ModulatedDeformConv2d fwd+bwd Msamples/s"
+
+WORKLOADS = {
+    # name: (nd, modulated, per-GPU batch, C, Co, size, k, s, p, d, g, dg, dtype)
+    "cfg2": dict(nd=2, modulated=True, B=32, C=256, Co=256, size=(56, 56), k=(3, 3), s=(1, 1), p=(1, 1), d=(1, 1),
+                 g=1, dg=1, dtype="f16",
+                 desc="cfg2: ModulatedDeformConv2d N=32/GPU C=256->256 56x56 k3 s1 p1 dg=1 fp16"),
+    "cfg3": dict(nd=2, modulated=False, B=16, C=512, Co=512, size=(28, 28), k=(3, 3), s=(2, 2), p=(1, 1), d=(1, 1),
+                 g=4, dg=4, dtype="f32", desc="cfg3: DeformConv2d N=16 C=512->512 28x28 k3 s2 p1 dg=4 g=4 fp32"),
+    "cfg4": dict(nd=3, modulated=True, B=8, C=64, Co=128, size=(16, 32, 32), k=(3, 3, 3), s=(1, 1, 1), p=(1, 1, 1),
+                 d=(1, 1, 1), g=1, dg=1, dtype="f16",
+                 desc="cfg4: ModulatedDeformConv3d N=8 C=64->128 16x32x32 k3 s1 p1 fp16"),
+}
+DTYPES = {"f16": torch.float16, "f32": torch.float32, "bf16": torch.bfloat16, "f64": torch.float64}
+
+
+def out_size(w):
+    return tuple((i + 2 * p - (d * (k - 1) + 1)) // s + 1 for i, k, s, p, d in zip(w["size"], w["k"], w["s"], w["p"], w["d"]))
+
+
+def make_host_inputs(w, batch, seed, dtype, pin):
+    """Synthetic inputs per SURVEY 8(d): x~N(0,1), offset~N(0,1) px, mask=sigmoid(N(0,1)), grad_out~N(0,1)."""
+    gen = torch.Generator().manual_seed(seed)
+    K = 1
+    for k in w["k"]:
+        K *= k
+    o = out_size(w)
+    x = torch.randn(batch, w["C"], *w["size"], generator=gen)
+    off = torch.randn(batch, w["dg"] * w["nd"] * K, *o, generator=gen)
+    msk = torch.sigmoid(torch.randn(batch, w["dg"] * K, *o, generator=gen)) if w["modulated"] else None
+    go = torch.randn(batch, w["Co"], *o, generator=gen)
+    t = {"x": x, "offset": off, "mask": msk, "grad_output": go}
+    t = {k: (None if v is None else v.to(dtype).contiguous()) for k, v in t.items()}
+    if pin:
+        t = {k: (None if v is None else v.pin_memory()) for k, v in t.items()}
+    return t
+
+
+def algorithmic(w, batch, es):
+    """Compulsory HBM bytes and dense-contraction FLOPs of one fwd / bwd."""
+    K = 1
+    for k in w["k"]:
+        K *= k
+    P = 1
+    for o in out_size(w):
+        P *= o
+    IN = 1
+    for i in w["size"]:
+        IN *= i
+    nx = batch * w["C"] * IN
+    noff = batch * w["dg"] * w["nd"] * K * P
+    nm = batch * w["dg"] * K * P if w["modulated"] else 0
+    nw = w["Co"] * (w["C"] // w["g"]) * K
+    ny = batch * w["Co"] * P
+    bytes_fwd = es * (nx + noff + nm + nw + ny)
+    bytes_bwd = es * (2 * nx + 2 * noff + 2 * nm + 2 * nw + ny)
+    flops_fwd = 2.0 * batch * P * w["Co"] * (w["C"] // w["g"]) * K
+    return bytes_fwd, bytes_bwd, flops_fwd, 2.0 * flops_fwd
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed regions run."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake": 0x80, "sync_boost": 0x10, "applications_clocks_setting": 0x2}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for n, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def start(self):
+        if self.nv is not None:
+            self._stop.clear()
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        if self._thr is not None:
+            self._stop.set()
+            self._thr.join()
+            self._thr = None
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "tflops": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "tflops_burst": p["bf16_tflops"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "tflops_burst": 1590.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_oracle_rate(w, threads, reps, warmup):
+    """fwd+bwd of the CPU oracle (fp32 build, OpenMP) on ONE sample of the workload -> (Msamples/s, s/step)."""
+    import oracle
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    t = make_host_inputs(w, 1, 1234, torch.float32, pin=False)
+    gen = torch.Generator().manual_seed(5)
+    K = 1
+    for k in w["k"]:
+        K *= k
+    wt = (torch.rand(w["Co"], w["C"] // w["g"], *w["k"], generator=gen) * 2 - 1) / (w["C"] * K) ** 0.5
+    a = (w["s"], w["p"], w["d"], w["g"], w["dg"])
+
+    def step():
+        oracle.forward(t["x"], wt, None, t["offset"], t["mask"], *a, precision="f32")
+        oracle.backward(t["x"], wt, t["offset"], t["mask"], t["grad_output"], *a, precision="f32", with_bias=False)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        step()
+    dt = (time.perf_counter() - t0) / reps
+    return 1.0 / dt / 1e6, dt
+
+
+def run_reference_arm(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # rank 0 alone runs the CPU arm
+    threads = os.cpu_count() or 1
+    steps = max(1, args.steps)
+    warm = max(1, min(args.warmup, 2))
+    val, dt = cpu_oracle_rate(w, threads, steps, warm)
+    sample = "1 sample per step of the workload shape (fwd+bwd, fp32 arithmetic, OpenMP)"
+    line = {"metric": METRIC, "value": val, "unit": "Msamples/s", "impl": "reference", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["desc"], "note": "reference ships no CPU path; CPU restatement (oracle/) timed"},
+            "cpu_baseline": {"value": val, "unit": "Msamples/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--path", type=int, default=0, help="0 auto, 1 generic SIMT, 2 tcgen05")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+
+    if args.impl == "reference":
+        run_reference_arm(args, w)
+        return
+
+    import torch.distributed as dist
+    import MDCONV_CUDA
+    import modulated_deform_conv as mdc
+    import mdconv_dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    MDCONV_CUDA.set_path(args.path)
+    W = max(3, args.warmup)
+    K_steps = max(1, args.steps)
+    dtype = DTYPES[w["dtype"]]
+    es = torch.tensor([], dtype=dtype).element_size()
+    B = w["B"]
+
+    cls = {(2, True): mdc.ModulatedDeformConv2d, (2, False): mdc.DeformConv2d,
+           (3, True): mdc.ModulatedDeformConv3d, (3, False): mdc.DeformConv3d}[(w["nd"], w["modulated"])]
+    torch.manual_seed(0)
+    mod = cls(w["C"], w["Co"], w["k"], stride=w["s"], padding=w["p"], dilation=w["d"], groups=w["g"],
+              deformable_groups=w["dg"], bias=False).to(dev).to(dtype)
+    params = [p for p in mod.parameters()]
+    bucket = mdconv_dist.GradBucket(params) if world > 1 else None
+
+    host = make_host_inputs(w, B, 100 + rank, dtype, pin=True)
+    d = {k: (None if v is None else v.to(dev)) for k, v in host.items()}
+    leaves = {k: d[k].clone().requires_grad_() for k in ("x", "offset") + (("mask",) if w["modulated"] else ())}
+
+    launches = [0]
+
+    def fwd_bwd(x, off, msk, go):
+        args_ = (x, off, msk) if w["modulated"] else (x, off)
+        y = mod(*args_)
+        launches[0] += MDCONV_CUDA.last_launch_count()
+        y.backward(go)
+        launches[0] += MDCONV_CUDA.last_launch_count()
+        if bucket is not None:
+            bucket.pack()
+            bucket.all_reduce()
+            bucket.unpack()
+        return y
+
+    def step_resident():
+        for t in leaves.values():
+            t.grad = None
+        mod.weight.grad = None
+        return fwd_bwd(leaves["x"], leaves["offset"], leaves.get("mask"), d["grad_output"])
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up ----
+    for _ in range(W):
+        step_resident()
+    sync_all()
+
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+
+    # ---- timed region 1: inputs resident in HBM ("value") ----
+    launches[0] = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for _ in range(K_steps):
+        step_resident()
+    e1.record()
+    sync_all()
+    ms_total = e0.elapsed_time(e1)
+    n_launch = launches[0]
+    if world > 1:
+        tmax = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms_total = float(tmax.item())
+    ms_per_step = ms_total / K_steps
+    value = (B * world) / (ms_per_step * 1e-3) / 1e6
+
+    # ---- timed region 2: end to end through the public Module API with HOST buffers ("e2e") ----
+    keys = [k for k in ("x", "offset", "mask", "grad_output") if host[k] is not None]
+    h2d = sum(host[k].numel() * es for k in keys)
+    out_host = None
+
+    def step_e2e():
+        nonlocal out_host
+        dd = {k: host[k].to(dev, non_blocking=True) for k in keys}
+        lv = {k: dd[k].requires_grad_() for k in keys if k != "grad_output"}
+        mod.weight.grad = None
+        y = fwd_bwd(lv["x"], lv["offset"], lv.get("mask"), dd["grad_output"])
+        res = [y.detach(), lv["x"].grad, lv["offset"].grad, mod.weight.grad] + ([lv["mask"].grad] if "mask" in lv else [])
+        if out_host is None:
+            out_host = [torch.empty(r.shape, dtype=r.dtype).pin_memory() for r in res]
+        for hbuf, r in zip(out_host, res):
+            hbuf.copy_(r, non_blocking=True)
+        return sum(r.numel() * r.element_size() for r in res)
+
+    d2h = 0
+    for _ in range(3):
+        d2h = step_e2e()
+    sync_all()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ke = max(3, min(K_steps, 10))
+    e2.record()
+    for _ in range(ke):
+        step_e2e()
+    e3.record()
+    sync_all()
+    ms_e2e = e2.elapsed_time(e3)
+    if world > 1:
+        tmax = torch.tensor([ms_e2e], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms_e2e = float(tmax.item())
+    e2e_value = (B * world) / (ms_e2e / ke * 1e-3) / 1e6
+    clocks.stop()
+
+    # ---- per-kernel durations (CUDA events on the launching stream, inside the library) ----
+    MDCONV_CUDA.profile_enable(True)
+    kt = {}
+    nprof = max(3, min(K_steps, 10))
+    for _ in range(nprof):
+        step_resident()
+    for name, ms in MDCONV_CUDA.profile_read():
+        kt.setdefault(name, []).append(ms)
+    MDCONV_CUDA.profile_enable(False)
+    kernels = {k: sum(v) / nprof for k, v in kt.items()}  # ms per step, summed over launches of that kernel
+    calls = {k: len(v) // nprof for k, v in kt.items()}
+
+    peaks = load_peaks()
+    bytes_fwd, bytes_bwd, flops_fwd, flops_bwd = algorithmic(w, B, es)
+    # dominant kernel and the algorithmic work of ONE launch of it
+    flop_share = {"fwd": flops_fwd, "bwd_data": flops_fwd, "bwd_weight": flops_fwd}
+    dom = max(kernels, key=kernels.get) if kernels else None
+    roofline = None
+    if dom is not None:
+        which = "bwd_data" if "bwd_data" in dom or "gcol" in dom else "bwd_weight" if "weight" in dom else "fwd"
+        dur = kernels[dom] / max(1, calls[dom]) * 1e-3
+        ach = flop_share[which] / max(1, calls[dom]) / dur / 1e12
+        roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                    "frac": ach / peaks["tflops"], "traffic": None, "launch_ms": dur * 1e3,
+                    "peak_source": peaks["source"] + ", sustained bf16 cuBLAS",
+                    "share_of_step": kernels[dom] / max(1e-9, sum(kernels.values()))}
+    hbm_ach = (bytes_fwd + bytes_bwd) / (ms_per_step * 1e-3) / 1e9
+    roofline_hbm = {"scope": "whole fwd+bwd step, algorithmic bytes", "achieved": hbm_ach, "peak": peaks["hbm_gbs"],
+                    "unit": "GB/s", "frac": hbm_ach / peaks["hbm_gbs"], "frac_of_8TBs_spec": hbm_ach / 8000.0,
+                    "algorithmic_bytes_fwd": bytes_fwd, "algorithmic_bytes_bwd": bytes_bwd}
+
+    line = None
+    if rank == 0:
+        cpu_base = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                threads = os.cpu_count() or 1
+                v, dt = cpu_oracle_rate(w, threads, 2, 1)
+                cpu_base = {"value": v, "unit": "Msamples/s", "cores": threads, "kind": "port",
+                            "sample": f"1 sample of the workload shape, fwd+bwd, 2 reps ({dt:.2f} s each), fp32 C+OpenMP oracle"}
+            except Exception as e:  # the baseline is informative; never fail the bench for it
+                cpu_base = {"value": None, "unit": "Msamples/s", "cores": os.cpu_count(), "kind": "port",
+                            "sample": f"failed: {e}"}
+        ref_cuda = None
+        if world == 1 and not args.no_ref_cuda:
+            ref_cuda = time_reference_cuda(w, d, mod, B)
+        line = {"metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": K_steps, "warmup": W,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": w["dtype"], "data": "synthetic",
+                "config": {"workload": w["desc"], "global_batch": B * world, "parallelism": f"batch-shard x{world}",
+                           "l2": "working set (277 MB at cfg2) exceeds the 126 MB L2; no explicit flush",
+                           "path": {0: "auto", 1: "generic", 2: "tensor"}[args.path],
+                           "collective": "1 NCCL all-reduce(sum) of [grad_weight||grad_bias] per step" if world > 1 else "none"},
+                "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e / ke},
+                "gpu_launches": n_launch, "clocks": clocks.summary(), "roofline": roofline, "roofline_hbm": roofline_hbm,
+                "kernels_ms_per_step": kernels, "cpu_baseline": cpu_base, "reference_cuda": ref_cuda}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def time_reference_cuda(w, d, mod, B):
+    """The UNMODIFIED reference kernels (oracle/_ref) on the same GPU and tensors: reported beside our
+    number, never part of it."""
+    try:
+        from oracle import ref_runner
+        if not ref_runner.available():
+            return {"unavailable": "oracle/_ref not built"}
+        a = (w["s"], w["p"], w["d"], w["g"], w["dg"])
+        wt = mod.weight.detach()
+
+        def step():
+            y = ref_runner.forward(d["x"], wt, None, d["offset"], d["mask"], *a, in_step=64)
+            g = ref_runner.backward(d["x"], wt, None, d["offset"], d["mask"], d["grad_output"], *a, in_step=64)
+            return y, g
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        ef, eb, ee = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        n = 5
+        tf = tb = 0.0
+        for _ in range(n):
+            ef.record()
+            ref_runner.forward(d["x"], wt, None, d["offset"], d["mask"], *a, in_step=64)
+            eb.record()
+            ref_runner.backward(d["x"], wt, None, d["offset"], d["mask"], d["grad_output"], *a, in_step=64)
+            ee.record()
+            torch.cuda.synchronize()
+            tf += ef.elapsed_time(eb)
+            tb += eb.elapsed_time(ee)
+        tf, tb = tf / n, tb / n
+        return {"value": B / ((tf + tb) * 1e-3) / 1e6, "unit": "Msamples/s", "fwd_ms": tf, "bwd_ms": tb,
+                "in_step": 64, "note": "unmodified reference kernels + cuBLAS, same GPU, same tensors"}
+    except Exception as e:
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+
+
+if __name__ == "__main__":
+    main()

@@ -109,6 +109,13 @@ int mdconv_selected_path(const mdconv_geom_t* g, int backward);
 /* Number of kernel launches the last forward/backward call of this thread enqueued. */
 int mdconv_last_launch_count(void);
 
+/* Per-kernel timing for benchmarks: while enabled, every kernel this library launches is bracketed
+ * by CUDA events on the launching stream.  mdconv_profile_read() waits for them, writes one
+ * "kernel_name=milliseconds\n" line per launch (launch order) into buf, clears the list and returns
+ * the number of entries.  Thread-local; off by default. */
+int mdconv_profile_enable(int on);
+int mdconv_profile_read(char* buf, size_t cap);
+
 int mdconv_forward(const mdconv_geom_t* g, const void* input, const void* weight, const void* bias,
                    const void* offset, const void* mask, void* output, void* workspace,
                    size_t workspace_bytes, void* stream);

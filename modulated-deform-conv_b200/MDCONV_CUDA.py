@@ -96,6 +96,28 @@ def library_path() -> str:
     return _LIB_PATH
 
 
+_lib.mdconv_profile_enable.restype = _i
+_lib.mdconv_profile_enable.argtypes = [_i]
+_lib.mdconv_profile_read.restype = _i
+_lib.mdconv_profile_read.argtypes = [ctypes.c_char_p, _sz]
+
+
+def profile_enable(on: bool) -> None:
+    """Bracket every kernel this library launches with CUDA events (benchmark use)."""
+    _lib.mdconv_profile_enable(1 if on else 0)
+
+
+def profile_read():
+    """-> list of (kernel_name, milliseconds) in launch order since the last read (synchronises)."""
+    buf = ctypes.create_string_buffer(1 << 16)
+    _lib.mdconv_profile_read(buf, len(buf))
+    out = []
+    for line in buf.value.decode().splitlines():
+        name, _, ms = line.partition("=")
+        out.append((name, float(ms)))
+    return out
+
+
 def _check(rc: int, what: str) -> None:
     if rc != 0:
         msg = _lib.mdconv_status_string(rc).decode()

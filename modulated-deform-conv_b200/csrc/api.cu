@@ -3,6 +3,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <string>
+#include <vector>
+
 #include "common.cuh"
 #include "tensor_path.cuh"
 
@@ -12,6 +15,13 @@ namespace {
 
 thread_local char g_cuda_err[256] = "";
 thread_local int g_last_launches = 0;
+
+struct ProfEntry {
+  const char* name;
+  cudaEvent_t a, b;
+};
+thread_local bool g_prof_on = false;
+thread_local std::vector<ProfEntry>* g_prof = nullptr;
 
 int resolve(const mdconv_geom_t* in, DevGeom& g) {
   if (in == nullptr) return MDCONV_ERR_NULL_POINTER;
@@ -70,7 +80,52 @@ int finish(LaunchCtx& ctx) {
 
 }  // namespace
 
+namespace mdconv {
+void prof_begin(LaunchCtx& ctx, const char* name) {
+  if (!g_prof_on) return;
+  if (!g_prof) g_prof = new std::vector<ProfEntry>();
+  ProfEntry e{name, nullptr, nullptr};
+  cudaEventCreate(&e.a);
+  cudaEventCreate(&e.b);
+  cudaEventRecord(e.a, ctx.stream);
+  g_prof->push_back(e);
+}
+void prof_end(LaunchCtx& ctx) {
+  if (!g_prof_on || !g_prof || g_prof->empty()) return;
+  cudaEventRecord(g_prof->back().b, ctx.stream);
+}
+}  // namespace mdconv
+
 extern "C" {
+
+int mdconv_profile_enable(int on) {
+  g_prof_on = on != 0;
+  return MDCONV_OK;
+}
+
+// Waits for the recorded events, writes "name=milliseconds\n" per timed kernel (in launch order)
+// into buf and clears the list.  Returns the number of entries.
+int mdconv_profile_read(char* buf, size_t cap) {
+  int n = 0;
+  std::string out;
+  if (g_prof) {
+    for (ProfEntry& e : *g_prof) {
+      float ms = -1.f;
+      if (cudaEventSynchronize(e.b) == cudaSuccess) cudaEventElapsedTime(&ms, e.a, e.b);
+      char line[160];
+      snprintf(line, sizeof(line), "%s=%.6f\n", e.name, ms);
+      out += line;
+      cudaEventDestroy(e.a);
+      cudaEventDestroy(e.b);
+      ++n;
+    }
+    g_prof->clear();
+  }
+  if (buf && cap) {
+    snprintf(buf, cap, "%s", out.c_str());
+  }
+  return n;
+}
 
 int mdconv_abi_version(void) { return MDCONV_B200_ABI_VERSION; }
 

@@ -189,6 +189,16 @@ struct LaunchCtx {
     if (e__ != cudaSuccess && (ctx).err == cudaSuccess) (ctx).err = e__; \
   } while (0)
 
+// Optional per-kernel timing (mdconv_profile_enable): CUDA events recorded on the launching
+// stream around one kernel.  No-ops unless profiling is on.  Implemented in api.cu.
+void prof_begin(LaunchCtx& ctx, const char* name);
+void prof_end(LaunchCtx& ctx);
+struct ProfScope {
+  LaunchCtx& ctx;
+  ProfScope(LaunchCtx& c, const char* name) : ctx(c) { prof_begin(ctx, name); }
+  ~ProfScope() { prof_end(ctx); }
+};
+
 // generic (SIMT) path, generic_kernels.cu
 size_t generic_workspace_bytes(const DevGeom& g, int dtype, int backward);
 void generic_forward(const DevGeom& g, int dtype, const void* x, const void* w, const void* bias, const void* off,

@@ -397,6 +397,7 @@ void launch_forward(const DevGeom& g, const void* x, const void* w, const void* 
                     const void* mask, void* y, LaunchCtx& ctx) {
   const int tilesP = (g.P + BM - 1) / BM;
   dim3 grid((unsigned)(g.B * tilesP), (unsigned)((g.Cog + BN - 1) / BN), (unsigned)g.g);
+  ProfScope prof(ctx, "generic_forward");
   k_generic_forward<T, F, ND, MOD><<<grid, NT, 0, ctx.stream>>>(g, (const T*)x, (const T*)w, (const T*)bias,
                                                                 (const T*)off, (const T*)mask, (T*)y);
   MDCONV_CHECK_LAUNCH(ctx);
@@ -439,6 +440,7 @@ void launch_backward(const DevGeom& g, const void* x, const void* w, const void*
   const int tilesP = (g.P + BM - 1) / BM;
   {
     dim3 grid((unsigned)(g.B * tilesP), (unsigned)((g.Kg + BN - 1) / BN), (unsigned)g.g);
+    ProfScope prof(ctx, "generic_bwd_data");
     k_generic_bwd_data<T, F, ND, MOD><<<grid, NT, 0, ctx.stream>>>(g, (const T*)x, (const T*)w, (const T*)off,
                                                                    (const T*)mask, (const T*)go, a_gx, a_goff,
                                                                    a_gmask);
@@ -453,11 +455,13 @@ void launch_backward(const DevGeom& g, const void* x, const void* w, const void*
     if (splits < 1) splits = 1;
     if (splits > 65535) splits = 65535;
     dim3 grid((unsigned)tilesK, (unsigned)(tilesN * g.g), (unsigned)splits);
+    ProfScope prof(ctx, "generic_bwd_weight");
     k_generic_bwd_weight<T, F, ND, MOD><<<grid, NT, 0, ctx.stream>>>(g, (const T*)x, (const T*)off,
                                                                      (const T*)mask, (const T*)go, a_gw);
     MDCONV_CHECK_LAUNCH(ctx);
   }
   if (g.with_bias && gb != nullptr) {
+    ProfScope prof(ctx, "grad_bias");
     k_grad_bias<T, F><<<g.Co, NT, 0, ctx.stream>>>(g, (const T*)go, (T*)gb);
     MDCONV_CHECK_LAUNCH(ctx);
   }

@@ -14,6 +14,7 @@ Outputs only go to oracle/_ref/ (git-ignored, shipped to the GPU box by gpurun).
 /root/reference, so it runs in the build container only; the GPU box uses the prebuilt files.
 """
 import os
+import shutil
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -57,6 +58,7 @@ def build(verbose=False):
             print("note:", type(e).__name__, e, file=sys.stderr)
         so = os.path.join(bd, name + ".so")
         os.replace(so, os.path.join(OUT, name + ".so"))
+        shutil.rmtree(bd, ignore_errors=True)  # objects are not needed on the GPU box
     return built()
 
 
