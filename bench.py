@@ -251,9 +251,7 @@ def main():
     def fwd_bwd(x, off, msk, go):
         args_ = (x, off, msk) if w["modulated"] else (x, off)
         y = mod(*args_)
-        launches[0] += MDCONV_CUDA.last_launch_count()
         y.backward(go)
-        launches[0] += MDCONV_CUDA.last_launch_count()
         if bucket is not None:
             bucket.pack()
             bucket.all_reduce()
@@ -280,7 +278,7 @@ def main():
     clocks.start()
 
     # ---- timed region 1: inputs resident in HBM ("value") ----
-    launches[0] = 0
+    launches[0] = MDCONV_CUDA.total_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
     e0.record()
@@ -289,7 +287,7 @@ def main():
     e1.record()
     sync_all()
     ms_total = e0.elapsed_time(e1)
-    n_launch = launches[0]
+    n_launch = MDCONV_CUDA.total_launch_count() - launches[0]
     if world > 1:
         tmax = torch.tensor([ms_total], device=dev)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)

@@ -106,13 +106,15 @@ size_t mdconv_workspace_bytes(const mdconv_geom_t* g, int backward);
 /* Which path AUTO would take for this geometry: MDCONV_PATH_GENERIC or MDCONV_PATH_TENSOR. */
 int mdconv_selected_path(const mdconv_geom_t* g, int backward);
 
-/* Number of kernel launches the last forward/backward call of this thread enqueued. */
+/* Kernel launches enqueued by the most recent forward/backward call, and by all calls of this
+ * process so far (process-wide counters: frameworks run backward on their own threads). */
 int mdconv_last_launch_count(void);
+long long mdconv_total_launch_count(void);
 
 /* Per-kernel timing for benchmarks: while enabled, every kernel this library launches is bracketed
  * by CUDA events on the launching stream.  mdconv_profile_read() waits for them, writes one
  * "kernel_name=milliseconds\n" line per launch (launch order) into buf, clears the list and returns
- * the number of entries.  Thread-local; off by default. */
+ * the number of entries.  Process-wide; off by default. */
 int mdconv_profile_enable(int on);
 int mdconv_profile_read(char* buf, size_t cap);
 

@@ -92,6 +92,14 @@ def last_launch_count() -> int:
     return int(_lib.mdconv_last_launch_count())
 
 
+_lib.mdconv_total_launch_count.restype = ctypes.c_longlong
+
+
+def total_launch_count() -> int:
+    """Kernel launches enqueued by this library in this process so far (forward and backward)."""
+    return int(_lib.mdconv_total_launch_count())
+
+
 def library_path() -> str:
     return _LIB_PATH
 

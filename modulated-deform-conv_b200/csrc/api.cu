@@ -3,6 +3,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -14,14 +16,16 @@ using namespace mdconv;
 namespace {
 
 thread_local char g_cuda_err[256] = "";
-thread_local int g_last_launches = 0;
+std::atomic<int> g_last_launches{0};   // process-wide: autograd runs backward on its own thread
+std::atomic<long long> g_total_launches{0};
 
 struct ProfEntry {
   const char* name;
   cudaEvent_t a, b;
 };
-thread_local bool g_prof_on = false;
-thread_local std::vector<ProfEntry>* g_prof = nullptr;
+std::atomic<bool> g_prof_on{false};
+std::mutex g_prof_mu;
+std::vector<ProfEntry>* g_prof = nullptr;
 
 int resolve(const mdconv_geom_t* in, DevGeom& g) {
   if (in == nullptr) return MDCONV_ERR_NULL_POINTER;
@@ -71,6 +75,7 @@ int pick_path(const mdconv_geom_t* in, const DevGeom& g, int backward) {
 
 int finish(LaunchCtx& ctx) {
   g_last_launches = ctx.launches;
+  g_total_launches += ctx.launches;
   if (ctx.err != cudaSuccess) {
     snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", cudaGetErrorName(ctx.err), cudaGetErrorString(ctx.err));
     return MDCONV_ERR_CUDA;
@@ -83,6 +88,7 @@ int finish(LaunchCtx& ctx) {
 namespace mdconv {
 void prof_begin(LaunchCtx& ctx, const char* name) {
   if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
   if (!g_prof) g_prof = new std::vector<ProfEntry>();
   ProfEntry e{name, nullptr, nullptr};
   cudaEventCreate(&e.a);
@@ -91,7 +97,9 @@ void prof_begin(LaunchCtx& ctx, const char* name) {
   g_prof->push_back(e);
 }
 void prof_end(LaunchCtx& ctx) {
-  if (!g_prof_on || !g_prof || g_prof->empty()) return;
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof || g_prof->empty()) return;
   cudaEventRecord(g_prof->back().b, ctx.stream);
 }
 }  // namespace mdconv
@@ -108,6 +116,7 @@ int mdconv_profile_enable(int on) {
 int mdconv_profile_read(char* buf, size_t cap) {
   int n = 0;
   std::string out;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
   if (g_prof) {
     for (ProfEntry& e : *g_prof) {
       float ms = -1.f;
@@ -144,6 +153,7 @@ const char* mdconv_status_string(int status) {
 
 const char* mdconv_last_cuda_error(void) { return g_cuda_err; }
 int mdconv_last_launch_count(void) { return g_last_launches; }
+long long mdconv_total_launch_count(void) { return g_total_launches; }
 
 int mdconv_out_size(const mdconv_geom_t* gi, int32_t out[3]) {
   DevGeom g;
