@@ -1,10 +1,542 @@
-// tensor_path.cu -- placeholder until the tcgen05 kernels land (next commit).
+// tensor_path.cu -- tcgen05 / TMEM / TMA path (fp16, bf16) for sm_100a.
+//
+// Forward = implicit GEMM  D[pixels x Co] = Col[pixels x (Ci/g)*K] * W^T  per group, with the
+// offset-driven gather fused into the A-operand staging: the column matrix only ever exists as
+// 128x64 swizzled shared-memory tiles that tcgen05.mma consumes; nothing column-shaped touches HBM.
+//
+//   warp 0      TMA producer: weight K-slices [BN x 64] (128B swizzle) -> smem ring
+//   warp 1      MMA issuer: one lane issues tcgen05.mma (M=128, N=BN, K=16) x4 per K-block,
+//               accumulators in TMEM (2 stages x 256 columns), tcgen05.commit -> mbarriers
+//   warp 2      TMEM allocator
+//   warps 4-7   epilogue: tcgen05.ld -> +bias -> convert -> NCHW stores (overlaps the next tile)
+//   warps 8-15  gather producers: per K-block (64 channels x 1 tap) compute one sampling plan per
+//               pixel row (corner indices + weight*mask, once per (pixel, tap), not per channel as
+//               the reference does, src/mdeformable_conv.cu:59-83), then 128-bit channels-last
+//               loads of the corners, interpolate, and store 16-byte chunks into the swizzled tile.
+//
+// Data layout: the kernel reads x as channels-last [B][positions][C] (one 128-byte line = 64
+// channels of one position, so 8 lanes x 16 B cover a line) and the weight re-ordered to
+// [Co][(channel-block, tap, 64 channels)] so a K-block is 64 contiguous elements; both are produced
+// by two small pre-pass kernels into the caller's workspace.
+//
+// Replaces reference K1-K4 + G1 (src/mdeformable_conv.cu:38-87,172-184 and twins).
+#include <type_traits>
+
+#include "sm100_ptx.cuh"
 #include "tensor_path.cuh"
+
 namespace mdconv {
-bool tensor_path_supported(const DevGeom&, int, int) { return false; }
-size_t tensor_workspace_bytes(const DevGeom&, int, int) { return 0; }
-void tensor_forward(const DevGeom&, int, const void*, const void*, const void*, const void*, const void*, void*,
-                    void*, LaunchCtx&) {}
+
+namespace {
+
+constexpr int TC_BM = 128;        // pixels per tile (UMMA M)
+constexpr int TC_BK = 64;         // K elements per block = 128 bytes = one swizzle row
+constexpr int TC_STAGES = 3;
+constexpr int TC_MAX_BN = 256;
+constexpr int TC_THREADS = 512;
+constexpr int TC_GATHER_THREADS = 256;
+constexpr int TC_A_BYTES = TC_BM * 128;
+constexpr int TC_B_BYTES = TC_MAX_BN * 128;
+
+size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+struct TcFwdParams {
+  DevGeom g;
+  const void* xt;    // channels-last input
+  const void* off;
+  const void* mask;
+  const void* bias;
+  void* y;
+  int BN;            // output channels per tile
+  int m_tiles, n_tiles, total_tiles;
+  int ccs;           // channel blocks per group (Cg / 64)
+  int kblocks;       // ccs * K
+};
+
+template <int ND>
+struct __align__(16) PlanEntry {  // one (pixel row, tap): corner addresses (uint4 units, channel offset excluded) + weights
+  int idx[1 << ND];
+  uint32_t w[1 << ND];  // __half2 / __nv_bfloat162 pair (HALF2 math) or float bits (fp32 math)
+};
+
+template <typename T> struct Vec2;
+template <> struct Vec2<__half> { using type = __half2; };
+template <> struct Vec2<__nv_bfloat16> { using type = __nv_bfloat162; };
+
+__device__ __forceinline__ uint32_t pack_w(float w, __half) {
+  __half2 h = __float2half2_rn(w);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack_w(float w, __nv_bfloat16) { return __float_as_uint(w); }
+
+// acc += w * v for 8 channels held in a uint4.  fp16: packed HFMA2 (weights as half2);
+// bf16: fp32 FMAs (8 mantissa bits are too few to accumulate four products in).
+__device__ __forceinline__ void fma8(float (&accf)[8], uint4& acch, uint32_t w, const uint4& v, __half) {
+  const __half2 wh = *reinterpret_cast<const __half2*>(&w);
+  __half2* a = reinterpret_cast<__half2*>(&acch);
+  const __half2* x = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) a[i] = __hfma2(wh, x[i], a[i]);
+  (void)accf;
+}
+__device__ __forceinline__ void fma8(float (&accf)[8], uint4& acch, uint32_t w, const uint4& v, __nv_bfloat16) {
+  const float wf = __uint_as_float(w);
+  const uint32_t* x = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    accf[2 * i] = fmaf(wf, __uint_as_float(x[i] << 16), accf[2 * i]);
+    accf[2 * i + 1] = fmaf(wf, __uint_as_float(x[i] & 0xFFFF0000u), accf[2 * i + 1]);
+  }
+  (void)acch;
+}
+__device__ __forceinline__ uint4 finish8(const float (&accf)[8], const uint4& acch, __half) {
+  (void)accf;
+  return acch;
+}
+__device__ __forceinline__ uint4 finish8(const float (&accf)[8], const uint4& acch, __nv_bfloat16) {
+  (void)acch;
+  uint4 r;
+  uint32_t* o = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 p = __floats2bfloat162_rn(accf[2 * i], accf[2 * i + 1]);
+    o[i] = *reinterpret_cast<uint32_t*>(&p);
+  }
+  return r;
+}
+
+template <typename T, int ND, bool MOD>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const TcFwdParams prm) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve-up (all stage buffers 1024-byte aligned for the 128B swizzle)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + TC_STAGES * TC_A_BYTES;
+  PlanEntry<ND>* sPlan = reinterpret_cast<PlanEntry<ND>*>(sB + TC_STAGES * TC_B_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sPlan) +
+                                               TC_STAGES * TC_BM * sizeof(PlanEntry<ND>));
+  uint64_t* full_a = bars;
+  uint64_t* full_b = bars + TC_STAGES;
+  uint64_t* empty = bars + 2 * TC_STAGES;
+  uint64_t* tmem_full = bars + 3 * TC_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const DevGeom& g = prm.g;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmap_w);
+    for (int s = 0; s < TC_STAGES; ++s) {
+      ptx::mbar_init(&full_a[s], TC_GATHER_THREADS);
+      ptx::mbar_init(&full_b[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&tmem_full[s], 1);
+      ptx::mbar_init(&tmem_empty[s], 128);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<512>(tmem_ptr);
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int BN = prm.BN;
+  const long long total_pix = (long long)g.B * g.P;
+
+  if (warp == 0) {
+    // ===================== TMA producer: weight K-slices =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x) {
+        const int rest = t / prm.m_tiles;
+        const int nt = rest % prm.n_tiles, grp = rest / prm.n_tiles;
+        const int row0 = grp * g.Cog + nt * BN;
+        for (int kb = 0; kb < prm.kblocks; ++kb) {
+          ptx::mbar_wait(&empty[s], ph ^ 1);
+          ptx::mbar_arrive_expect_tx(&full_b[s], (uint32_t)BN * 128u);
+          ptx::tma_load_2d(sB + s * TC_B_BYTES, &tmap_w, &full_b[s], kb * TC_BK, row0);
+          if (++s == TC_STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr int fmt = sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
+      const uint32_t idesc = ptx::umma_idesc_f16(fmt, 0, 0, TC_BM, BN);
+      int s = 0;
+      uint32_t ph = 0;
+      int as = 0;
+      uint32_t aph = 0;
+      for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x) {
+        ptx::mbar_wait(&tmem_empty[as], aph ^ 1);
+        ptx::tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * TC_MAX_BN);
+        for (int kb = 0; kb < prm.kblocks; ++kb) {
+          ptx::mbar_wait(&full_b[s], ph);
+          ptx::mbar_wait(&full_a[s], ph);
+          ptx::tc_fence_after_sync();
+          const uint32_t a_addr = ptx::smem_u32(sA + s * TC_A_BYTES);
+          const uint32_t b_addr = ptx::smem_u32(sB + s * TC_B_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t ad = ptx::umma_smem_desc_sw128(a_addr + k * 32, 0, 1024);
+            const uint64_t bd = ptx::umma_smem_desc_sw128(b_addr + k * 32, 0, 1024);
+            ptx::umma_f16(d_tmem, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty[s]);
+          if (++s == TC_STAGES) { s = 0; ph ^= 1; }
+        }
+        ptx::umma_commit(&tmem_full[as]);
+        if (++as == 2) { as = 0; aph ^= 1; }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================== epilogue =====================
+    const int ew = warp & 3;
+    T* __restrict__ y = reinterpret_cast<T*>(prm.y);
+    const T* __restrict__ bias = reinterpret_cast<const T*>(prm.bias);
+    int as = 0;
+    uint32_t aph = 0;
+    for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x) {
+      const int mt = t % prm.m_tiles;
+      const int rest = t / prm.m_tiles;
+      const int nt = rest % prm.n_tiles, grp = rest / prm.n_tiles;
+      const long long gp = (long long)mt * TC_BM + ew * 32 + lane;
+      const bool valid = gp < total_pix;
+      const int b = valid ? (int)(gp / g.P) : 0;
+      const int p = valid ? (int)(gp % g.P) : 0;
+      const int co0 = grp * g.Cog + nt * BN;
+      T* yrow = y + ((size_t)b * g.Co + co0) * g.P + p;
+      ptx::mbar_wait(&tmem_full[as], aph);
+      ptx::tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * TC_MAX_BN);
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(taddr + c0, v);
+        ptx::tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float f = __uint_as_float(v[j]);
+            if (g.with_bias) f += ld_as<float>(bias + co0 + c0 + j);
+            yrow[(size_t)(c0 + j) * g.P] = cvt_to<T, float>(f);
+          }
+        }
+      }
+      ptx::tc_fence_before_sync();
+      ptx::mbar_arrive(&tmem_empty[as]);
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+  } else if (warp >= 8) {
+    // ===================== gather producers =====================
+    const int gt = threadIdx.x - 256;  // 0..255
+    const int gw = gt >> 5;            // gather warp 0..7
+    const T* __restrict__ off = reinterpret_cast<const T*>(prm.off);
+    const T* __restrict__ mask = reinterpret_cast<const T*>(prm.mask);
+    const uint4* __restrict__ xq = reinterpret_cast<const uint4*>(prm.xt);
+    const int C8 = g.C >> 3;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x) {
+      const int mt = t % prm.m_tiles;
+      const int grp = (t / prm.m_tiles) / prm.n_tiles;
+      // row metadata for the plan threads (gt < 128 owns pixel row gt of the tile)
+      int rb = 0, rp = 0, base[ND];
+      bool rvalid = false;
+      if (gt < TC_BM) {
+        const long long gp = (long long)mt * TC_BM + gt;
+        rvalid = gp < total_pix;
+        if (rvalid) {
+          rb = (int)(gp / g.P);
+          rp = (int)(gp % g.P);
+        }
+        int o[3];
+        if (ND == 2) {
+          o[1] = rp % g.out[1]; o[0] = rp / g.out[1];
+        } else {
+          o[2] = rp % g.out[2]; const int r2 = rp / g.out[2]; o[1] = r2 % g.out[1]; o[0] = r2 / g.out[1];
+        }
+#pragma unroll
+        for (int a = 0; a < ND; ++a) base[a] = o[a] * g.s[a] - g.p[a];
+      }
+      for (int kb = 0; kb < prm.kblocks; ++kb) {
+        const int cc = kb / g.K, tap = kb - cc * g.K;
+        const int c0 = grp * g.Cg + cc * TC_BK;  // first channel of this K-block
+        PlanEntry<ND>* plan = sPlan + s * TC_BM;
+        if (gt < TC_BM) {
+          PlanEntry<ND> e;
+#pragma unroll
+          for (int c = 0; c < (1 << ND); ++c) { e.idx[c] = 0; e.w[c] = 0u; }
+          if (rvalid) {
+            const int dgi = c0 / g.Cdg;
+            int tt[3];
+            if (ND == 2) {
+              tt[1] = tap % g.k[1]; tt[0] = tap / g.k[1];
+            } else {
+              tt[2] = tap % g.k[2]; const int q = tap / g.k[2]; tt[1] = q % g.k[1]; tt[0] = q / g.k[1];
+            }
+            const T* op = off + ((size_t)rb * g.dg * g.K + (size_t)dgi * g.K + tap) * ND * g.P + rp;
+            int lo[ND];
+            float fr[ND];
+            bool in_range = true;
+#pragma unroll
+            for (int a = 0; a < ND; ++a) {
+              const float pos = (float)(base[a] + tt[a] * g.d[a]) + ld_as<float>(op + (size_t)a * g.P);
+              const float fl = floorf(pos);
+              lo[a] = (int)fl;
+              fr[a] = pos - fl;
+              in_range = in_range && (pos > -1.f) && (pos < (float)g.in[a]);
+            }
+            if (in_range) {
+              float m = 1.f;
+              if (MOD) m = ld_as<float>(mask + ((size_t)rb * g.dg * g.K + (size_t)dgi * g.K + tap) * g.P + rp);
+#pragma unroll
+              for (int c = 0; c < (1 << ND); ++c) {
+                float w = m;
+                bool ok = true;
+                int pix = 0;
+#pragma unroll
+                for (int a = 0; a < ND; ++a) {
+                  const int hi = (c >> a) & 1;
+                  const int ia = lo[a] + hi;
+                  ok = ok && (hi ? (ia <= g.in[a] - 1) : (ia >= 0));
+                  w *= hi ? fr[a] : (1.f - fr[a]);
+                  pix = pix * g.in[a] + ia;
+                }
+                if (ok) {
+                  e.idx[c] = (rb * g.IN + pix) * C8;
+                  e.w[c] = pack_w(w, T());
+                }
+              }
+            }
+          }
+          plan[gt] = e;
+        }
+        ptx::named_bar_sync(1, TC_GATHER_THREADS);  // plan visible to all gather warps
+
+        ptx::mbar_wait(&empty[s], ph ^ 1);          // MMA has finished reading A[s]
+        uint8_t* a_tile = sA + s * TC_A_BYTES;
+        const int chunk = lane & 7;
+        const uint4* xc = xq + (c0 >> 3) + chunk;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int row = gw * 16 + j * 4 + (lane >> 3);
+          const PlanEntry<ND> e = plan[row];
+          float accf[8];
+          uint4 acch = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) accf[i] = 0.f;
+          uint4 v[1 << ND];
+#pragma unroll
+          for (int c = 0; c < (1 << ND); ++c) v[c] = __ldg(xc + e.idx[c]);
+#pragma unroll
+          for (int c = 0; c < (1 << ND); ++c) fma8(accf, acch, e.w[c], v[c], T());
+          const uint4 r = finish8(accf, acch, T());
+          *reinterpret_cast<uint4*>(a_tile + row * 128 + ((chunk ^ (row & 7)) << 4)) = r;
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive(&full_a[s]);
+        if (++s == TC_STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc<512>(tmem_base);
+}
+
+// ---- pre-pass kernels ---------------------------------------------------------------------------
+// x [B][C][IN] -> xt [B][IN][C]
+template <typename T>
+__global__ void __launch_bounds__(256) k_to_channels_last(const T* __restrict__ x, T* __restrict__ xt, int C, int IN) {
+  __shared__ T tile[64][66];
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * 64, i0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const T* xb = x + (size_t)b * C * IN;
+  T* xtb = xt + (size_t)b * C * IN;
+#pragma unroll
+  for (int rr = 0; rr < 8; ++rr) {
+    const int c = ty + 8 * rr;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = tx + 32 * h;
+      if (c0 + c < C && i0 + i < IN) tile[c][i] = xb[(size_t)(c0 + c) * IN + i0 + i];
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int rr = 0; rr < 8; ++rr) {
+    const int i = ty + 8 * rr;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = tx + 32 * h;
+      if (c0 + c < C && i0 + i < IN) xtb[(size_t)(i0 + i) * C + c0 + c] = tile[c][i];
+    }
+  }
+}
+
+// W [Co][Cg][K] -> Wr [Co][(cc*K + tap)*64 + ci],  c = cc*64 + ci
+template <typename T>
+__global__ void k_reorder_weight(const T* __restrict__ w, T* __restrict__ wr, int Co, int Cg, int K) {
+  const size_t n = (size_t)Co * Cg * K;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int Kg = Cg * K;
+    const int co = (int)(i / Kg);
+    const int r = (int)(i % Kg);
+    const int ci = r & 63;
+    const int q = r >> 6;
+    const int tap = q % K, cc = q / K;
+    wr[i] = w[(size_t)co * Kg + (size_t)(cc * 64 + ci) * K + tap];
+  }
+}
+
+// ---- host side --------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+int pick_bn(const DevGeom& g) { return g.Cog <= TC_MAX_BN ? g.Cog : TC_MAX_BN; }
+
+template <int ND>
+size_t fwd_smem_bytes() {
+  return 1024 + (size_t)TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + (size_t)TC_STAGES * TC_BM * sizeof(PlanEntry<ND>) +
+         (3 * TC_STAGES + 4) * sizeof(uint64_t) + 16;
+}
+
+template <typename T, int ND, bool MOD>
+void launch_tc_forward(const CUtensorMap& tmap, const TcFwdParams& prm, LaunchCtx& ctx) {
+  const size_t smem = fwd_smem_bytes<ND>();
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_tc_forward<T, ND, MOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess && ctx.err == cudaSuccess) ctx.err = e;
+    configured = true;
+  }
+  const int grid = prm.total_tiles < sm_count() ? prm.total_tiles : sm_count();
+  ProfScope prof(ctx, "tc_forward");
+  k_tc_forward<T, ND, MOD><<<grid, TC_THREADS, smem, ctx.stream>>>(tmap, prm);
+  MDCONV_CHECK_LAUNCH(ctx);
+}
+
+template <typename T>
+void tensor_forward_t(const DevGeom& g, const void* x, const void* w, const void* bias, const void* off,
+                      const void* mask, void* y, void* ws, LaunchCtx& ctx) {
+  T* xt = reinterpret_cast<T*>(ws);
+  T* wr = reinterpret_cast<T*>(reinterpret_cast<char*>(ws) + align256((size_t)g.B * g.C * g.IN * sizeof(T)));
+  {
+    ProfScope prof(ctx, "to_channels_last");
+    dim3 grid((unsigned)((g.IN + 63) / 64), (unsigned)((g.C + 63) / 64), (unsigned)g.B);
+    k_to_channels_last<T><<<grid, 256, 0, ctx.stream>>>((const T*)x, xt, g.C, g.IN);
+    MDCONV_CHECK_LAUNCH(ctx);
+  }
+  {
+    ProfScope prof(ctx, "reorder_weight");
+    const size_t n = (size_t)g.Co * g.Kg;
+    const int blocks = (int)((n + 255) / 256 > 1184 ? 1184 : (n + 255) / 256);
+    k_reorder_weight<T><<<blocks, 256, 0, ctx.stream>>>((const T*)w, wr, g.Co, g.Cg, g.K);
+    MDCONV_CHECK_LAUNCH(ctx);
+  }
+  TcFwdParams prm;
+  prm.g = g;
+  prm.xt = xt; prm.off = off; prm.mask = mask; prm.bias = bias; prm.y = y;
+  prm.BN = pick_bn(g);
+  const long long total_pix = (long long)g.B * g.P;
+  prm.m_tiles = (int)((total_pix + TC_BM - 1) / TC_BM);
+  prm.n_tiles = g.Cog / prm.BN;
+  prm.total_tiles = prm.m_tiles * prm.n_tiles * g.g;
+  prm.ccs = g.Cg / TC_BK;
+  prm.kblocks = prm.ccs * g.K;
+
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) {
+    if (ctx.err == cudaSuccess) ctx.err = cudaErrorNotSupported;
+    return;
+  }
+  CUtensorMap tmap;
+  const cuuint64_t dims[2] = {(cuuint64_t)g.Kg, (cuuint64_t)g.Co};
+  const cuuint64_t strides[1] = {(cuuint64_t)g.Kg * sizeof(T)};
+  const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)prm.BN};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapDataType dt =
+      std::is_same<T, __half>::value ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUresult r = enc(&tmap, dt, 2, wr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    if (ctx.err == cudaSuccess) ctx.err = cudaErrorInvalidValue;
+    return;
+  }
+  if (g.nd == 2) {
+    if (g.modulated) launch_tc_forward<T, 2, true>(tmap, prm, ctx);
+    else launch_tc_forward<T, 2, false>(tmap, prm, ctx);
+  } else {
+    if (g.modulated) launch_tc_forward<T, 3, true>(tmap, prm, ctx);
+    else launch_tc_forward<T, 3, false>(tmap, prm, ctx);
+  }
+}
+
+}  // namespace
+
+bool tensor_path_supported(const DevGeom& g, int dtype, int backward) {
+  if (backward) return false;  // backward still runs on the generic kernels
+  if (dtype != MDCONV_F16 && dtype != MDCONV_BF16) return false;
+  if (g.Cg % TC_BK != 0 || g.Cdg % TC_BK != 0) return false;
+  if (g.Cog % 32 != 0) return false;
+  if (g.Cog > TC_MAX_BN && g.Cog % TC_MAX_BN != 0) return false;
+  if ((long long)g.B * g.IN * (g.C / 8) > 2147483647LL) return false;
+  return true;
+}
+
+size_t tensor_workspace_bytes(const DevGeom& g, int dtype, int backward) {
+  (void)dtype;
+  if (backward) return 0;
+  return align256((size_t)g.B * g.C * g.IN * 2) + align256((size_t)g.Co * g.Kg * 2);
+}
+
+void tensor_forward(const DevGeom& g, int dtype, const void* x, const void* w, const void* bias, const void* off,
+                    const void* mask, void* y, void* ws, LaunchCtx& ctx) {
+  if (dtype == MDCONV_F16) tensor_forward_t<__half>(g, x, w, bias, off, mask, y, ws, ctx);
+  else tensor_forward_t<__nv_bfloat16>(g, x, w, bias, off, mask, y, ws, ctx);
+}
+
 void tensor_backward(const DevGeom&, int, const void*, const void*, const void*, const void*, const void*, void*,
-                     void*, void*, void*, void*, void*, LaunchCtx&) {}
+                     void*, void*, void*, void*, void*, LaunchCtx& ctx) {
+  if (ctx.err == cudaSuccess) ctx.err = cudaErrorNotSupported;
+}
+
 }  // namespace mdconv

@@ -14,14 +14,19 @@ pytestmark = pytest.mark.gpu
 TOL = {torch.float64: 1e-10, torch.float32: 1e-4, torch.float16: 1e-2, torch.bfloat16: 3e-2}
 
 
-def _run_ours(case, t, dev="cuda"):
+def _run_ours(case, t, dev="cuda", fwd_path=None, bwd_path=None):
+    import MDCONV_CUDA
     import modulated_deform_conv as mdc
     fn = {(2, False): mdc.deform_conv2d, (2, True): mdc.modulated_deform_conv2d,
           (3, False): mdc.deform_conv3d, (3, True): mdc.modulated_deform_conv3d}[(case.nd, case.modulated)]
     leaves = {k: (v.to(dev).requires_grad_() if v is not None and k != "grad_output" else v) for k, v in t.items()}
     args = [leaves["x"], leaves["offset"]] + ([leaves["mask"]] if case.modulated else []) + \
            [leaves["weight"], leaves["bias"], case.s, case.p, case.d, case.g, case.dg, 64]
+    if fwd_path is not None:
+        MDCONV_CUDA.set_path(fwd_path)
     y = fn(*args)
+    if bwd_path is not None:
+        MDCONV_CUDA.set_path(bwd_path)
     y.backward(t["grad_output"].to(dev))
     torch.cuda.synchronize()
     out = {"y": y.detach(), "grad_input": leaves["x"].grad, "grad_offset": leaves["offset"].grad,
@@ -68,7 +73,7 @@ def test_generic_path_matches_oracle(case, dtype):
 TENSOR_CASES = [
     Case("tc_m2d_c64", 2, True, B=2, C=64, Co=64, size=(12, 11), seed=50),
     Case("tc_m2d_c128_co256_nobias", 2, True, B=3, C=128, Co=256, size=(9, 14), bias=False, seed=51),
-    Case("tc_m2d_stride2_dg2", 2, True, B=2, C=64, Co=128, size=(15, 13), s=(2, 2), dg=2, seed=52),
+    Case("tc_m2d_stride2_dg2", 2, True, B=2, C=128, Co=128, size=(15, 13), s=(2, 2), dg=2, seed=52),
     Case("tc_m2d_dil2_sigma4", 2, True, B=1, C=64, Co=64, size=(16, 16), p=(2, 2), d=(2, 2), sigma=4.0, seed=53),
     Case("tc_m2d_integer_grid", 2, True, B=2, C=64, Co=64, size=(8, 9), sigma=0.0, seed=54),
     Case("tc_m2d_half_grid", 2, True, B=2, C=64, Co=64, size=(8, 9), sigma=0.5, seed=55),
@@ -88,18 +93,20 @@ TENSOR_CASES = [
 @pytest.mark.parametrize("case", TENSOR_CASES, ids=lambda c: c.name)
 def test_tensor_path_matches_oracle(case, dtype):
     """tcgen05 path (forced; the test fails if the path refuses a shape it claims to support)."""
+    import ctypes
     import MDCONV_CUDA
     t = make_inputs(case, dtype)
-    MDCONV_CUDA.set_path(2)
+    # which directions does the tensor path take for this geometry?  (forward is mandatory here)
+    g = MDCONV_CUDA._geom(t["x"], t["weight"], case.k, case.s, case.p, case.d, case.g, case.dg, case.modulated,
+                          case.bias)
+    g.path = 2
+    assert MDCONV_CUDA._lib.mdconv_selected_path(ctypes.byref(g), 0) == 2, "tensor path refused the forward"
+    bwd = 2 if MDCONV_CUDA._lib.mdconv_selected_path(ctypes.byref(g), 1) == 2 else 1
     try:
-        ours = _run_ours(case, t)
-    except RuntimeError as e:
-        if "bad geometry" in str(e):
-            pytest.skip(f"tensor path does not take this shape: {e}")
-        raise
+        ours = _run_ours(case, t, fwd_path=2, bwd_path=bwd)
     finally:
         MDCONV_CUDA.set_path(0)
-    _compare(ours, _oracle(case, t), TOL[dtype], f"{case.name}/{dtype}")
+    _compare(ours, _oracle(case, t), TOL[dtype], f"{case.name}/{dtype} (bwd path {bwd})")
 
 
 def test_results_do_not_depend_on_in_step():
