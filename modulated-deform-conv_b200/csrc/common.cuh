@@ -203,7 +203,11 @@ struct ProfScope {
 size_t generic_workspace_bytes(const DevGeom& g, int dtype, int backward);
 void generic_forward(const DevGeom& g, int dtype, const void* x, const void* w, const void* bias, const void* off,
                      const void* mask, void* y, LaunchCtx& ctx);
+// `parts` selects which gradients the generic kernels produce (the tensor path delegates the ones
+// it does not compute itself).
+enum { GENERIC_BWD_DATA = 1, GENERIC_BWD_WEIGHT = 2, GENERIC_BWD_BIAS = 4, GENERIC_BWD_ALL = 7 };
 void generic_backward(const DevGeom& g, int dtype, const void* x, const void* w, const void* off, const void* mask,
-                      const void* go, void* gx, void* gw, void* gb, void* goff, void* gmask, void* ws, LaunchCtx& ctx);
+                      const void* go, void* gx, void* gw, void* gb, void* goff, void* gmask, void* ws, LaunchCtx& ctx,
+                      int parts = GENERIC_BWD_ALL);
 
 }  // namespace mdconv

@@ -414,7 +414,9 @@ void convert_from_f32(const float* src, void* dst, size_t n, LaunchCtx& ctx) {
 template <typename T, typename F, int ND, bool MOD>
 void launch_backward(const DevGeom& g, const void* x, const void* w, const void* off, const void* mask,
                      const void* go, void* gx, void* gw, void* gb, void* goff, void* gmask, void* ws,
-                     LaunchCtx& ctx) {
+                     LaunchCtx& ctx, int parts) {
+  const bool do_data = parts & GENERIC_BWD_DATA, do_weight = parts & GENERIC_BWD_WEIGHT,
+             do_bias = parts & GENERIC_BWD_BIAS;
   const BwdSizes sz = bwd_sizes(g);
   constexpr bool direct = sizeof(T) == sizeof(F);  // f32 / f64 accumulate straight into the outputs
   F *a_gx, *a_goff, *a_gmask, *a_gw;
@@ -432,13 +434,15 @@ void launch_backward(const DevGeom& g, const void* x, const void* w, const void*
     cudaError_t e = cudaMemsetAsync(p, 0, bytes, ctx.stream);
     if (e != cudaSuccess && ctx.err == cudaSuccess) ctx.err = e;
   };
-  zero(a_gx, sz.n_gx * sizeof(F));
-  zero(a_goff, sz.n_goff * sizeof(F));
-  if (MOD) zero(a_gmask, sz.n_gmask * sizeof(F));
-  zero(a_gw, sz.n_gw * sizeof(F));
+  if (do_data) {
+    zero(a_gx, sz.n_gx * sizeof(F));
+    zero(a_goff, sz.n_goff * sizeof(F));
+    if (MOD) zero(a_gmask, sz.n_gmask * sizeof(F));
+  }
+  if (do_weight) zero(a_gw, sz.n_gw * sizeof(F));
 
   const int tilesP = (g.P + BM - 1) / BM;
-  {
+  if (do_data) {
     dim3 grid((unsigned)(g.B * tilesP), (unsigned)((g.Kg + BN - 1) / BN), (unsigned)g.g);
     ProfScope prof(ctx, "generic_bwd_data");
     k_generic_bwd_data<T, F, ND, MOD><<<grid, NT, 0, ctx.stream>>>(g, (const T*)x, (const T*)w, (const T*)off,
@@ -446,7 +450,7 @@ void launch_backward(const DevGeom& g, const void* x, const void* w, const void*
                                                                    a_gmask);
     MDCONV_CHECK_LAUNCH(ctx);
   }
-  {
+  if (do_weight) {
     const int tilesK = (g.Kg + BN - 1) / BN;
     const int tilesN = (g.Cog + BN - 1) / BN;
     const int units = g.B * ((g.P + BP - 1) / BP);
@@ -460,17 +464,19 @@ void launch_backward(const DevGeom& g, const void* x, const void* w, const void*
                                                                      (const T*)mask, (const T*)go, a_gw);
     MDCONV_CHECK_LAUNCH(ctx);
   }
-  if (g.with_bias && gb != nullptr) {
+  if (do_bias && g.with_bias && gb != nullptr) {
     ProfScope prof(ctx, "grad_bias");
     k_grad_bias<T, F><<<g.Co, NT, 0, ctx.stream>>>(g, (const T*)go, (T*)gb);
     MDCONV_CHECK_LAUNCH(ctx);
   }
   if (!direct) {
     if constexpr (!direct) {
-      convert_from_f32<T>((const float*)a_gx, gx, sz.n_gx, ctx);
-      convert_from_f32<T>((const float*)a_goff, goff, sz.n_goff, ctx);
-      if (MOD) convert_from_f32<T>((const float*)a_gmask, gmask, sz.n_gmask, ctx);
-      convert_from_f32<T>((const float*)a_gw, gw, sz.n_gw, ctx);
+      if (do_data) {
+        convert_from_f32<T>((const float*)a_gx, gx, sz.n_gx, ctx);
+        convert_from_f32<T>((const float*)a_goff, goff, sz.n_goff, ctx);
+        if (MOD) convert_from_f32<T>((const float*)a_gmask, gmask, sz.n_gmask, ctx);
+      }
+      if (do_weight) convert_from_f32<T>((const float*)a_gw, gw, sz.n_gw, ctx);
     }
   }
 }
@@ -490,13 +496,13 @@ void dispatch_forward(const DevGeom& g, const void* x, const void* w, const void
 template <typename T, typename F>
 void dispatch_backward(const DevGeom& g, const void* x, const void* w, const void* off, const void* mask,
                        const void* go, void* gx, void* gw, void* gb, void* goff, void* gmask, void* ws,
-                       LaunchCtx& ctx) {
+                       LaunchCtx& ctx, int parts) {
   if (g.nd == 2) {
-    if (g.modulated) launch_backward<T, F, 2, true>(g, x, w, off, mask, go, gx, gw, gb, goff, gmask, ws, ctx);
-    else launch_backward<T, F, 2, false>(g, x, w, off, mask, go, gx, gw, gb, goff, gmask, ws, ctx);
+    if (g.modulated) launch_backward<T, F, 2, true>(g, x, w, off, mask, go, gx, gw, gb, goff, gmask, ws, ctx, parts);
+    else launch_backward<T, F, 2, false>(g, x, w, off, mask, go, gx, gw, gb, goff, gmask, ws, ctx, parts);
   } else {
-    if (g.modulated) launch_backward<T, F, 3, true>(g, x, w, off, mask, go, gx, gw, gb, goff, gmask, ws, ctx);
-    else launch_backward<T, F, 3, false>(g, x, w, off, mask, go, gx, gw, gb, goff, gmask, ws, ctx);
+    if (g.modulated) launch_backward<T, F, 3, true>(g, x, w, off, mask, go, gx, gw, gb, goff, gmask, ws, ctx, parts);
+    else launch_backward<T, F, 3, false>(g, x, w, off, mask, go, gx, gw, gb, goff, gmask, ws, ctx, parts);
   }
 }
 
@@ -522,14 +528,14 @@ void generic_forward(const DevGeom& g, int dtype, const void* x, const void* w, 
 
 void generic_backward(const DevGeom& g, int dtype, const void* x, const void* w, const void* off, const void* mask,
                       const void* go, void* gx, void* gw, void* gb, void* goff, void* gmask, void* ws,
-                      LaunchCtx& ctx) {
+                      LaunchCtx& ctx, int parts) {
   switch (dtype) {
-    case MDCONV_F32: dispatch_backward<float, float>(g, x, w, off, mask, go, gx, gw, gb, goff, gmask, ws, ctx); break;
-    case MDCONV_F16: dispatch_backward<__half, float>(g, x, w, off, mask, go, gx, gw, gb, goff, gmask, ws, ctx); break;
+    case MDCONV_F32: dispatch_backward<float, float>(g, x, w, off, mask, go, gx, gw, gb, goff, gmask, ws, ctx, parts); break;
+    case MDCONV_F16: dispatch_backward<__half, float>(g, x, w, off, mask, go, gx, gw, gb, goff, gmask, ws, ctx, parts); break;
     case MDCONV_BF16:
-      dispatch_backward<__nv_bfloat16, float>(g, x, w, off, mask, go, gx, gw, gb, goff, gmask, ws, ctx);
+      dispatch_backward<__nv_bfloat16, float>(g, x, w, off, mask, go, gx, gw, gb, goff, gmask, ws, ctx, parts);
       break;
-    case MDCONV_F64: dispatch_backward<double, double>(g, x, w, off, mask, go, gx, gw, gb, goff, gmask, ws, ctx); break;
+    case MDCONV_F64: dispatch_backward<double, double>(g, x, w, off, mask, go, gx, gw, gb, goff, gmask, ws, ctx, parts); break;
     default: break;
   }
 }

@@ -1,0 +1,225 @@
+// tc_common.cuh -- pieces shared by the tcgen05 kernels (forward, grad-weight, grad-data):
+// the per-(pixel, tap) sampling plan, the 8-channel corner gather, and the pre-pass kernels.
+#pragma once
+#include <type_traits>
+
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace mdconv {
+namespace tc {
+
+constexpr int BK = 64;  // K elements per block = 128 bytes = one 128B-swizzle row
+
+inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// ---- explicit shared-state-space accesses (generic LD/ST through a computed pointer is slower) ----
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+
+// byte offset of 16-byte chunk `chunk` of row `row` inside a [rows][128 B] tile with 128B swizzle
+__device__ __forceinline__ uint32_t sw128(int row, int chunk) {
+  return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4));
+}
+
+// ---- sampling plan --------------------------------------------------------------------------------
+// One (output position, tap): per corner the address of the 8-channel vector in the channels-last
+// input (uint4 units, channel offset excluded) and the interpolation weight (x mask), zero for
+// corners outside the input or points outside the sampling range (reference rule:
+// src/mdeformable_conv.cu:19-29,80).  Computed once per (position, tap), shared by all channels
+// of the deformable group.
+template <int ND>
+struct __align__(16) PlanEntry {
+  int idx[1 << ND];
+  uint32_t w[1 << ND];  // fp16: half2 pair (w, w); bf16: fp32 bits
+};
+
+template <int ND>
+struct RowCoord {
+  int b, p;
+  int base[ND];  // out*stride - pad per axis
+  bool valid;
+};
+
+template <int ND>
+__device__ __forceinline__ void decode_row(const DevGeom& g, int b, int p, bool valid, RowCoord<ND>& rc) {
+  rc.b = valid ? b : 0;
+  rc.p = valid ? p : 0;
+  rc.valid = valid;
+  int o[3];
+  if (ND == 2) {
+    o[1] = rc.p % g.out[1]; o[0] = rc.p / g.out[1];
+  } else {
+    o[2] = rc.p % g.out[2]; const int r2 = rc.p / g.out[2]; o[1] = r2 % g.out[1]; o[0] = r2 / g.out[1];
+  }
+#pragma unroll
+  for (int a = 0; a < ND; ++a) rc.base[a] = o[a] * g.s[a] - g.p[a];
+}
+
+__device__ __forceinline__ uint32_t pack_w(float w, __half) {
+  __half2 h = __float2half2_rn(w);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack_w(float w, __nv_bfloat16) { return __float_as_uint(w); }
+
+// Sampling position of (row, tap): floor, fraction, range flag, mask value.
+template <int ND>
+struct SamplePos {
+  int lo[ND];
+  float fr[ND];
+  bool in_range;
+  float m;
+};
+
+template <typename T, int ND, bool MOD>
+__device__ __forceinline__ void sample_pos(const DevGeom& g, const T* __restrict__ off, const T* __restrict__ mask,
+                                           const RowCoord<ND>& rc, int dgi, int tap, SamplePos<ND>& sp) {
+  int tt[3];
+  if (ND == 2) {
+    tt[1] = tap % g.k[1]; tt[0] = tap / g.k[1];
+  } else {
+    tt[2] = tap % g.k[2]; const int q = tap / g.k[2]; tt[1] = q % g.k[1]; tt[0] = q / g.k[1];
+  }
+  const size_t ch = (size_t)rc.b * g.dg * g.K + (size_t)dgi * g.K + tap;
+  const T* op = off + ch * ND * g.P + rc.p;
+  sp.in_range = true;
+#pragma unroll
+  for (int a = 0; a < ND; ++a) {
+    const float pos = (float)(rc.base[a] + tt[a] * g.d[a]) + ld_as<float>(op + (size_t)a * g.P);
+    const float fl = floorf(pos);
+    sp.lo[a] = (int)fl;
+    sp.fr[a] = pos - fl;
+    sp.in_range = sp.in_range && (pos > -1.f) && (pos < (float)g.in[a]);
+  }
+  sp.m = 1.f;
+  if (MOD) sp.m = ld_as<float>(mask + ch * g.P + rc.p);
+}
+
+template <typename T, int ND, bool MOD>
+__device__ __forceinline__ PlanEntry<ND> make_plan_entry(const DevGeom& g, const T* __restrict__ off,
+                                                         const T* __restrict__ mask, const RowCoord<ND>& rc, int c0,
+                                                         int tap, int C8) {
+  PlanEntry<ND> e;
+#pragma unroll
+  for (int c = 0; c < (1 << ND); ++c) { e.idx[c] = 0; e.w[c] = 0u; }
+  if (!rc.valid) return e;
+  SamplePos<ND> sp;
+  sample_pos<T, ND, MOD>(g, off, mask, rc, c0 / g.Cdg, tap, sp);
+  if (!sp.in_range) return e;
+#pragma unroll
+  for (int c = 0; c < (1 << ND); ++c) {
+    float w = sp.m;
+    bool ok = true;
+    int pix = 0;
+#pragma unroll
+    for (int a = 0; a < ND; ++a) {
+      const int hi = (c >> a) & 1;
+      const int ia = sp.lo[a] + hi;
+      ok = ok && (hi ? (ia <= g.in[a] - 1) : (ia >= 0));
+      w *= hi ? sp.fr[a] : (1.f - sp.fr[a]);
+      pix = pix * g.in[a] + ia;
+    }
+    if (ok) {
+      e.idx[c] = (rc.b * g.IN + pix) * C8;
+      e.w[c] = pack_w(w, T());
+    }
+  }
+  return e;
+}
+
+template <int ND>
+__device__ __forceinline__ void store_plan(uint32_t saddr, const PlanEntry<ND>& e) {
+  const uint4* q = reinterpret_cast<const uint4*>(&e);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(PlanEntry<ND>) / 16); ++i) sts128(saddr + 16 * i, q[i]);
+}
+template <int ND>
+__device__ __forceinline__ PlanEntry<ND> load_plan(uint32_t saddr) {
+  PlanEntry<ND> e;
+  uint4* q = reinterpret_cast<uint4*>(&e);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(PlanEntry<ND>) / 16); ++i) q[i] = lds128(saddr + 16 * i);
+  return e;
+}
+
+// ---- 8-channel interpolation ------------------------------------------------------------------------
+// fp16: packed HFMA2 with half2 weights; bf16: fp32 FMAs (8 mantissa bits cannot hold four products).
+__device__ __forceinline__ uint4 interp8(const uint4* v, const uint32_t* w, int nc, __half) {
+  uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+  __half2* a = reinterpret_cast<__half2*>(&acc);
+  for (int c = 0; c < nc; ++c) {
+    const __half2 wh = *reinterpret_cast<const __half2*>(&w[c]);
+    const __half2* x = reinterpret_cast<const __half2*>(&v[c]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = __hfma2(wh, x[i], a[i]);
+  }
+  return acc;
+}
+__device__ __forceinline__ uint4 interp8(const uint4* v, const uint32_t* w, int nc, __nv_bfloat16) {
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int c = 0; c < nc; ++c) {
+    const float wf = __uint_as_float(w[c]);
+    const uint32_t* x = reinterpret_cast<const uint32_t*>(&v[c]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      acc[2 * i] = fmaf(wf, __uint_as_float(x[i] << 16), acc[2 * i]);
+      acc[2 * i + 1] = fmaf(wf, __uint_as_float(x[i] & 0xFFFF0000u), acc[2 * i + 1]);
+    }
+  }
+  uint4 r;
+  uint32_t* o = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 p = __floats2bfloat162_rn(acc[2 * i], acc[2 * i + 1]);
+    o[i] = *reinterpret_cast<uint32_t*>(&p);
+  }
+  return r;
+}
+
+// column value (8 channels) of one plan entry; xc already points at the channel chunk
+template <typename T, int ND>
+__device__ __forceinline__ uint4 gather8(const uint4* __restrict__ xc, const PlanEntry<ND>& e) {
+  uint4 v[1 << ND];
+#pragma unroll
+  for (int c = 0; c < (1 << ND); ++c) v[c] = __ldg(xc + e.idx[c]);
+  return interp8(v, e.w, 1 << ND, T());
+}
+
+// ---- pre-pass kernels (tensor_path.cu) ----------------------------------------------------------------
+template <typename T> void launch_to_channels_last(const T* x, T* xt, int B, int C, int IN, LaunchCtx& ctx);
+// W [Co][Cg][K] -> Wr [Co][(cc*K + tap)*64 + ci]   (c = cc*64 + ci)
+template <typename T> void launch_reorder_weight(const T* w, T* wr, int Co, int Cg, int K, LaunchCtx& ctx);
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encode_fn();
+int sm_count();
+
+template <typename T>
+inline CUtensorMapDataType tmap_dtype() {
+  return std::is_same<T, __half>::value ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+}
+template <typename T>
+constexpr int umma_fmt() {
+  return std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
+}
+
+// backward kernels (tensor_bwd.cu)
+template <typename T>
+void tensor_backward_t(const DevGeom& g, const void* x, const void* w, const void* off, const void* mask,
+                       const void* go, void* gx, void* gw, void* gb, void* goff, void* gmask, void* ws, LaunchCtx& ctx);
+size_t tensor_backward_workspace(const DevGeom& g);
+bool tensor_backward_supported(const DevGeom& g, int dtype);
+
+}  // namespace tc
+}  // namespace mdconv

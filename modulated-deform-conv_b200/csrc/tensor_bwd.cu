@@ -1,0 +1,342 @@
+// tensor_bwd.cu -- tcgen05 backward kernels (fp16 / bf16).
+//
+// grad_weight:  gW[co, kk] = sum over positions of go[co, pos] * col[kk, pos]   (reference G3,
+//   src/mdeformable_conv.cu:436-439, which reads a materialised 462 MB column buffer at cfg2).
+//   Here it is one implicit GEMM with the reduction over positions split across CTAs:
+//     A = go tile [128 co x 64 pos], K-major, straight from the NCHW grad_output by TMA (3D map);
+//     B = re-gathered column tile [64 pos x 64*NB kk], MN-major (the same swizzled 128-byte rows
+//         the forward kernel produces, read by the tensor core "transposed");
+//     D = fp32 [co x kk] in TMEM, written once per CTA as a partial; a second kernel folds the
+//         partials in a fixed order (deterministic) and un-permutes kk -> (channel, tap).
+//
+// grad_input / grad_offset / grad_mask still run on the generic kernels in this revision.
+#include "tc_common.cuh"
+
+namespace mdconv {
+namespace tc {
+
+namespace {
+
+constexpr int GW_THREADS = 512;
+constexpr int GW_GATHER_THREADS = 256;
+constexpr int GW_STAGES = 3;
+constexpr int GW_NB = 2;                       // 64-wide kk blocks per CTA tile (N = 128)
+constexpr int GW_GO_BYTES = 2 * 128 * 128;     // two M tiles of [128 co x 64 pos]
+constexpr int GW_COL_BYTES = GW_NB * 64 * 128; // NB blocks of [64 pos x 64 kk]
+
+struct TcGwParams {
+  DevGeom g;
+  const void* xt;
+  const void* off;
+  const void* mask;
+  float* part;   // [S][Co][Kg] fp32, kk in (channel-block, tap, 64 ch) order
+  int nblocks;   // 64-wide kk blocks per group = (Cg/64) * K
+  int n_tiles;   // ceil(nblocks / GW_NB)
+  int m_pairs;   // ceil(Cog / 256)
+  int S;         // splits of the position reduction
+  int pbi;       // 64-position blocks per image
+  int total_pb;  // B * pbi
+};
+
+template <typename T, int ND, bool MOD>
+__global__ void __launch_bounds__(GW_THREADS, 1)
+k_tc_grad_weight(const __grid_constant__ CUtensorMap tmap_go, const TcGwParams prm) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sGo = smem;
+  uint8_t* sCol = sGo + GW_STAGES * GW_GO_BYTES;
+  PlanEntry<ND>* sPlan = reinterpret_cast<PlanEntry<ND>*>(sCol + GW_STAGES * GW_COL_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sPlan) +
+                                               GW_STAGES * 128 * sizeof(PlanEntry<ND>));
+  uint64_t* full_go = bars;
+  uint64_t* full_col = bars + GW_STAGES;
+  uint64_t* empty = bars + 2 * GW_STAGES;
+  uint64_t* done = bars + 3 * GW_STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done + 1);
+
+  const DevGeom& g = prm.g;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // work item
+  int w = blockIdx.x;
+  const int split = w % prm.S; w /= prm.S;
+  const int nt = w % prm.n_tiles; w /= prm.n_tiles;
+  const int mp = w % prm.m_pairs;
+  const int grp = w / prm.m_pairs;
+  const int nb = min(GW_NB, prm.nblocks - nt * GW_NB);     // kk blocks in this tile
+  const int co_left = g.Cog - mp * 256;
+  const int MT = co_left > 128 ? 2 : 1;                      // 128-row M tiles in this CTA
+  const int pb0 = (int)((long long)prm.total_pb * split / prm.S);
+  const int pb1 = (int)((long long)prm.total_pb * (split + 1) / prm.S);
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmap_go);
+    for (int s = 0; s < GW_STAGES; ++s) {
+      ptx::mbar_init(&full_go[s], 1);
+      ptx::mbar_init(&full_col[s], GW_GATHER_THREADS);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    ptx::mbar_init(done, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<256>(tmem_ptr);
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer: grad_output tiles =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      const int co_base = grp * g.Cog + mp * 256;
+      for (int pb = pb0; pb < pb1; ++pb) {
+        const int b = pb / prm.pbi, p0 = (pb - b * prm.pbi) * 64;
+        ptx::mbar_wait(&empty[s], ph ^ 1);
+        ptx::mbar_arrive_expect_tx(&full_go[s], (uint32_t)MT * 16384u);
+        for (int mt = 0; mt < MT; ++mt)
+          ptx::tma_load_3d(sGo + s * GW_GO_BYTES + mt * 16384, &tmap_go, &full_go[s], p0, co_base + mt * 128, b);
+        if (++s == GW_STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = ptx::umma_idesc_f16(umma_fmt<T>(), /*A K-major*/ 0, /*B MN-major*/ 1, 128, nb * 64);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int pb = pb0; pb < pb1; ++pb) {
+        ptx::mbar_wait(&full_go[s], ph);
+        ptx::mbar_wait(&full_col[s], ph);
+        ptx::tc_fence_after_sync();
+        const uint32_t go_addr = ptx::smem_u32(sGo + s * GW_GO_BYTES);
+        const uint32_t col_addr = ptx::smem_u32(sCol + s * GW_COL_BYTES);
+        for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 16 positions per MMA
+            const uint64_t ad = ptx::umma_smem_desc_sw128(go_addr + mt * 16384 + k * 32, 0, 1024);
+            const uint64_t bd = ptx::umma_smem_desc_sw128(col_addr + k * 2048, 8192, 1024);
+            ptx::umma_f16(tmem_base + (uint32_t)(mt * 128), ad, bd, idesc, (pb > pb0 || k > 0) ? 1u : 0u);
+          }
+        }
+        ptx::umma_commit(&empty[s]);
+        if (++s == GW_STAGES) { s = 0; ph ^= 1; }
+      }
+      ptx::umma_commit(done);
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================== epilogue: TMEM -> fp32 partial =====================
+    const int ew = warp & 3;
+    ptx::mbar_wait(done, 0);
+    ptx::tc_fence_after_sync();
+    const int N = nb * 64;
+    for (int mt = 0; mt < MT; ++mt) {
+      const int co = mp * 256 + mt * 128 + ew * 32 + lane;  // within the group
+      const bool valid = co < g.Cog;
+      float* dst = prm.part + ((size_t)split * g.Co + (size_t)grp * g.Cog + (valid ? co : 0)) * g.Kg +
+                   (size_t)nt * GW_NB * 64;
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(mt * 128);
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(taddr + c0, v);
+        ptx::tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(dst + c0 + j) =
+                make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                            __uint_as_float(v[j + 3]));
+        }
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================== gather producers: column tiles =====================
+    const int gt = threadIdx.x - 256;
+    const T* __restrict__ off = reinterpret_cast<const T*>(prm.off);
+    const T* __restrict__ mask = reinterpret_cast<const T*>(prm.mask);
+    const uint4* __restrict__ xq = reinterpret_cast<const uint4*>(prm.xt);
+    const int C8 = g.C >> 3;
+    // the (channel block, tap) of the block this thread plans for
+    const int prow = gt & 63, pblk = (gt >> 6) & 1;
+    const int kkb = nt * GW_NB + pblk;
+    const int pcc = kkb / g.K, ptap = kkb - pcc * g.K;
+    const int pc0 = grp * g.Cg + pcc * BK;
+    int c0_blk[GW_NB];
+#pragma unroll
+    for (int j = 0; j < GW_NB; ++j) c0_blk[j] = grp * g.Cg + ((nt * GW_NB + j) / g.K) * BK;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int pb = pb0; pb < pb1; ++pb) {
+      const int b = pb / prm.pbi, p0 = (pb - b * prm.pbi) * 64;
+      const uint32_t plan_addr = ptx::smem_u32(sPlan + s * 128);
+      if (gt < 128) {
+        RowCoord<ND> rc;
+        const bool v = (pblk < nb) && (p0 + prow < g.P);
+        decode_row<ND>(g, b, p0 + prow, v, rc);
+        const PlanEntry<ND> e = make_plan_entry<T, ND, MOD>(g, off, mask, rc, pc0, ptap, C8);
+        store_plan<ND>(plan_addr + gt * (uint32_t)sizeof(PlanEntry<ND>), e);
+      }
+      ptx::named_bar_sync(1, GW_GATHER_THREADS);
+      ptx::mbar_wait(&empty[s], ph ^ 1);
+      const uint32_t col_addr = ptx::smem_u32(sCol + s * GW_COL_BYTES);
+      const int chunk = gt & 7;
+#pragma unroll
+      for (int j = 0; j < GW_NB; ++j) {
+        if (j < nb) {
+          const uint4* xc = xq + (c0_blk[j] >> 3) + chunk;
+#pragma unroll
+          for (int pass = 0; pass < 2; ++pass) {
+            const int row = pass * 32 + (gt >> 3);
+            const PlanEntry<ND> e = load_plan<ND>(plan_addr + (j * 64 + row) * (uint32_t)sizeof(PlanEntry<ND>));
+            const uint4 r = gather8<T, ND>(xc, e);
+            sts128(col_addr + j * 8192 + sw128(row, chunk), r);
+          }
+        }
+      }
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(&full_col[s]);
+      if (++s == GW_STAGES) { s = 0; ph ^= 1; }
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc<256>(tmem_base);
+}
+
+// gW[co][c][tap] = sum_s part[s][co][((c/64)*K + tap)*64 + c%64]   (fixed order => deterministic)
+template <typename T>
+__global__ void k_reduce_grad_weight(const float* __restrict__ part, T* __restrict__ gw, int S, int Co, int Cg, int K) {
+  const size_t n = (size_t)Co * Cg * K;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int Kg = Cg * K;
+    const int co = (int)(i / Kg);
+    const int r = (int)(i % Kg);
+    const int c = r / K, tap = r - c * K;
+    const size_t src = (size_t)co * Kg + (size_t)((c >> 6) * K + tap) * 64 + (c & 63);
+    float acc = 0.f;
+    for (int s = 0; s < S; ++s) acc += part[(size_t)s * n + src];
+    gw[i] = cvt_to<T, float>(acc);
+  }
+}
+
+int gw_splits(const DevGeom& g) {
+  const int nblocks = (g.Cg / BK) * g.K;
+  const int n_tiles = (nblocks + GW_NB - 1) / GW_NB;
+  const int m_pairs = (g.Cog + 255) / 256;
+  const int items = g.g * m_pairs * n_tiles;
+  const int pbi = (g.P + 63) / 64;
+  const long long total_pb = (long long)g.B * pbi;
+  int S = (sm_count() + items - 1) / items;
+  if (S < 1) S = 1;
+  if (S > 32) S = 32;
+  if ((long long)S > total_pb) S = (int)total_pb;
+  return S;
+}
+
+template <int ND>
+size_t gw_smem_bytes() {
+  return 1024 + (size_t)GW_STAGES * (GW_GO_BYTES + GW_COL_BYTES) + (size_t)GW_STAGES * 128 * sizeof(PlanEntry<ND>) +
+         (3 * GW_STAGES + 1) * sizeof(uint64_t) + 16;
+}
+
+template <typename T, int ND, bool MOD>
+void launch_grad_weight(const CUtensorMap& tmap, const TcGwParams& prm, int grid, LaunchCtx& ctx) {
+  const size_t smem = gw_smem_bytes<ND>();
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e =
+        cudaFuncSetAttribute(k_tc_grad_weight<T, ND, MOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess && ctx.err == cudaSuccess) ctx.err = e;
+    configured = true;
+  }
+  ProfScope prof(ctx, "tc_grad_weight");
+  k_tc_grad_weight<T, ND, MOD><<<grid, GW_THREADS, smem, ctx.stream>>>(tmap, prm);
+  MDCONV_CHECK_LAUNCH(ctx);
+}
+
+}  // namespace
+
+bool tensor_backward_supported(const DevGeom& g, int dtype) {
+  (void)dtype;
+  if (g.P % 8 != 0) return false;  // TMA global strides of grad_output must be multiples of 16 bytes
+  return true;
+}
+
+size_t tensor_backward_workspace(const DevGeom& g) {
+  const size_t xt = align256((size_t)g.B * g.C * g.IN * 2);
+  const size_t part = align256((size_t)gw_splits(g) * g.Co * g.Kg * sizeof(float));
+  return xt + part + generic_workspace_bytes(g, MDCONV_F16, 1);
+}
+
+template <typename T>
+void tensor_backward_t(const DevGeom& g, const void* x, const void* w, const void* off, const void* mask,
+                       const void* go, void* gx, void* gw, void* gb, void* goff, void* gmask, void* ws, LaunchCtx& ctx) {
+  char* base = reinterpret_cast<char*>(ws);
+  T* xt = reinterpret_cast<T*>(base);
+  base += align256((size_t)g.B * g.C * g.IN * sizeof(T));
+  const int S = gw_splits(g);
+  float* part = reinterpret_cast<float*>(base);
+  base += align256((size_t)S * g.Co * g.Kg * sizeof(float));
+  void* generic_ws = base;
+
+  // grad_input / grad_offset / grad_mask (+ grad_bias): generic kernels for now
+  const int dtype = std::is_same<T, __half>::value ? MDCONV_F16 : MDCONV_BF16;
+  generic_backward(g, dtype, x, w, off, mask, go, gx, gw, gb, goff, gmask, generic_ws, ctx,
+                   GENERIC_BWD_DATA | GENERIC_BWD_BIAS);
+
+  // grad_weight on the tensor cores
+  launch_to_channels_last<T>((const T*)x, xt, g.B, g.C, g.IN, ctx);
+  TcGwParams prm;
+  prm.g = g;
+  prm.xt = xt; prm.off = off; prm.mask = mask; prm.part = part;
+  prm.nblocks = (g.Cg / BK) * g.K;
+  prm.n_tiles = (prm.nblocks + GW_NB - 1) / GW_NB;
+  prm.m_pairs = (g.Cog + 255) / 256;
+  prm.S = S;
+  prm.pbi = (g.P + 63) / 64;
+  prm.total_pb = g.B * prm.pbi;
+  const int grid = g.g * prm.m_pairs * prm.n_tiles * S;
+
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) {
+    if (ctx.err == cudaSuccess) ctx.err = cudaErrorNotSupported;
+    return;
+  }
+  CUtensorMap tmap;
+  const cuuint64_t dims[3] = {(cuuint64_t)g.P, (cuuint64_t)g.Co, (cuuint64_t)g.B};
+  const cuuint64_t strides[2] = {(cuuint64_t)g.P * sizeof(T), (cuuint64_t)g.Co * g.P * sizeof(T)};
+  const cuuint32_t box[3] = {64, 128, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = enc(&tmap, tmap_dtype<T>(), 3, const_cast<void*>(go), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    if (ctx.err == cudaSuccess) ctx.err = cudaErrorInvalidValue;
+    return;
+  }
+  if (g.nd == 2) {
+    if (g.modulated) launch_grad_weight<T, 2, true>(tmap, prm, grid, ctx);
+    else launch_grad_weight<T, 2, false>(tmap, prm, grid, ctx);
+  } else {
+    if (g.modulated) launch_grad_weight<T, 3, true>(tmap, prm, grid, ctx);
+    else launch_grad_weight<T, 3, false>(tmap, prm, grid, ctx);
+  }
+  {
+    ProfScope prof(ctx, "reduce_grad_weight");
+    const size_t n = (size_t)g.Co * g.Kg;
+    const int blocks = (int)((n + 255) / 256 > 1184 ? 1184 : (n + 255) / 256);
+    k_reduce_grad_weight<T><<<blocks, 256, 0, ctx.stream>>>(part, (T*)gw, S, g.Co, g.Cg, g.K);
+    MDCONV_CHECK_LAUNCH(ctx);
+  }
+}
+
+template void tensor_backward_t<__half>(const DevGeom&, const void*, const void*, const void*, const void*,
+                                        const void*, void*, void*, void*, void*, void*, void*, LaunchCtx&);
+template void tensor_backward_t<__nv_bfloat16>(const DevGeom&, const void*, const void*, const void*, const void*,
+                                               const void*, void*, void*, void*, void*, void*, void*, LaunchCtx&);
+
+}  // namespace tc
+}  // namespace mdconv

@@ -20,17 +20,18 @@
 // by two small pre-pass kernels into the caller's workspace.
 //
 // Replaces reference K1-K4 + G1 (src/mdeformable_conv.cu:38-87,172-184 and twins).
-#include <type_traits>
-
-#include "sm100_ptx.cuh"
+#include "tc_common.cuh"
 #include "tensor_path.cuh"
 
 namespace mdconv {
 
+using tc::PlanEntry;
+using tc::RowCoord;
+
 namespace {
 
 constexpr int TC_BM = 128;        // pixels per tile (UMMA M)
-constexpr int TC_BK = 64;         // K elements per block = 128 bytes = one swizzle row
+constexpr int TC_BK = tc::BK;     // K elements per block = 128 bytes = one swizzle row
 constexpr int TC_STAGES = 3;
 constexpr int TC_MAX_BN = 256;
 constexpr int TC_THREADS = 512;
@@ -38,7 +39,7 @@ constexpr int TC_GATHER_THREADS = 256;
 constexpr int TC_A_BYTES = TC_BM * 128;
 constexpr int TC_B_BYTES = TC_MAX_BN * 128;
 
-size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+using tc::align256;
 
 struct TcFwdParams {
   DevGeom g;
@@ -52,58 +53,6 @@ struct TcFwdParams {
   int ccs;           // channel blocks per group (Cg / 64)
   int kblocks;       // ccs * K
 };
-
-template <int ND>
-struct __align__(16) PlanEntry {  // one (pixel row, tap): corner addresses (uint4 units, channel offset excluded) + weights
-  int idx[1 << ND];
-  uint32_t w[1 << ND];  // __half2 / __nv_bfloat162 pair (HALF2 math) or float bits (fp32 math)
-};
-
-template <typename T> struct Vec2;
-template <> struct Vec2<__half> { using type = __half2; };
-template <> struct Vec2<__nv_bfloat16> { using type = __nv_bfloat162; };
-
-__device__ __forceinline__ uint32_t pack_w(float w, __half) {
-  __half2 h = __float2half2_rn(w);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-__device__ __forceinline__ uint32_t pack_w(float w, __nv_bfloat16) { return __float_as_uint(w); }
-
-// acc += w * v for 8 channels held in a uint4.  fp16: packed HFMA2 (weights as half2);
-// bf16: fp32 FMAs (8 mantissa bits are too few to accumulate four products in).
-__device__ __forceinline__ void fma8(float (&accf)[8], uint4& acch, uint32_t w, const uint4& v, __half) {
-  const __half2 wh = *reinterpret_cast<const __half2*>(&w);
-  __half2* a = reinterpret_cast<__half2*>(&acch);
-  const __half2* x = reinterpret_cast<const __half2*>(&v);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) a[i] = __hfma2(wh, x[i], a[i]);
-  (void)accf;
-}
-__device__ __forceinline__ void fma8(float (&accf)[8], uint4& acch, uint32_t w, const uint4& v, __nv_bfloat16) {
-  const float wf = __uint_as_float(w);
-  const uint32_t* x = reinterpret_cast<const uint32_t*>(&v);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    accf[2 * i] = fmaf(wf, __uint_as_float(x[i] << 16), accf[2 * i]);
-    accf[2 * i + 1] = fmaf(wf, __uint_as_float(x[i] & 0xFFFF0000u), accf[2 * i + 1]);
-  }
-  (void)acch;
-}
-__device__ __forceinline__ uint4 finish8(const float (&accf)[8], const uint4& acch, __half) {
-  (void)accf;
-  return acch;
-}
-__device__ __forceinline__ uint4 finish8(const float (&accf)[8], const uint4& acch, __nv_bfloat16) {
-  (void)acch;
-  uint4 r;
-  uint32_t* o = reinterpret_cast<uint32_t*>(&r);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    __nv_bfloat162 p = __floats2bfloat162_rn(accf[2 * i], accf[2 * i + 1]);
-    o[i] = *reinterpret_cast<uint32_t*>(&p);
-  }
-  return r;
-}
 
 template <typename T, int ND, bool MOD>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -169,7 +118,7 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const TcFwdParams prm) 
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr int fmt = sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
+      constexpr int fmt = tc::umma_fmt<T>();
       const uint32_t idesc = ptx::umma_idesc_f16(fmt, 0, 0, TC_BM, BN);
       int s = 0;
       uint32_t ph = 0;
@@ -249,98 +198,33 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const TcFwdParams prm) 
       const int mt = t % prm.m_tiles;
       const int grp = (t / prm.m_tiles) / prm.n_tiles;
       // row metadata for the plan threads (gt < 128 owns pixel row gt of the tile)
-      int rb = 0, rp = 0, base[ND];
-      bool rvalid = false;
+      RowCoord<ND> rc;
+      rc.valid = false;
       if (gt < TC_BM) {
         const long long gp = (long long)mt * TC_BM + gt;
-        rvalid = gp < total_pix;
-        if (rvalid) {
-          rb = (int)(gp / g.P);
-          rp = (int)(gp % g.P);
-        }
-        int o[3];
-        if (ND == 2) {
-          o[1] = rp % g.out[1]; o[0] = rp / g.out[1];
-        } else {
-          o[2] = rp % g.out[2]; const int r2 = rp / g.out[2]; o[1] = r2 % g.out[1]; o[0] = r2 / g.out[1];
-        }
-#pragma unroll
-        for (int a = 0; a < ND; ++a) base[a] = o[a] * g.s[a] - g.p[a];
+        const bool v = gp < total_pix;
+        tc::decode_row<ND>(g, v ? (int)(gp / g.P) : 0, v ? (int)(gp % g.P) : 0, v, rc);
       }
       for (int kb = 0; kb < prm.kblocks; ++kb) {
         const int cc = kb / g.K, tap = kb - cc * g.K;
         const int c0 = grp * g.Cg + cc * TC_BK;  // first channel of this K-block
-        PlanEntry<ND>* plan = sPlan + s * TC_BM;
+        const uint32_t plan_addr = ptx::smem_u32(sPlan + s * TC_BM);
         if (gt < TC_BM) {
-          PlanEntry<ND> e;
-#pragma unroll
-          for (int c = 0; c < (1 << ND); ++c) { e.idx[c] = 0; e.w[c] = 0u; }
-          if (rvalid) {
-            const int dgi = c0 / g.Cdg;
-            int tt[3];
-            if (ND == 2) {
-              tt[1] = tap % g.k[1]; tt[0] = tap / g.k[1];
-            } else {
-              tt[2] = tap % g.k[2]; const int q = tap / g.k[2]; tt[1] = q % g.k[1]; tt[0] = q / g.k[1];
-            }
-            const T* op = off + ((size_t)rb * g.dg * g.K + (size_t)dgi * g.K + tap) * ND * g.P + rp;
-            int lo[ND];
-            float fr[ND];
-            bool in_range = true;
-#pragma unroll
-            for (int a = 0; a < ND; ++a) {
-              const float pos = (float)(base[a] + tt[a] * g.d[a]) + ld_as<float>(op + (size_t)a * g.P);
-              const float fl = floorf(pos);
-              lo[a] = (int)fl;
-              fr[a] = pos - fl;
-              in_range = in_range && (pos > -1.f) && (pos < (float)g.in[a]);
-            }
-            if (in_range) {
-              float m = 1.f;
-              if (MOD) m = ld_as<float>(mask + ((size_t)rb * g.dg * g.K + (size_t)dgi * g.K + tap) * g.P + rp);
-#pragma unroll
-              for (int c = 0; c < (1 << ND); ++c) {
-                float w = m;
-                bool ok = true;
-                int pix = 0;
-#pragma unroll
-                for (int a = 0; a < ND; ++a) {
-                  const int hi = (c >> a) & 1;
-                  const int ia = lo[a] + hi;
-                  ok = ok && (hi ? (ia <= g.in[a] - 1) : (ia >= 0));
-                  w *= hi ? fr[a] : (1.f - fr[a]);
-                  pix = pix * g.in[a] + ia;
-                }
-                if (ok) {
-                  e.idx[c] = (rb * g.IN + pix) * C8;
-                  e.w[c] = pack_w(w, T());
-                }
-              }
-            }
-          }
-          plan[gt] = e;
+          const PlanEntry<ND> e = tc::make_plan_entry<T, ND, MOD>(g, off, mask, rc, c0, tap, C8);
+          tc::store_plan<ND>(plan_addr + gt * (uint32_t)sizeof(PlanEntry<ND>), e);
         }
         ptx::named_bar_sync(1, TC_GATHER_THREADS);  // plan visible to all gather warps
 
         ptx::mbar_wait(&empty[s], ph ^ 1);          // MMA has finished reading A[s]
-        uint8_t* a_tile = sA + s * TC_A_BYTES;
+        const uint32_t a_addr = ptx::smem_u32(sA + s * TC_A_BYTES);
         const int chunk = lane & 7;
         const uint4* xc = xq + (c0 >> 3) + chunk;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int row = gw * 16 + j * 4 + (lane >> 3);
-          const PlanEntry<ND> e = plan[row];
-          float accf[8];
-          uint4 acch = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) accf[i] = 0.f;
-          uint4 v[1 << ND];
-#pragma unroll
-          for (int c = 0; c < (1 << ND); ++c) v[c] = __ldg(xc + e.idx[c]);
-#pragma unroll
-          for (int c = 0; c < (1 << ND); ++c) fma8(accf, acch, e.w[c], v[c], T());
-          const uint4 r = finish8(accf, acch, T());
-          *reinterpret_cast<uint4*>(a_tile + row * 128 + ((chunk ^ (row & 7)) << 4)) = r;
+          const PlanEntry<ND> e = tc::load_plan<ND>(plan_addr + row * (uint32_t)sizeof(PlanEntry<ND>));
+          const uint4 r = tc::gather8<T, ND>(xc, e);
+          tc::sts128(a_addr + tc::sw128(row, chunk), r);
         }
         ptx::fence_proxy_async_smem();
         ptx::mbar_arrive(&full_a[s]);
@@ -401,9 +285,77 @@ __global__ void k_reorder_weight(const T* __restrict__ w, T* __restrict__ wr, in
 }
 
 // ---- host side --------------------------------------------------------------------------------
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int pick_bn(const DevGeom& g) { return g.Cog <= TC_MAX_BN ? g.Cog : TC_MAX_BN; }
+
+template <int ND>
+size_t fwd_smem_bytes() {
+  return 1024 + (size_t)TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + (size_t)TC_STAGES * TC_BM * sizeof(PlanEntry<ND>) +
+         (3 * TC_STAGES + 4) * sizeof(uint64_t) + 16;
+}
+
+template <typename T, int ND, bool MOD>
+void launch_tc_forward(const CUtensorMap& tmap, const TcFwdParams& prm, LaunchCtx& ctx) {
+  const size_t smem = fwd_smem_bytes<ND>();
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_tc_forward<T, ND, MOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess && ctx.err == cudaSuccess) ctx.err = e;
+    configured = true;
+  }
+  const int grid = prm.total_tiles < tc::sm_count() ? prm.total_tiles : tc::sm_count();
+  ProfScope prof(ctx, "tc_forward");
+  k_tc_forward<T, ND, MOD><<<grid, TC_THREADS, smem, ctx.stream>>>(tmap, prm);
+  MDCONV_CHECK_LAUNCH(ctx);
+}
+
+template <typename T>
+void tensor_forward_t(const DevGeom& g, const void* x, const void* w, const void* bias, const void* off,
+                      const void* mask, void* y, void* ws, LaunchCtx& ctx) {
+  T* xt = reinterpret_cast<T*>(ws);
+  T* wr = reinterpret_cast<T*>(reinterpret_cast<char*>(ws) + align256((size_t)g.B * g.C * g.IN * sizeof(T)));
+  tc::launch_to_channels_last<T>((const T*)x, xt, g.B, g.C, g.IN, ctx);
+  tc::launch_reorder_weight<T>((const T*)w, wr, g.Co, g.Cg, g.K, ctx);
+  TcFwdParams prm;
+  prm.g = g;
+  prm.xt = xt; prm.off = off; prm.mask = mask; prm.bias = bias; prm.y = y;
+  prm.BN = pick_bn(g);
+  const long long total_pix = (long long)g.B * g.P;
+  prm.m_tiles = (int)((total_pix + TC_BM - 1) / TC_BM);
+  prm.n_tiles = g.Cog / prm.BN;
+  prm.total_tiles = prm.m_tiles * prm.n_tiles * g.g;
+  prm.ccs = g.Cg / TC_BK;
+  prm.kblocks = prm.ccs * g.K;
+
+  tc::PFN_encodeTiled enc = tc::get_encode_fn();
+  if (!enc) {
+    if (ctx.err == cudaSuccess) ctx.err = cudaErrorNotSupported;
+    return;
+  }
+  CUtensorMap tmap;
+  const cuuint64_t dims[2] = {(cuuint64_t)g.Kg, (cuuint64_t)g.Co};
+  const cuuint64_t strides[1] = {(cuuint64_t)g.Kg * sizeof(T)};
+  const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)prm.BN};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapDataType dt = tc::tmap_dtype<T>();
+  const CUresult r = enc(&tmap, dt, 2, wr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    if (ctx.err == cudaSuccess) ctx.err = cudaErrorInvalidValue;
+    return;
+  }
+  if (g.nd == 2) {
+    if (g.modulated) launch_tc_forward<T, 2, true>(tmap, prm, ctx);
+    else launch_tc_forward<T, 2, false>(tmap, prm, ctx);
+  } else {
+    if (g.modulated) launch_tc_forward<T, 3, true>(tmap, prm, ctx);
+    else launch_tc_forward<T, 3, false>(tmap, prm, ctx);
+  }
+}
+
+}  // namespace
+
+namespace tc {
 
 PFN_encodeTiled get_encode_fn() {
   static PFN_encodeTiled fn = nullptr;
@@ -430,101 +382,41 @@ int sm_count() {
   return n;
 }
 
-int pick_bn(const DevGeom& g) { return g.Cog <= TC_MAX_BN ? g.Cog : TC_MAX_BN; }
-
-template <int ND>
-size_t fwd_smem_bytes() {
-  return 1024 + (size_t)TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + (size_t)TC_STAGES * TC_BM * sizeof(PlanEntry<ND>) +
-         (3 * TC_STAGES + 4) * sizeof(uint64_t) + 16;
-}
-
-template <typename T, int ND, bool MOD>
-void launch_tc_forward(const CUtensorMap& tmap, const TcFwdParams& prm, LaunchCtx& ctx) {
-  const size_t smem = fwd_smem_bytes<ND>();
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_tc_forward<T, ND, MOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess && ctx.err == cudaSuccess) ctx.err = e;
-    configured = true;
-  }
-  const int grid = prm.total_tiles < sm_count() ? prm.total_tiles : sm_count();
-  ProfScope prof(ctx, "tc_forward");
-  k_tc_forward<T, ND, MOD><<<grid, TC_THREADS, smem, ctx.stream>>>(tmap, prm);
+template <typename T>
+void launch_to_channels_last(const T* x, T* xt, int B, int C, int IN, LaunchCtx& ctx) {
+  ProfScope prof(ctx, "to_channels_last");
+  dim3 grid((unsigned)((IN + 63) / 64), (unsigned)((C + 63) / 64), (unsigned)B);
+  k_to_channels_last<T><<<grid, 256, 0, ctx.stream>>>(x, xt, C, IN);
   MDCONV_CHECK_LAUNCH(ctx);
 }
-
 template <typename T>
-void tensor_forward_t(const DevGeom& g, const void* x, const void* w, const void* bias, const void* off,
-                      const void* mask, void* y, void* ws, LaunchCtx& ctx) {
-  T* xt = reinterpret_cast<T*>(ws);
-  T* wr = reinterpret_cast<T*>(reinterpret_cast<char*>(ws) + align256((size_t)g.B * g.C * g.IN * sizeof(T)));
-  {
-    ProfScope prof(ctx, "to_channels_last");
-    dim3 grid((unsigned)((g.IN + 63) / 64), (unsigned)((g.C + 63) / 64), (unsigned)g.B);
-    k_to_channels_last<T><<<grid, 256, 0, ctx.stream>>>((const T*)x, xt, g.C, g.IN);
-    MDCONV_CHECK_LAUNCH(ctx);
-  }
-  {
-    ProfScope prof(ctx, "reorder_weight");
-    const size_t n = (size_t)g.Co * g.Kg;
-    const int blocks = (int)((n + 255) / 256 > 1184 ? 1184 : (n + 255) / 256);
-    k_reorder_weight<T><<<blocks, 256, 0, ctx.stream>>>((const T*)w, wr, g.Co, g.Cg, g.K);
-    MDCONV_CHECK_LAUNCH(ctx);
-  }
-  TcFwdParams prm;
-  prm.g = g;
-  prm.xt = xt; prm.off = off; prm.mask = mask; prm.bias = bias; prm.y = y;
-  prm.BN = pick_bn(g);
-  const long long total_pix = (long long)g.B * g.P;
-  prm.m_tiles = (int)((total_pix + TC_BM - 1) / TC_BM);
-  prm.n_tiles = g.Cog / prm.BN;
-  prm.total_tiles = prm.m_tiles * prm.n_tiles * g.g;
-  prm.ccs = g.Cg / TC_BK;
-  prm.kblocks = prm.ccs * g.K;
-
-  PFN_encodeTiled enc = get_encode_fn();
-  if (!enc) {
-    if (ctx.err == cudaSuccess) ctx.err = cudaErrorNotSupported;
-    return;
-  }
-  CUtensorMap tmap;
-  const cuuint64_t dims[2] = {(cuuint64_t)g.Kg, (cuuint64_t)g.Co};
-  const cuuint64_t strides[1] = {(cuuint64_t)g.Kg * sizeof(T)};
-  const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)prm.BN};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUtensorMapDataType dt =
-      std::is_same<T, __half>::value ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-  const CUresult r = enc(&tmap, dt, 2, wr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    if (ctx.err == cudaSuccess) ctx.err = cudaErrorInvalidValue;
-    return;
-  }
-  if (g.nd == 2) {
-    if (g.modulated) launch_tc_forward<T, 2, true>(tmap, prm, ctx);
-    else launch_tc_forward<T, 2, false>(tmap, prm, ctx);
-  } else {
-    if (g.modulated) launch_tc_forward<T, 3, true>(tmap, prm, ctx);
-    else launch_tc_forward<T, 3, false>(tmap, prm, ctx);
-  }
+void launch_reorder_weight(const T* w, T* wr, int Co, int Cg, int K, LaunchCtx& ctx) {
+  ProfScope prof(ctx, "reorder_weight");
+  const size_t n = (size_t)Co * Cg * K;
+  const int blocks = (int)((n + 255) / 256 > 1184 ? 1184 : (n + 255) / 256);
+  k_reorder_weight<T><<<blocks, 256, 0, ctx.stream>>>(w, wr, Co, Cg, K);
+  MDCONV_CHECK_LAUNCH(ctx);
 }
+template void launch_to_channels_last<__half>(const __half*, __half*, int, int, int, LaunchCtx&);
+template void launch_to_channels_last<__nv_bfloat16>(const __nv_bfloat16*, __nv_bfloat16*, int, int, int, LaunchCtx&);
+template void launch_reorder_weight<__half>(const __half*, __half*, int, int, int, LaunchCtx&);
+template void launch_reorder_weight<__nv_bfloat16>(const __nv_bfloat16*, __nv_bfloat16*, int, int, int, LaunchCtx&);
 
-}  // namespace
+}  // namespace tc
 
 bool tensor_path_supported(const DevGeom& g, int dtype, int backward) {
-  if (backward) return false;  // backward still runs on the generic kernels
   if (dtype != MDCONV_F16 && dtype != MDCONV_BF16) return false;
   if (g.Cg % TC_BK != 0 || g.Cdg % TC_BK != 0) return false;
+  if ((long long)g.B * g.IN * (g.C / 8) > 2147483647LL) return false;
+  if (backward) return tc::tensor_backward_supported(g, dtype);
   if (g.Cog % 32 != 0) return false;
   if (g.Cog > TC_MAX_BN && g.Cog % TC_MAX_BN != 0) return false;
-  if ((long long)g.B * g.IN * (g.C / 8) > 2147483647LL) return false;
   return true;
 }
 
 size_t tensor_workspace_bytes(const DevGeom& g, int dtype, int backward) {
   (void)dtype;
-  if (backward) return 0;
+  if (backward) return tc::tensor_backward_workspace(g);
   return align256((size_t)g.B * g.C * g.IN * 2) + align256((size_t)g.Co * g.Kg * 2);
 }
 
@@ -534,9 +426,10 @@ void tensor_forward(const DevGeom& g, int dtype, const void* x, const void* w, c
   else tensor_forward_t<__nv_bfloat16>(g, x, w, bias, off, mask, y, ws, ctx);
 }
 
-void tensor_backward(const DevGeom&, int, const void*, const void*, const void*, const void*, const void*, void*,
-                     void*, void*, void*, void*, void*, LaunchCtx& ctx) {
-  if (ctx.err == cudaSuccess) ctx.err = cudaErrorNotSupported;
+void tensor_backward(const DevGeom& g, int dtype, const void* x, const void* w, const void* off, const void* mask,
+                     const void* go, void* gx, void* gw, void* gb, void* goff, void* gmask, void* ws, LaunchCtx& ctx) {
+  if (dtype == MDCONV_F16) tc::tensor_backward_t<__half>(g, x, w, off, mask, go, gx, gw, gb, goff, gmask, ws, ctx);
+  else tc::tensor_backward_t<__nv_bfloat16>(g, x, w, off, mask, go, gx, gw, gb, goff, gmask, ws, ctx);
 }
 
 }  // namespace mdconv

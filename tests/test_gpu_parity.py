@@ -72,19 +72,20 @@ def test_generic_path_matches_oracle(case, dtype):
 
 TENSOR_CASES = [
     Case("tc_m2d_c64", 2, True, B=2, C=64, Co=64, size=(12, 11), seed=50),
-    Case("tc_m2d_c128_co256_nobias", 2, True, B=3, C=128, Co=256, size=(9, 14), bias=False, seed=51),
+    Case("tc_m2d_c128_co256_nobias", 2, True, B=3, C=128, Co=256, size=(8, 14), bias=False, seed=51),
     Case("tc_m2d_stride2_dg2", 2, True, B=2, C=128, Co=128, size=(15, 13), s=(2, 2), dg=2, seed=52),
     Case("tc_m2d_dil2_sigma4", 2, True, B=1, C=64, Co=64, size=(16, 16), p=(2, 2), d=(2, 2), sigma=4.0, seed=53),
     Case("tc_m2d_integer_grid", 2, True, B=2, C=64, Co=64, size=(8, 9), sigma=0.0, seed=54),
     Case("tc_m2d_half_grid", 2, True, B=2, C=64, Co=64, size=(8, 9), sigma=0.5, seed=55),
     Case("tc_m2d_all_oob", 2, True, B=1, C=64, Co=64, size=(8, 8), offset_bias=1e4, seed=56),
-    Case("tc_m2d_g2", 2, True, B=2, C=128, Co=128, size=(10, 10), g=2, dg=2, seed=57),
-    Case("tc_d2d_c64", 2, False, B=2, C=64, Co=64, size=(12, 11), seed=60),
+    Case("tc_m2d_g2", 2, True, B=2, C=128, Co=128, size=(10, 12), g=2, dg=2, seed=57),
+    Case("tc_d2d_c64", 2, False, B=2, C=64, Co=64, size=(12, 12), seed=60),
+    Case("tc_m2d_c256_multi_tile", 2, True, B=2, C=256, Co=256, size=(24, 20), bias=False, seed=63),
     Case("tc_d2d_integer_grid", 2, False, B=2, C=64, Co=64, size=(8, 9), sigma=0.0, seed=61),
     Case("tc_d2d_k1x3", 2, False, B=2, C=64, Co=64, size=(8, 9), k=(1, 3), p=(0, 1), seed=62),
     Case("tc_m3d_c64", 3, True, B=1, C=64, Co=64, size=(4, 6, 5), k=(3, 3, 3), s=(1, 1, 1), p=(1, 1, 1),
          d=(1, 1, 1), seed=70),
-    Case("tc_d3d_c64_half_grid", 3, False, B=1, C=64, Co=64, size=(4, 5, 5), k=(3, 3, 3), s=(1, 1, 1),
+    Case("tc_d3d_c64_half_grid", 3, False, B=1, C=64, Co=64, size=(4, 5, 6), k=(3, 3, 3), s=(1, 1, 1),
          p=(1, 1, 1), d=(1, 1, 1), sigma=0.5, seed=71),
 ]
 
