@@ -221,5 +221,17 @@ void tensor_backward_t(const DevGeom& g, const void* x, const void* w, const voi
 size_t tensor_backward_workspace(const DevGeom& g);
 bool tensor_backward_supported(const DevGeom& g, int dtype);
 
+// grad_offset / grad_mask (tensor_bwd_sample.cu)
+bool grad_sample_supported(const DevGeom& g);
+template <typename T>
+void tensor_grad_sample(const DevGeom& g, const T* xt, const T* wr, const void* off, const void* mask, const void* go,
+                        void* goff, void* gmask, LaunchCtx& ctx);
+// grad_input (tensor_bwd_input.cu)
+bool grad_input_supported(const DevGeom& g);
+size_t grad_input_workspace(const DevGeom& g);
+template <typename T>
+void tensor_grad_input(const DevGeom& g, const void* w, const void* off, const void* mask, const void* go, void* gx,
+                       void* ws, LaunchCtx& ctx);
+
 }  // namespace tc
 }  // namespace mdconv

@@ -229,7 +229,7 @@ int gw_splits(const DevGeom& g) {
   const int items = g.g * m_pairs * n_tiles;
   const int pbi = (g.P + 63) / 64;
   const long long total_pb = (long long)g.B * pbi;
-  int S = (sm_count() + items - 1) / items;
+  int S = sm_count() / items;  // one wave: S * items <= number of SMs
   if (S < 1) S = 1;
   if (S > 32) S = 32;
   if ((long long)S > total_pb) S = (int)total_pb;
@@ -265,10 +265,14 @@ bool tensor_backward_supported(const DevGeom& g, int dtype) {
   return true;
 }
 
+static bool data_on_tensor_cores(const DevGeom& g) { return grad_sample_supported(g) && grad_input_supported(g); }
+
 size_t tensor_backward_workspace(const DevGeom& g) {
   const size_t xt = align256((size_t)g.B * g.C * g.IN * 2);
+  const size_t wr = align256((size_t)g.Co * g.Kg * 2);
   const size_t part = align256((size_t)gw_splits(g) * g.Co * g.Kg * sizeof(float));
-  return xt + part + generic_workspace_bytes(g, MDCONV_F16, 1);
+  const size_t data = data_on_tensor_cores(g) ? grad_input_workspace(g) : generic_workspace_bytes(g, MDCONV_F16, 1);
+  return xt + wr + part + data;
 }
 
 template <typename T>
@@ -277,18 +281,18 @@ void tensor_backward_t(const DevGeom& g, const void* x, const void* w, const voi
   char* base = reinterpret_cast<char*>(ws);
   T* xt = reinterpret_cast<T*>(base);
   base += align256((size_t)g.B * g.C * g.IN * sizeof(T));
+  T* wr = reinterpret_cast<T*>(base);
+  base += align256((size_t)g.Co * g.Kg * sizeof(T));
   const int S = gw_splits(g);
   float* part = reinterpret_cast<float*>(base);
   base += align256((size_t)S * g.Co * g.Kg * sizeof(float));
-  void* generic_ws = base;
-
-  // grad_input / grad_offset / grad_mask (+ grad_bias): generic kernels for now
+  void* data_ws = base;
   const int dtype = std::is_same<T, __half>::value ? MDCONV_F16 : MDCONV_BF16;
-  generic_backward(g, dtype, x, w, off, mask, go, gx, gw, gb, goff, gmask, generic_ws, ctx,
-                   GENERIC_BWD_DATA | GENERIC_BWD_BIAS);
+  const bool data_tc = data_on_tensor_cores(g);
 
-  // grad_weight on the tensor cores
   launch_to_channels_last<T>((const T*)x, xt, g.B, g.C, g.IN, ctx);
+
+  // ---- grad_weight first (it is what a data-parallel caller all-reduces) ----
   TcGwParams prm;
   prm.g = g;
   prm.xt = xt; prm.off = off; prm.mask = mask; prm.part = part;
@@ -330,6 +334,17 @@ void tensor_backward_t(const DevGeom& g, const void* x, const void* w, const voi
     const int blocks = (int)((n + 255) / 256 > 1184 ? 1184 : (n + 255) / 256);
     k_reduce_grad_weight<T><<<blocks, 256, 0, ctx.stream>>>(part, (T*)gw, S, g.Co, g.Cg, g.K);
     MDCONV_CHECK_LAUNCH(ctx);
+  }
+
+  // ---- grad_offset / grad_mask / grad_input (+ grad_bias) ----
+  if (data_tc) {
+    launch_reorder_weight<T>((const T*)w, wr, g.Co, g.Cg, g.K, ctx);
+    tensor_grad_sample<T>(g, xt, wr, off, mask, go, goff, gmask, ctx);
+    tensor_grad_input<T>(g, w, off, mask, go, gx, data_ws, ctx);
+    generic_backward(g, dtype, x, w, off, mask, go, gx, gw, gb, goff, gmask, nullptr, ctx, GENERIC_BWD_BIAS);
+  } else {
+    generic_backward(g, dtype, x, w, off, mask, go, gx, gw, gb, goff, gmask, data_ws, ctx,
+                     GENERIC_BWD_DATA | GENERIC_BWD_BIAS);
   }
 }
 

@@ -1,0 +1,511 @@
+// tensor_bwd_input.cu -- tcgen05 kernel for grad_input (fp16 / bf16), atomics-free.
+//
+// Reference: the col2im half of the fused gradient kernels (src/mdeformable_conv.cu:282-293 and
+// twins): one thread per column element, 4 (2D) / 8 (3D) atomicAdd into grad_input each, fed by a
+// materialised grad_columns buffer (G2, :417-419).
+//
+// Here the scatter is turned into a gather.  A small inverse index (CSR) is built per call:
+//     bin (sample, deformable group, input position, tap)  ->  list of (output position, weight)
+// with weight = interpolation weight x mask of the corner that touches that input position.  Then
+//     G[pos, (tap, co)] = sum over the bin's entries of weight * go[entry position, co]
+//     grad_input[pos, c] = sum over (tap, co) of G[pos, (tap, co)] * W[co, c, tap]
+// is one implicit GEMM: G tiles are gathered straight into the swizzled UMMA A operand (never in
+// HBM), W^T slices come by TMA, the accumulator lives in TMEM and every grad_input element is
+// written exactly once (deterministic: bin entries are sorted).
+//
+//   warp 0      TMA producer: transposed-weight slices [BN channels x 64 co] -> smem ring
+//   warp 1      MMA issuer (M = 128 input positions, N = BN channels, K = 64 co per block)
+//   warp 2      TMEM allocator
+//   warps 4-7   epilogue: tcgen05.ld -> convert -> NCHW stores
+//   warps 8-15  gather producers: 8 lanes per input position walk the bin, 16-byte channels-last
+//               loads of grad_output, fp32 accumulate, 16-byte stores into the swizzled A tile
+#include <cub/device/device_scan.cuh>
+
+#include "tc_common.cuh"
+
+namespace mdconv {
+namespace tc {
+
+namespace {
+
+constexpr int GI_BM = 128;
+constexpr int GI_STAGES = 3;
+constexpr int GI_MAX_BN = 256;
+constexpr int GI_THREADS = 512;
+constexpr int GI_GATHER_THREADS = 256;
+constexpr int GI_A_BYTES = GI_BM * 128;
+constexpr int GI_B_BYTES = GI_MAX_BN * 128;
+
+struct BinEntry {
+  int row;   // b * P + output position: row of the channels-last grad_output
+  float w;   // interpolation weight x mask
+};
+
+// ---- inverse index ----------------------------------------------------------------------------
+// One thread per (sample, deformable group, output position, tap).  FILL == false: count the entries
+// of each bin; FILL == true: place them (slot taken from the remaining count).
+template <typename T, int ND, bool MOD, bool FILL>
+__global__ void __launch_bounds__(256) k_bin_entries(const DevGeom g, const T* __restrict__ off,
+                                                     const T* __restrict__ mask, int* __restrict__ count,
+                                                     const int* __restrict__ start, BinEntry* __restrict__ entries) {
+  const long long n = (long long)g.B * g.dg * g.K * g.P;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(i % g.P);
+    long long r = i / g.P;
+    const int tap = (int)(r % g.K); r /= g.K;
+    const int dgi = (int)(r % g.dg);
+    const int b = (int)(r / g.dg);
+    RowCoord<ND> rc;
+    decode_row<ND>(g, b, p, true, rc);
+    SamplePos<ND> sp;
+    sample_pos<T, ND, MOD>(g, off, mask, rc, dgi, tap, sp);
+    if (!sp.in_range) continue;
+#pragma unroll
+    for (int c = 0; c < (1 << ND); ++c) {
+      float w = sp.m;
+      bool ok = true;
+      int pix = 0;
+#pragma unroll
+      for (int a = 0; a < ND; ++a) {
+        const int hi = (c >> a) & 1;
+        const int ia = sp.lo[a] + hi;
+        // zero-weight "high" corners are skipped, as the reference skips their adds
+        // (src/mdeformable_conv.cu:285-293, src/deformable_conv.cu:254-261)
+        ok = ok && (hi ? (ia <= g.in[a] - 1 && sp.fr[a] > kEps) : (ia >= 0));
+        w *= hi ? sp.fr[a] : (1.f - sp.fr[a]);
+        pix = pix * g.in[a] + ia;
+      }
+      if (!ok) continue;
+      const size_t bin = (((size_t)b * g.dg + dgi) * g.IN + pix) * g.K + tap;
+      if (!FILL) {
+        atomicAdd(count + bin, 1);
+      } else {
+        const int slot = start[bin] + atomicSub(count + bin, 1) - 1;
+        BinEntry e;
+        e.row = b * g.P + p;
+        e.w = w;
+        entries[slot] = e;
+      }
+    }
+  }
+}
+
+// Sort each bin by output position so the summation order (and the result) is run-to-run identical.
+__global__ void __launch_bounds__(256) k_bin_sort(const int* __restrict__ start, BinEntry* __restrict__ entries,
+                                                  size_t nbins) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nbins; i += (size_t)gridDim.x * blockDim.x) {
+    const int s = start[i], e = start[i + 1];
+    for (int a = s + 1; a < e; ++a) {
+      const BinEntry v = entries[a];
+      int k = a - 1;
+      while (k >= s && entries[k].row > v.row) {
+        entries[k + 1] = entries[k];
+        --k;
+      }
+      entries[k + 1] = v;
+    }
+  }
+}
+
+struct TcGiParams {
+  DevGeom g;
+  const void* got;           // channels-last grad_output [B][P][Co]
+  const int* bin_start;      // [nbins + 1]
+  const BinEntry* entries;
+  void* gx;                  // grad_input, NCHW
+  int BN;                    // channels per tile
+  int m_tiles, n_tiles, total_tiles;
+  int cobs;                  // 64-wide output-channel blocks per group = Cog / 64
+  int kblocks;               // K * cobs
+};
+
+__device__ __forceinline__ void fma8(const uint4& v, float w, float (&acc)[8], __half) {
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __half22float2(h[i]);
+    acc[2 * i] = fmaf(w, t.x, acc[2 * i]);
+    acc[2 * i + 1] = fmaf(w, t.y, acc[2 * i + 1]);
+  }
+}
+__device__ __forceinline__ void fma8(const uint4& v, float w, float (&acc)[8], __nv_bfloat16) {
+  const uint32_t* u = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    acc[2 * i] = fmaf(w, __uint_as_float(u[i] << 16), acc[2 * i]);
+    acc[2 * i + 1] = fmaf(w, __uint_as_float(u[i] & 0xFFFF0000u), acc[2 * i + 1]);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&acc)[8], __half) {
+  uint4 r;
+  uint32_t* o = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 h = __floats2half2_rn(acc[2 * i], acc[2 * i + 1]);
+    o[i] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  return r;
+}
+__device__ __forceinline__ uint4 pack8(const float (&acc)[8], __nv_bfloat16) {
+  uint4 r;
+  uint32_t* o = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(acc[2 * i], acc[2 * i + 1]);
+    o[i] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  return r;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(GI_THREADS, 1)
+k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const TcGiParams prm) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + GI_STAGES * GI_A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + GI_STAGES * GI_B_BYTES);
+  uint64_t* full_a = bars;
+  uint64_t* full_b = bars + GI_STAGES;
+  uint64_t* empty = bars + 2 * GI_STAGES;
+  uint64_t* tmem_full = bars + 3 * GI_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const DevGeom& g = prm.g;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmap_wt);
+    for (int s = 0; s < GI_STAGES; ++s) {
+      ptx::mbar_init(&full_a[s], GI_GATHER_THREADS);
+      ptx::mbar_init(&full_b[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&tmem_full[s], 1);
+      ptx::mbar_init(&tmem_empty[s], 128);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<512>(tmem_ptr);
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int BN = prm.BN;
+  const long long total_pos = (long long)g.B * g.IN;
+
+  if (warp == 0) {
+    // ===================== TMA producer: W^T slices =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x) {
+        const int nt = t / prm.m_tiles;
+        const int c0 = nt * BN;
+        for (int kb = 0; kb < prm.kblocks; ++kb) {
+          ptx::mbar_wait(&empty[s], ph ^ 1);
+          ptx::mbar_arrive_expect_tx(&full_b[s], (uint32_t)BN * 128u);
+          ptx::tma_load_2d(sB + s * GI_B_BYTES, &tmap_wt, &full_b[s], kb * 64, c0);
+          if (++s == GI_STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = ptx::umma_idesc_f16(umma_fmt<T>(), 0, 0, GI_BM, BN);
+      int s = 0;
+      uint32_t ph = 0;
+      int as = 0;
+      uint32_t aph = 0;
+      for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x) {
+        ptx::mbar_wait(&tmem_empty[as], aph ^ 1);
+        ptx::tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * GI_MAX_BN);
+        for (int kb = 0; kb < prm.kblocks; ++kb) {
+          ptx::mbar_wait(&full_b[s], ph);
+          ptx::mbar_wait(&full_a[s], ph);
+          ptx::tc_fence_after_sync();
+          const uint32_t a_addr = ptx::smem_u32(sA + s * GI_A_BYTES);
+          const uint32_t b_addr = ptx::smem_u32(sB + s * GI_B_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ad = ptx::umma_smem_desc_sw128(a_addr + k * 32, 0, 1024);
+            const uint64_t bd = ptx::umma_smem_desc_sw128(b_addr + k * 32, 0, 1024);
+            ptx::umma_f16(d_tmem, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty[s]);
+          if (++s == GI_STAGES) { s = 0; ph ^= 1; }
+        }
+        ptx::umma_commit(&tmem_full[as]);
+        if (++as == 2) { as = 0; aph ^= 1; }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================== epilogue: TMEM -> grad_input (NCHW) =====================
+    const int ew = warp & 3;
+    T* __restrict__ gx = reinterpret_cast<T*>(prm.gx);
+    int as = 0;
+    uint32_t aph = 0;
+    for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x) {
+      const int mt = t % prm.m_tiles;
+      const int nt = t / prm.m_tiles;
+      const long long gp = (long long)mt * GI_BM + ew * 32 + lane;
+      const bool valid = gp < total_pos;
+      const int b = valid ? (int)(gp / g.IN) : 0;
+      const int pix = valid ? (int)(gp % g.IN) : 0;
+      T* xrow = gx + ((size_t)b * g.C + (size_t)nt * BN) * g.IN + pix;
+      ptx::mbar_wait(&tmem_full[as], aph);
+      ptx::tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * GI_MAX_BN);
+      for (int cc = 0; cc < BN; cc += 32) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(taddr + cc, v);
+        ptx::tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) xrow[(size_t)(cc + j) * g.IN] = cvt_to<T, float>(__uint_as_float(v[j]));
+        }
+      }
+      ptx::tc_fence_before_sync();
+      ptx::mbar_arrive(&tmem_empty[as]);
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+  } else if (warp >= 8) {
+    // ===================== gather producers =====================
+    const int gt = threadIdx.x - 256;
+    const int gw = gt >> 5;
+    const int chunk = lane & 7;
+    const uint4* __restrict__ gq = reinterpret_cast<const uint4*>(prm.got);
+    const int* __restrict__ bin_start = prm.bin_start;
+    const BinEntry* __restrict__ entries = prm.entries;
+    const int Co8 = g.Co >> 3;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x) {
+      const int mt = t % prm.m_tiles;
+      const int nt = t / prm.m_tiles;
+      const int c0 = nt * BN;
+      const int grp = c0 / g.Cg;
+      const int dgi = c0 / g.Cdg;
+      // first bin (tap 0) of this thread's four rows
+      long long bin0[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const long long gp = (long long)mt * GI_BM + gw * 16 + j * 4 + (lane >> 3);
+        if (gp < total_pos) {
+          const long long b = gp / g.IN, pix = gp - b * g.IN;
+          bin0[j] = ((b * g.dg + dgi) * g.IN + pix) * g.K;
+        } else {
+          bin0[j] = -1;
+        }
+      }
+      for (int kb = 0; kb < prm.kblocks; ++kb) {
+        const int tap = kb / prm.cobs, cob = kb - tap * prm.cobs;
+        const uint4* gc = gq + ((grp * g.Cog + cob * 64) >> 3) + chunk;
+        ptx::mbar_wait(&empty[s], ph ^ 1);
+        const uint32_t a_addr = ptx::smem_u32(sA + s * GI_A_BYTES);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int row = gw * 16 + j * 4 + (lane >> 3);
+          float acc[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+          if (bin0[j] >= 0) {
+            const int e0 = __ldg(bin_start + bin0[j] + tap), e1 = __ldg(bin_start + bin0[j] + tap + 1);
+            for (int e = e0; e < e1; ++e) {
+              const int2 ev = __ldg(reinterpret_cast<const int2*>(entries) + e);
+              const uint4 v = __ldg(gc + (size_t)ev.x * Co8);
+              fma8(v, __int_as_float(ev.y), acc, T());
+            }
+          }
+          sts128(a_addr + sw128(row, chunk), pack8(acc, T()));
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive(&full_a[s]);
+        if (++s == GI_STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc<512>(tmem_base);
+}
+
+// W [Co][Cg][K] -> Wt [C][tap * Cog + col]   (c = grp * Cg + cl, co = grp * Cog + col)
+template <typename T>
+__global__ void k_transpose_weight(const T* __restrict__ w, T* __restrict__ wt, int Co, int Cg, int Cog, int K) {
+  const size_t n = (size_t)Co * Cg * K;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    // destination-major so the writes coalesce
+    const int KC = K * Cog;
+    const int c = (int)(i / KC);
+    const int r = (int)(i % KC);
+    const int tap = r / Cog, col = r - tap * Cog;
+    const int grp = c / Cg, cl = c - grp * Cg;
+    wt[i] = w[((size_t)(grp * Cog + col) * Cg + cl) * K + tap];
+  }
+}
+
+size_t smem_bytes_gi() {
+  return 1024 + (size_t)GI_STAGES * (GI_A_BYTES + GI_B_BYTES) + (3 * GI_STAGES + 4) * sizeof(uint64_t) + 16;
+}
+
+int pick_bn_gi(const DevGeom& g) {
+  int bn = GI_MAX_BN;
+  while (bn > 64 && (g.Cg % bn != 0 || g.Cdg % bn != 0)) bn >>= 1;
+  return bn;
+}
+
+size_t num_bins(const DevGeom& g) { return (size_t)g.B * g.dg * g.IN * g.K; }
+size_t max_entries(const DevGeom& g) { return ((size_t)g.B * g.dg * g.K * g.P) << g.nd; }
+
+struct GiLayout {
+  size_t count, start, entries, scan_tmp, scan_tmp_bytes, total;
+};
+GiLayout gi_layout(const DevGeom& g) {
+  GiLayout L;
+  const size_t nb = num_bins(g);
+  size_t o = 0;
+  L.count = o; o += align256((nb + 1) * sizeof(int));
+  L.start = o; o += align256((nb + 1) * sizeof(int));
+  L.entries = o; o += align256(max_entries(g) * sizeof(BinEntry));
+  size_t tmp = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp, (const int*)nullptr, (int*)nullptr, (int)(nb + 1));
+  L.scan_tmp_bytes = tmp;
+  L.scan_tmp = o; o += align256(tmp);
+  L.total = o;
+  return L;
+}
+
+template <typename T, int ND, bool MOD>
+void build_bins(const DevGeom& g, const void* off, const void* mask, char* ws, const GiLayout& L, LaunchCtx& ctx) {
+  int* count = reinterpret_cast<int*>(ws + L.count);
+  int* start = reinterpret_cast<int*>(ws + L.start);
+  BinEntry* entries = reinterpret_cast<BinEntry*>(ws + L.entries);
+  const size_t nb = num_bins(g);
+  cudaError_t e = cudaMemsetAsync(count, 0, (nb + 1) * sizeof(int), ctx.stream);
+  if (e != cudaSuccess && ctx.err == cudaSuccess) ctx.err = e;
+  const long long n = (long long)g.B * g.dg * g.K * g.P;
+  const int blocks = (int)((n + 255) / 256 > 148 * 16 ? 148 * 16 : (n + 255) / 256);
+  {
+    ProfScope prof(ctx, "bin_count");
+    k_bin_entries<T, ND, MOD, false><<<blocks, 256, 0, ctx.stream>>>(g, (const T*)off, (const T*)mask, count, start, entries);
+    MDCONV_CHECK_LAUNCH(ctx);
+  }
+  {
+    ProfScope prof(ctx, "bin_scan");
+    size_t tmp = L.scan_tmp_bytes;
+    e = cub::DeviceScan::ExclusiveSum(ws + L.scan_tmp, tmp, count, start, (int)(nb + 1), ctx.stream);
+    if (e != cudaSuccess && ctx.err == cudaSuccess) ctx.err = e;
+    ctx.launches++;
+  }
+  {
+    ProfScope prof(ctx, "bin_fill");
+    k_bin_entries<T, ND, MOD, true><<<blocks, 256, 0, ctx.stream>>>(g, (const T*)off, (const T*)mask, count, start, entries);
+    MDCONV_CHECK_LAUNCH(ctx);
+  }
+  {
+    ProfScope prof(ctx, "bin_sort");
+    const int sb = (int)((nb + 255) / 256 > 148 * 16 ? 148 * 16 : (nb + 255) / 256);
+    k_bin_sort<<<sb, 256, 0, ctx.stream>>>(start, entries, nb);
+    MDCONV_CHECK_LAUNCH(ctx);
+  }
+}
+
+}  // namespace
+
+bool grad_input_supported(const DevGeom& g) {
+  if (g.Cog % 64 != 0 || g.Cg % 64 != 0 || g.Cdg % 64 != 0 || g.Co % 8 != 0) return false;
+  if (num_bins(g) + 1 > 2147483647ULL || max_entries(g) > 2147483647ULL) return false;
+  if ((long long)g.B * g.P * (g.Co / 8) > 2147483647LL) return false;
+  return true;
+}
+
+size_t grad_input_workspace(const DevGeom& g) {
+  // channels-last grad_output + transposed weight + inverse index
+  return align256((size_t)g.B * g.Co * g.P * 2) + align256((size_t)g.Co * g.Kg * 2) + gi_layout(g).total;
+}
+
+template <typename T>
+void tensor_grad_input(const DevGeom& g, const void* w, const void* off, const void* mask, const void* go, void* gx,
+                       void* ws, LaunchCtx& ctx) {
+  char* base = reinterpret_cast<char*>(ws);
+  T* got = reinterpret_cast<T*>(base);
+  base += align256((size_t)g.B * g.Co * g.P * sizeof(T));
+  T* wt = reinterpret_cast<T*>(base);
+  base += align256((size_t)g.Co * g.Kg * sizeof(T));
+  const GiLayout L = gi_layout(g);
+
+  launch_to_channels_last<T>((const T*)go, got, g.B, g.Co, g.P, ctx);
+  {
+    ProfScope prof(ctx, "transpose_weight");
+    const size_t n = (size_t)g.Co * g.Kg;
+    const int blocks = (int)((n + 255) / 256 > 1184 ? 1184 : (n + 255) / 256);
+    k_transpose_weight<T><<<blocks, 256, 0, ctx.stream>>>((const T*)w, wt, g.Co, g.Cg, g.Cog, g.K);
+    MDCONV_CHECK_LAUNCH(ctx);
+  }
+  if (g.nd == 2) {
+    if (g.modulated) build_bins<T, 2, true>(g, off, mask, base, L, ctx);
+    else build_bins<T, 2, false>(g, off, mask, base, L, ctx);
+  } else {
+    if (g.modulated) build_bins<T, 3, true>(g, off, mask, base, L, ctx);
+    else build_bins<T, 3, false>(g, off, mask, base, L, ctx);
+  }
+
+  TcGiParams prm;
+  prm.g = g;
+  prm.got = got;
+  prm.bin_start = reinterpret_cast<const int*>(base + L.start);
+  prm.entries = reinterpret_cast<const BinEntry*>(base + L.entries);
+  prm.gx = gx;
+  prm.BN = pick_bn_gi(g);
+  const long long total_pos = (long long)g.B * g.IN;
+  prm.m_tiles = (int)((total_pos + GI_BM - 1) / GI_BM);
+  prm.n_tiles = g.C / prm.BN;
+  prm.total_tiles = prm.m_tiles * prm.n_tiles;
+  prm.cobs = g.Cog / 64;
+  prm.kblocks = g.K * prm.cobs;
+
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) {
+    if (ctx.err == cudaSuccess) ctx.err = cudaErrorNotSupported;
+    return;
+  }
+  CUtensorMap tmap;
+  const cuuint64_t dims[2] = {(cuuint64_t)g.K * g.Cog, (cuuint64_t)g.C};
+  const cuuint64_t strides[1] = {(cuuint64_t)g.K * g.Cog * sizeof(T)};
+  const cuuint32_t box[2] = {64, (cuuint32_t)prm.BN};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(&tmap, tmap_dtype<T>(), 2, wt, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    if (ctx.err == cudaSuccess) ctx.err = cudaErrorInvalidValue;
+    return;
+  }
+  const size_t smem = smem_bytes_gi();
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_tc_grad_input<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess && ctx.err == cudaSuccess) ctx.err = e;
+    configured = true;
+  }
+  const int grid = prm.total_tiles < sm_count() ? prm.total_tiles : sm_count();
+  ProfScope prof(ctx, "tc_grad_input");
+  k_tc_grad_input<T><<<grid, GI_THREADS, smem, ctx.stream>>>(tmap, prm);
+  MDCONV_CHECK_LAUNCH(ctx);
+}
+
+template void tensor_grad_input<__half>(const DevGeom&, const void*, const void*, const void*, const void*, void*,
+                                        void*, LaunchCtx&);
+template void tensor_grad_input<__nv_bfloat16>(const DevGeom&, const void*, const void*, const void*, const void*,
+                                               void*, void*, LaunchCtx&);
+
+}  // namespace tc
+}  // namespace mdconv

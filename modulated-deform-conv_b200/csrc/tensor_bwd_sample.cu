@@ -1,0 +1,530 @@
+// tensor_bwd_sample.cu -- tcgen05 kernel for grad_offset and grad_mask (fp16 / bf16).
+//
+// Reference: the col2im_coord / mask-gradient half of the fused gradient kernels
+// (src/mdeformable_conv.cu:295-315, src/deformable_conv.cu:262-286, 3D twins), which run one
+// thread per column element and resolve the sum over channels with 2-3 atomicAdd per element onto
+// C/dg-way contended addresses, fed by a materialised grad_columns buffer (G2, :417-419).
+//
+// Here:   gcol[pos, kk] = sum_co go[pos, co] * W[co, kk]           (tcgen05.mma, accumulators in TMEM)
+//         S_c[pos, tap] = sum_ch gcol[pos, (ch, tap)] * x[corner_c(pos, tap), ch]
+//         grad_mask     = sum_c w_c * S_c
+//         grad_offset_a = mask * sum_c (d w_c / d p_a) * S_c
+// so neither gcol nor the columns exist in HBM, there are no atomics, and every output element is
+// written exactly once in a fixed summation order (deterministic).
+//
+//   warp 0      TMA producer: grad_output tile (MN-major A operand, straight from NCHW) and
+//               weight slices (MN-major B operand) -> 3-slot smem ring
+//   warp 1      MMA issuer, M=128 positions x N=64*nb channels of one tap, K = output channels
+//   warp 2      TMEM allocator (2 accumulator stages x 256 columns)
+//   warps 4-7   "movers": compute the per-(position, tap) sampling entry (corner indices, fractions,
+//               mask) for the next phase; tcgen05.ld the accumulator and re-lay it out in shared
+//               memory as [position][64 channels] fp32 (swizzled) for the dot warps
+//   warps 8-15  dot warps: 8 lanes per position, 16-byte channels-last loads of the corner values,
+//               fp32 dot products against gcol, warp-shuffle reduction over the 8 lanes, final
+//               combine and store of grad_offset / grad_mask
+#include "tc_common.cuh"
+
+namespace mdconv {
+namespace tc {
+
+namespace {
+
+constexpr int GS_THREADS = 512;
+constexpr int GS_STAGES = 3;
+constexpr int GS_A_BYTES = 2 * 8192;      // two [64 co x 64 pos] blocks
+constexpr int GS_B_BYTES = 4 * 8192;      // up to four [64 co x 64 kk] blocks
+constexpr int GS_T_BYTES = 128 * 64 * 4;  // one [128 pos x 64 ch] fp32 block
+
+template <int ND>
+struct __align__(16) SampleEntry {
+  int idx[1 << ND];  // uint4 index of the corner's 8-channel vector (channel offset excluded), -1: value is 0
+  float fr[ND];
+  float m;
+  uint32_t flags;    // bit 0: grad_offset is produced, bit 1: row is a real output position
+};
+
+struct TcGsParams {
+  DevGeom g;
+  const void* xt;    // channels-last input
+  const void* off;
+  const void* mask;
+  void* goff;
+  void* gmask;
+  int nb;            // 64-channel blocks per accumulator stage (1, 2 or 4)
+  int nsub;          // stages per (deformable group, tap) = Cdg / 64 / nb
+  int kblocks;       // K blocks per stage = Cog / 64
+  int pbi;           // 64-position blocks per sample
+  int total_pb;      // B * pbi
+  int m_tiles;       // ceil(total_pb / 2)
+};
+
+template <typename T>
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]);
+template <>
+__device__ __forceinline__ void unpack8<__half>(const uint4& v, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x; f[2 * i + 1] = t.y;
+  }
+}
+template <>
+__device__ __forceinline__ void unpack8<__nv_bfloat16>(const uint4& v, float (&f)[8]) {
+  const uint32_t* u = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(u[i] << 16);
+    f[2 * i + 1] = __uint_as_float(u[i] & 0xFFFF0000u);
+  }
+}
+
+// position of 16-byte quad q (4 channels) of row `row` inside a [128][64] fp32 block: lane j of a
+// dot group reads quads 2j and 2j+1 (channels 8j..8j+7); they are stored at chunk slots j and 8+j
+// so both the row-parallel writers and the chunk-parallel readers are bank-conflict free.
+__device__ __forceinline__ uint32_t t_off(int row, int q) {
+  const int slot = (q >> 1) | ((q & 1) << 3);
+  return (uint32_t)(row * 256 + ((slot ^ (row & 7)) << 4));
+}
+
+template <typename T, int ND, bool MOD>
+__global__ void __launch_bounds__(GS_THREADS, 1)
+k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_constant__ CUtensorMap tmap_w,
+                 const TcGsParams prm) {
+  constexpr int NC = 1 << ND;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + GS_STAGES * GS_A_BYTES;
+  uint8_t* sT = sB + GS_STAGES * GS_B_BYTES;
+  SampleEntry<ND>* sPlan = reinterpret_cast<SampleEntry<ND>*>(sT + 2 * GS_T_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sPlan) + 2 * 128 * sizeof(SampleEntry<ND>));
+  uint64_t* full = bars;                    // [GS_STAGES]  TMA -> MMA
+  uint64_t* empty = full + GS_STAGES;       // [GS_STAGES]  MMA -> TMA
+  uint64_t* tmem_full = empty + GS_STAGES;  // [2]          MMA -> movers
+  uint64_t* tmem_empty = tmem_full + 2;     // [2]          movers -> MMA
+  uint64_t* t_full = tmem_empty + 2;        // [2]          movers -> dot warps
+  uint64_t* t_empty = t_full + 2;           // [2]          dot warps -> movers
+  uint64_t* plan_full = t_empty + 2;        // [2]          movers -> dot warps
+  uint64_t* plan_empty = plan_full + 2;     // [2]          dot warps -> movers
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(plan_empty + 2);
+
+  const DevGeom& g = prm.g;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmap_go);
+    ptx::prefetch_tensormap(&tmap_w);
+    for (int s = 0; s < GS_STAGES; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&tmem_full[s], 1);
+      ptx::mbar_init(&tmem_empty[s], 128);
+      ptx::mbar_init(&t_full[s], 128);
+      ptx::mbar_init(&t_empty[s], 256);
+      ptx::mbar_init(&plan_full[s], 128);
+      ptx::mbar_init(&plan_empty[s], 256);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<512>(tmem_ptr);
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int nb = prm.nb, nsub = prm.nsub;
+  const int bpd = g.Cdg >> 6;            // 64-channel blocks per deformable group
+  const int bpg = g.Cg >> 6;             // 64-channel blocks per conv group
+  const int phases = g.dg * g.K;         // (deformable group, tap) phases per tile
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < prm.m_tiles; t += gridDim.x) {
+        int pb_b[2], pb_p0[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int pb = 2 * t + h;
+          pb_b[h] = pb < prm.total_pb ? pb / prm.pbi : g.B;  // b == B: fully out of bounds -> zero fill
+          pb_p0[h] = pb < prm.total_pb ? (pb % prm.pbi) * 64 : 0;
+        }
+        for (int phs = 0; phs < phases; ++phs) {
+          const int dgi = phs / g.K, tap = phs - dgi * g.K;
+          for (int sub = 0; sub < nsub; ++sub) {
+            const int blk0 = dgi * bpd + sub * nb;  // first 64-channel block (global numbering)
+            const int grp = blk0 / bpg;
+            const int ccl0 = blk0 - grp * bpg;      // block index inside the conv group
+            for (int kb = 0; kb < prm.kblocks; ++kb) {
+              const int co0 = grp * g.Cog + kb * 64;
+              ptx::mbar_wait(&empty[s], ph ^ 1);
+              ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)(GS_A_BYTES + nb * 8192));
+#pragma unroll
+              for (int h = 0; h < 2; ++h)
+                ptx::tma_load_3d(sA + s * GS_A_BYTES + h * 8192, &tmap_go, &full[s], pb_p0[h], co0, pb_b[h]);
+              for (int j = 0; j < nb; ++j)
+                ptx::tma_load_2d(sB + s * GS_B_BYTES + j * 8192, &tmap_w, &full[s], ((ccl0 + j) * g.K + tap) * 64, co0);
+              if (++s == GS_STAGES) { s = 0; ph ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = ptx::umma_idesc_f16(umma_fmt<T>(), /*A MN-major*/ 1, /*B MN-major*/ 1, 128, nb * 64);
+      int s = 0;
+      uint32_t ph = 0;
+      int as = 0;
+      uint32_t aph = 0;
+      for (int t = blockIdx.x; t < prm.m_tiles; t += gridDim.x) {
+        for (int st = 0; st < phases * nsub; ++st) {
+          ptx::mbar_wait(&tmem_empty[as], aph ^ 1);
+          ptx::tc_fence_after_sync();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
+          for (int kb = 0; kb < prm.kblocks; ++kb) {
+            ptx::mbar_wait(&full[s], ph);
+            ptx::tc_fence_after_sync();
+            const uint32_t a_addr = ptx::smem_u32(sA + s * GS_A_BYTES);
+            const uint32_t b_addr = ptx::smem_u32(sB + s * GS_B_BYTES);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {  // 16 output channels per MMA
+              const uint64_t ad = ptx::umma_smem_desc_sw128(a_addr + k * 2048, 8192, 1024);
+              const uint64_t bd = ptx::umma_smem_desc_sw128(b_addr + k * 2048, 8192, 1024);
+              ptx::umma_f16(d_tmem, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            ptx::umma_commit(&empty[s]);
+            if (++s == GS_STAGES) { s = 0; ph ^= 1; }
+          }
+          ptx::umma_commit(&tmem_full[as]);
+          if (++as == 2) { as = 0; aph ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================== movers: sampling entries + TMEM -> smem re-layout =====================
+    const int row = threadIdx.x - 128;  // TMEM lane == tile row
+    const T* __restrict__ off = reinterpret_cast<const T*>(prm.off);
+    const T* __restrict__ mask = reinterpret_cast<const T*>(prm.mask);
+    const int C8 = g.C >> 3;
+    const bool rule_b = g.rule != 0;
+    int as = 0, ts = 0, ps = 0;
+    uint32_t aph = 0, tph = 0, pph = 0;
+    for (int t = blockIdx.x; t < prm.m_tiles; t += gridDim.x) {
+      const int pb = 2 * t + (row >> 6);
+      const int p = (pb % prm.pbi) * 64 + (row & 63);
+      const bool valid = pb < prm.total_pb && p < g.P;
+      RowCoord<ND> rc;
+      decode_row<ND>(g, valid ? pb / prm.pbi : 0, p, valid, rc);
+      for (int phs = 0; phs < phases; ++phs) {
+        const int dgi = phs / g.K, tap = phs - dgi * g.K;
+        {
+          // ---- sampling entry of (row, dgi, tap) ----
+          SampleEntry<ND> e;
+#pragma unroll
+          for (int c = 0; c < NC; ++c) e.idx[c] = -1;
+#pragma unroll
+          for (int a = 0; a < ND; ++a) e.fr[a] = 0.f;
+          e.m = 0.f;
+          e.flags = 0u;
+          if (valid) {
+            SamplePos<ND> sp;
+            sample_pos<T, ND, MOD>(g, off, mask, rc, dgi, tap, sp);
+            bool lo_ok[ND], hi_ld[ND];
+#pragma unroll
+            for (int a = 0; a < ND; ++a) {
+              const int lo = sp.lo[a], hi = lo + 1;
+              lo_ok[a] = lo >= 0 && lo <= g.in[a] - 1;
+              const bool hi_in = hi >= 0 && hi <= g.in[a] - 1;
+              // rule B (reference src/deformable_conv.cu:254-261): a "high" corner on an axis whose
+              // fraction is <= EPS is absent; rule A loads it whenever it is inside the input.
+              hi_ld[a] = rule_b ? (hi_in && fabsf(sp.fr[a]) > kEps) : hi_in;
+              e.fr[a] = sp.fr[a];
+            }
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+              bool ok = true;
+              int pix = 0;
+#pragma unroll
+              for (int a = 0; a < ND; ++a) {
+                const int hi = (c >> a) & 1;
+                ok = ok && (hi ? hi_ld[a] : lo_ok[a]);
+                pix = pix * g.in[a] + sp.lo[a] + hi;
+              }
+              if (ok) e.idx[c] = (rc.b * g.IN + pix) * C8;
+            }
+            e.m = sp.m;
+            e.flags = 2u | ((rule_b || sp.in_range) ? 1u : 0u);
+          }
+          ptx::mbar_wait(&plan_empty[ps], pph ^ 1);
+          const uint32_t pa = ptx::smem_u32(sPlan + ps * 128 + row);
+          const uint4* q = reinterpret_cast<const uint4*>(&e);
+#pragma unroll
+          for (int i = 0; i < (int)(sizeof(SampleEntry<ND>) / 16); ++i) sts128(pa + 16 * i, q[i]);
+          ptx::mbar_arrive(&plan_full[ps]);
+          if (++ps == 2) { ps = 0; pph ^= 1; }
+        }
+        for (int sub = 0; sub < nsub; ++sub) {
+          ptx::mbar_wait(&tmem_full[as], aph);
+          ptx::tc_fence_after_sync();
+          const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(as * 256);
+          for (int j = 0; j < nb; ++j) {
+            ptx::mbar_wait(&t_empty[ts], tph ^ 1);
+            const uint32_t tb = ptx::smem_u32(sT + ts * GS_T_BYTES);
+#pragma unroll
+            for (int hlf = 0; hlf < 2; ++hlf) {
+              uint32_t v[32];
+              ptx::tmem_ld_32x32(taddr + j * 64 + hlf * 32, v);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                sts128(tb + t_off(row, hlf * 8 + q), make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+            }
+            ptx::mbar_arrive(&t_full[ts]);
+            if (++ts == 2) { ts = 0; tph ^= 1; }
+          }
+          ptx::tc_fence_before_sync();
+          ptx::mbar_arrive(&tmem_empty[as]);
+          if (++as == 2) { as = 0; aph ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================== dot warps =====================
+    const int dt = threadIdx.x - 256;
+    const int dw = dt >> 5;
+    const int rq = lane >> 3;  // row inside a pass
+    const int j = lane & 7;    // 8-channel chunk
+    const uint4* __restrict__ xq = reinterpret_cast<const uint4*>(prm.xt);
+    T* __restrict__ goff = reinterpret_cast<T*>(prm.goff);
+    T* __restrict__ gmask = reinterpret_cast<T*>(prm.gmask);
+    int ts = 0, ps = 0;
+    uint32_t tph = 0, pph = 0;
+    for (int t = blockIdx.x; t < prm.m_tiles; t += gridDim.x) {
+      for (int phs = 0; phs < phases; ++phs) {
+        const int dgi = phs / g.K, tap = phs - dgi * g.K;
+        ptx::mbar_wait(&plan_full[ps], pph);
+        const uint32_t plan_addr = ptx::smem_u32(sPlan + ps * 128);
+        float S[4][NC];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int c = 0; c < NC; ++c) S[i][c] = 0.f;
+        for (int sub = 0; sub < nsub; ++sub) {
+          for (int jb = 0; jb < nb; ++jb) {
+            const int c0 = (dgi * bpd + sub * nb + jb) * 64;  // first channel of this block
+            const uint4* xc = xq + (c0 >> 3) + j;
+            ptx::mbar_wait(&t_full[ts], tph);
+            const uint32_t tb = ptx::smem_u32(sT + ts * GS_T_BYTES);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int row = dw * 16 + i * 4 + rq;
+              const uint32_t ea = plan_addr + row * (uint32_t)sizeof(SampleEntry<ND>);
+              int idx[NC];
+#pragma unroll
+              for (int c4 = 0; c4 < NC / 4; ++c4) {
+                const uint4 iv = lds128(ea + 16 * c4);
+                idx[4 * c4] = (int)iv.x; idx[4 * c4 + 1] = (int)iv.y; idx[4 * c4 + 2] = (int)iv.z; idx[4 * c4 + 3] = (int)iv.w;
+              }
+              const uint4 g0 = lds128(tb + t_off(row, 2 * j));
+              const uint4 g1 = lds128(tb + t_off(row, 2 * j + 1));
+              const float gc[8] = {__uint_as_float(g0.x), __uint_as_float(g0.y), __uint_as_float(g0.z),
+                                   __uint_as_float(g0.w), __uint_as_float(g1.x), __uint_as_float(g1.y),
+                                   __uint_as_float(g1.z), __uint_as_float(g1.w)};
+              uint4 xv[NC];
+#pragma unroll
+              for (int c = 0; c < NC; ++c) xv[c] = idx[c] >= 0 ? __ldg(xc + idx[c]) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+              for (int c = 0; c < NC; ++c) {
+                float xf[8];
+                unpack8<T>(xv[c], xf);
+                float acc = S[i][c];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc = fmaf(gc[k], xf[k], acc);
+                S[i][c] = acc;
+              }
+            }
+            ptx::mbar_arrive(&t_empty[ts]);
+            if (++ts == 2) { ts = 0; tph ^= 1; }
+          }
+        }
+        // ---- reduce over the 8 lanes of each row, combine, store ----
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            float v = S[i][c];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            S[i][c] = v;
+          }
+        if (j < 4) {
+          // lane j of a row group finishes pass j (all 8 lanes hold the same totals)
+          float Sc[NC];
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            float v = S[0][c];
+            v = j == 1 ? S[1][c] : v;
+            v = j == 2 ? S[2][c] : v;
+            v = j == 3 ? S[3][c] : v;
+            Sc[c] = v;
+          }
+          const int row = dw * 16 + j * 4 + rq;
+          const uint32_t ea = plan_addr + row * (uint32_t)sizeof(SampleEntry<ND>) + 16 * (NC / 4);
+          const uint4 tail = lds128(ea);  // fr[ND], m, flags (2D)  /  fr[3], m (3D)
+          float fr[3];
+          float m;
+          uint32_t flags;
+          fr[0] = __uint_as_float(tail.x);
+          fr[1] = __uint_as_float(tail.y);
+          if (ND == 2) {
+            fr[2] = 0.f;
+            m = __uint_as_float(tail.z);
+            flags = tail.w;
+          } else {
+            fr[2] = __uint_as_float(tail.z);
+            m = __uint_as_float(tail.w);
+            const uint4 tail2 = lds128(ea + 16);
+            flags = tail2.x;
+          }
+          if (flags & 2u) {
+            const int pb = 2 * t + (row >> 6);
+            const int b = pb / prm.pbi;
+            const int p = (pb % prm.pbi) * 64 + (row & 63);
+            float gm = 0.f;
+            float go_a[ND];
+#pragma unroll
+            for (int a = 0; a < ND; ++a) go_a[a] = 0.f;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+              float w = 1.f;
+#pragma unroll
+              for (int a = 0; a < ND; ++a) w *= ((c >> a) & 1) ? fr[a] : (1.f - fr[a]);
+              gm = fmaf(w, Sc[c], gm);
+#pragma unroll
+              for (int a = 0; a < ND; ++a) {
+                float d = ((c >> a) & 1) ? 1.f : -1.f;
+#pragma unroll
+                for (int bb = 0; bb < ND; ++bb)
+                  if (bb != a) d *= ((c >> bb) & 1) ? fr[bb] : (1.f - fr[bb]);
+                go_a[a] = fmaf(d, Sc[c], go_a[a]);
+              }
+            }
+            const size_t ch = (size_t)b * g.dg * g.K + (size_t)dgi * g.K + tap;
+#pragma unroll
+            for (int a = 0; a < ND; ++a)
+              goff[(ch * ND + a) * g.P + p] = cvt_to<T, float>((flags & 1u) ? m * go_a[a] : 0.f);
+            if (MOD) gmask[ch * g.P + p] = cvt_to<T, float>(gm);
+          }
+        }
+        ptx::mbar_arrive(&plan_empty[ps]);
+        if (++ps == 2) { ps = 0; pph ^= 1; }
+      }
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc<512>(tmem_base);
+}
+
+template <int ND>
+size_t gs_smem_bytes() {
+  return 1024 + (size_t)GS_STAGES * (GS_A_BYTES + GS_B_BYTES) + 2 * GS_T_BYTES + 2 * 128 * sizeof(SampleEntry<ND>) +
+         (2 * GS_STAGES + 12) * sizeof(uint64_t) + 16;
+}
+
+template <typename T, int ND, bool MOD>
+void launch_grad_sample(const CUtensorMap& tmap_go, const CUtensorMap& tmap_w, const TcGsParams& prm, LaunchCtx& ctx) {
+  const size_t smem = gs_smem_bytes<ND>();
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e =
+        cudaFuncSetAttribute(k_tc_grad_sample<T, ND, MOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess && ctx.err == cudaSuccess) ctx.err = e;
+    configured = true;
+  }
+  const int grid = prm.m_tiles < sm_count() ? prm.m_tiles : sm_count();
+  ProfScope prof(ctx, "tc_grad_sample");
+  k_tc_grad_sample<T, ND, MOD><<<grid, GS_THREADS, smem, ctx.stream>>>(tmap_go, tmap_w, prm);
+  MDCONV_CHECK_LAUNCH(ctx);
+}
+
+}  // namespace
+
+bool grad_sample_supported(const DevGeom& g) {
+  return g.Cog % 64 == 0 && g.P % 8 == 0 && g.Cg % 64 == 0 && g.Cdg % 64 == 0;
+}
+
+// xt: channels-last input; wr: weight re-ordered to [Co][(channel-block, tap, 64 channels)].
+template <typename T>
+void tensor_grad_sample(const DevGeom& g, const T* xt, const T* wr, const void* off, const void* mask, const void* go,
+                        void* goff, void* gmask, LaunchCtx& ctx) {
+  TcGsParams prm;
+  prm.g = g;
+  prm.xt = xt; prm.off = off; prm.mask = mask; prm.goff = goff; prm.gmask = gmask;
+  const int bpd = g.Cdg / 64, bpg = g.Cg / 64;
+  int nb = 4;
+  while (nb > 1 && (bpd % nb != 0 || bpg % nb != 0)) nb >>= 1;
+  prm.nb = nb;
+  prm.nsub = bpd / nb;
+  prm.kblocks = g.Cog / 64;
+  prm.pbi = (g.P + 63) / 64;
+  prm.total_pb = g.B * prm.pbi;
+  prm.m_tiles = (prm.total_pb + 1) / 2;
+
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) {
+    if (ctx.err == cudaSuccess) ctx.err = cudaErrorNotSupported;
+    return;
+  }
+  CUtensorMap tmap_go, tmap_w;
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)g.P, (cuuint64_t)g.Co, (cuuint64_t)g.B};
+    const cuuint64_t strides[2] = {(cuuint64_t)g.P * sizeof(T), (cuuint64_t)g.Co * g.P * sizeof(T)};
+    const cuuint32_t box[3] = {64, 64, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(&tmap_go, tmap_dtype<T>(), 3, const_cast<void*>(go), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      if (ctx.err == cudaSuccess) ctx.err = cudaErrorInvalidValue;
+      return;
+    }
+  }
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)g.Kg, (cuuint64_t)g.Co};
+    const cuuint64_t strides[1] = {(cuuint64_t)g.Kg * sizeof(T)};
+    const cuuint32_t box[2] = {64, 64};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(&tmap_w, tmap_dtype<T>(), 2, const_cast<T*>(wr), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      if (ctx.err == cudaSuccess) ctx.err = cudaErrorInvalidValue;
+      return;
+    }
+  }
+  if (g.nd == 2) {
+    if (g.modulated) launch_grad_sample<T, 2, true>(tmap_go, tmap_w, prm, ctx);
+    else launch_grad_sample<T, 2, false>(tmap_go, tmap_w, prm, ctx);
+  } else {
+    if (g.modulated) launch_grad_sample<T, 3, true>(tmap_go, tmap_w, prm, ctx);
+    else launch_grad_sample<T, 3, false>(tmap_go, tmap_w, prm, ctx);
+  }
+}
+
+template void tensor_grad_sample<__half>(const DevGeom&, const __half*, const __half*, const void*, const void*,
+                                         const void*, void*, void*, LaunchCtx&);
+template void tensor_grad_sample<__nv_bfloat16>(const DevGeom&, const __nv_bfloat16*, const __nv_bfloat16*,
+                                                const void*, const void*, const void*, void*, void*, LaunchCtx&);
+
+}  // namespace tc
+}  // namespace mdconv
