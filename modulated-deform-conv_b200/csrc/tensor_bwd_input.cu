@@ -18,7 +18,7 @@
 //   warp 2      TMEM allocator
 //   warps 4-7   epilogue: tcgen05.ld -> convert -> NCHW stores
 //   warps 8-15  gather producers: 8 lanes per input position walk the bin, 16-byte channels-last
-//               loads of grad_output, fp32 accumulate, 16-byte stores into the swizzled A tile
+//               loads of grad_output, weighted accumulate, 16-byte stores into the swizzled A tile
 #include <cub/device/device_scan.cuh>
 
 #include "tc_common.cuh"
@@ -119,43 +119,56 @@ struct TcGiParams {
   int kblocks;               // K * cobs
 };
 
-__device__ __forceinline__ void fma8(const uint4& v, float w, float (&acc)[8], __half) {
-  const __half2* h = reinterpret_cast<const __half2*>(&v);
+// 8-channel accumulator of the gather: packed half2 for fp16 (one HFMA2 per channel pair, as in the
+// forward gather), fp32 for bf16 (8 mantissa bits cannot carry a multi-term sum).
+template <typename T> struct Acc8;
+template <> struct Acc8<__half> {
+  __half2 a[4];
+  __device__ __forceinline__ void clear() {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 t = __half22float2(h[i]);
-    acc[2 * i] = fmaf(w, t.x, acc[2 * i]);
-    acc[2 * i + 1] = fmaf(w, t.y, acc[2 * i + 1]);
+    for (int i = 0; i < 4; ++i) a[i] = __float2half2_rn(0.f);
   }
-}
-__device__ __forceinline__ void fma8(const uint4& v, float w, float (&acc)[8], __nv_bfloat16) {
-  const uint32_t* u = reinterpret_cast<const uint32_t*>(&v);
+  __device__ __forceinline__ void fma(const uint4& v, float w) {
+    const __half2 wh = __float2half2_rn(w);
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    acc[2 * i] = fmaf(w, __uint_as_float(u[i] << 16), acc[2 * i]);
-    acc[2 * i + 1] = fmaf(w, __uint_as_float(u[i] & 0xFFFF0000u), acc[2 * i + 1]);
+    for (int i = 0; i < 4; ++i) a[i] = __hfma2(wh, h[i], a[i]);
   }
-}
-__device__ __forceinline__ uint4 pack8(const float (&acc)[8], __half) {
-  uint4 r;
-  uint32_t* o = reinterpret_cast<uint32_t*>(&r);
+  __device__ __forceinline__ uint4 pack() const {
+    uint4 r;
+    uint32_t* o = reinterpret_cast<uint32_t*>(&r);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const __half2 h = __floats2half2_rn(acc[2 * i], acc[2 * i + 1]);
-    o[i] = *reinterpret_cast<const uint32_t*>(&h);
+    for (int i = 0; i < 4; ++i) o[i] = *reinterpret_cast<const uint32_t*>(&a[i]);
+    return r;
   }
-  return r;
-}
-__device__ __forceinline__ uint4 pack8(const float (&acc)[8], __nv_bfloat16) {
-  uint4 r;
-  uint32_t* o = reinterpret_cast<uint32_t*>(&r);
+};
+template <> struct Acc8<__nv_bfloat16> {
+  float a[8];
+  __device__ __forceinline__ void clear() {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const __nv_bfloat162 h = __floats2bfloat162_rn(acc[2 * i], acc[2 * i + 1]);
-    o[i] = *reinterpret_cast<const uint32_t*>(&h);
+    for (int i = 0; i < 8; ++i) a[i] = 0.f;
   }
-  return r;
-}
+  __device__ __forceinline__ void fma(const uint4& v, float w) {
+    const uint32_t* u = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      a[2 * i] = fmaf(w, __uint_as_float(u[i] << 16), a[2 * i]);
+      a[2 * i + 1] = fmaf(w, __uint_as_float(u[i] & 0xFFFF0000u), a[2 * i + 1]);
+    }
+  }
+  __device__ __forceinline__ uint4 pack() const {
+    uint4 r;
+    uint32_t* o = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(a[2 * i], a[2 * i + 1]);
+      o[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    return r;
+  }
+};
+
+constexpr int GI_NE = 8;  // bin entries fetched as one batch (loads issued together); longer bins loop
 
 template <typename T>
 __global__ void __launch_bounds__(GI_THREADS, 1)
@@ -312,18 +325,28 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const TcGiParams pr
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int row = gw * 16 + j * 4 + (lane >> 3);
-          float acc[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+          Acc8<T> acc;
+          acc.clear();
           if (bin0[j] >= 0) {
             const int e0 = __ldg(bin_start + bin0[j] + tap), e1 = __ldg(bin_start + bin0[j] + tap + 1);
-            for (int e = e0; e < e1; ++e) {
-              const int2 ev = __ldg(reinterpret_cast<const int2*>(entries) + e);
-              const uint4 v = __ldg(gc + (size_t)ev.x * Co8);
-              fma8(v, __int_as_float(ev.y), acc, T());
+            const int n = e1 - e0;
+            const int2* ep = reinterpret_cast<const int2*>(entries) + e0;
+            int2 ev[GI_NE];
+#pragma unroll
+            for (int i = 0; i < GI_NE; ++i) ev[i] = i < n ? __ldg(ep + i) : make_int2(0, 0);
+            uint4 v[GI_NE];
+#pragma unroll
+            for (int i = 0; i < GI_NE; ++i)
+              if (i < n) v[i] = __ldg(gc + (size_t)ev[i].x * Co8);
+#pragma unroll
+            for (int i = 0; i < GI_NE; ++i)
+              if (i < n) acc.fma(v[i], __int_as_float(ev[i].y));
+            for (int e = GI_NE; e < n; ++e) {
+              const int2 ee = __ldg(ep + e);
+              acc.fma(__ldg(gc + (size_t)ee.x * Co8), __int_as_float(ee.y));
             }
           }
-          sts128(a_addr + sw128(row, chunk), pack8(acc, T()));
+          sts128(a_addr + sw128(row, chunk), acc.pack());
         }
         ptx::fence_proxy_async_smem();
         ptx::mbar_arrive(&full_a[s]);
