@@ -4,15 +4,17 @@
 // offset-driven gather fused into the A-operand staging: the column matrix only ever exists as
 // 128x64 swizzled shared-memory tiles that tcgen05.mma consumes; nothing column-shaped touches HBM.
 //
-//   warp 0      TMA producer: weight K-slices [BN x 64] (128B swizzle) -> smem ring
-//   warp 1      MMA issuer: one lane issues tcgen05.mma (M=128, N=BN, K=16) x4 per K-block,
-//               accumulators in TMEM (2 stages x 256 columns), tcgen05.commit -> mbarriers
-//   warp 2      TMEM allocator
-//   warps 4-7   epilogue: tcgen05.ld -> +bias -> convert -> NCHW stores (overlaps the next tile)
-//   warps 8-15  gather producers: per K-block (64 channels x 1 tap) compute one sampling plan per
-//               pixel row (corner indices + weight*mask, once per (pixel, tap), not per channel as
-//               the reference does, src/mdeformable_conv.cu:59-83), then 128-bit channels-last
-//               loads of the corners, interpolate, and store 16-byte chunks into the swizzled tile.
+//   warp 0       TMA producer: weight K-slices [BN x 64] (128B swizzle) -> smem ring
+//   warp 1       MMA issuer: one lane issues tcgen05.mma (M=128, N=BN, K=16) x4 per K-block,
+//                accumulators in TMEM (2 stages x 256 columns), tcgen05.commit -> mbarriers
+//   warp 2       TMEM allocator
+//   warps 4-7    epilogue: tcgen05.ld -> +bias -> convert -> NCHW stores (overlaps the next tile)
+//   warps 8-11   plan producers: one sampling plan per (pixel row, tap) -- corner indices + weight*mask,
+//                once per (pixel, tap), not per channel as the reference does
+//                (src/mdeformable_conv.cu:59-83) -- into a 4-slot ring that runs ahead of the gather
+//   warps 12-27  gather producers: per K-block (64 channels x 1 tap) 128-bit channels-last loads of the
+//                corners (all loads of a thread in flight together), HFMA2 interpolation, 16-byte
+//                stores into the swizzled A tile, fence.proxy.async, mbarrier arrive
 //
 // Data layout: the kernel reads x as channels-last [B][positions][C] (one 128-byte line = 64
 // channels of one position, so 8 lanes x 16 B cover a line) and the weight re-ordered to
@@ -32,10 +34,14 @@ namespace {
 
 constexpr int TC_BM = 128;        // pixels per tile (UMMA M)
 constexpr int TC_BK = tc::BK;     // K elements per block = 128 bytes = one swizzle row
-constexpr int TC_STAGES = 3;
+constexpr int TC_STAGES = 3;      // A/B operand ring
+constexpr int TC_PLAN_SLOTS = 4;  // sampling-plan ring
 constexpr int TC_MAX_BN = 256;
-constexpr int TC_THREADS = 512;
-constexpr int TC_GATHER_THREADS = 256;
+constexpr int TC_PLAN_WARP0 = 8;      // warps 8-11: plan producers (one tile row per thread)
+constexpr int TC_GATHER_WARP0 = 12;   // warps 12-27: gather producers
+constexpr int TC_GATHER_WARPS = 16;
+constexpr int TC_GATHER_THREADS = TC_GATHER_WARPS * 32;
+constexpr int TC_THREADS = (TC_GATHER_WARP0 + TC_GATHER_WARPS) * 32;  // 896
 constexpr int TC_A_BYTES = TC_BM * 128;
 constexpr int TC_B_BYTES = TC_MAX_BN * 128;
 
@@ -51,8 +57,26 @@ struct TcFwdParams {
   int BN;            // output channels per tile
   int m_tiles, n_tiles, total_tiles;
   int ccs;           // channel blocks per group (Cg / 64)
+  int bpd;           // channel blocks per deformable group (Cdg / 64)
   int kblocks;       // ccs * K
 };
+
+// K-block order inside one (tile, group): channel blocks are walked in runs that share a deformable
+// group; inside a run the tap is the outer loop, so ONE sampling plan (per position and tap) serves
+// every channel block of the run.  All warp roles iterate this same sequence.
+//   F(cc, tap, first_of_phase, blocks_in_phase)
+template <typename F>
+__device__ __forceinline__ void for_each_kblock(const TcFwdParams& prm, int grp, F&& f) {
+  const int gb0 = grp * prm.ccs;
+  int cc = 0;
+  while (cc < prm.ccs) {
+    const int room = prm.bpd - (gb0 + cc) % prm.bpd;
+    const int run_end = cc + room < prm.ccs ? cc + room : prm.ccs;
+    for (int tap = 0; tap < prm.g.K; ++tap)
+      for (int c = cc; c < run_end; ++c) f(c, tap, c == cc, run_end - cc);
+    cc = run_end;
+  }
+}
 
 template <typename T, int ND, bool MOD>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -64,11 +88,13 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const TcFwdParams prm) 
   uint8_t* sB = sA + TC_STAGES * TC_A_BYTES;
   PlanEntry<ND>* sPlan = reinterpret_cast<PlanEntry<ND>*>(sB + TC_STAGES * TC_B_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sPlan) +
-                                               TC_STAGES * TC_BM * sizeof(PlanEntry<ND>));
+                                               TC_PLAN_SLOTS * TC_BM * sizeof(PlanEntry<ND>));
   uint64_t* full_a = bars;
-  uint64_t* full_b = bars + TC_STAGES;
-  uint64_t* empty = bars + 2 * TC_STAGES;
-  uint64_t* tmem_full = bars + 3 * TC_STAGES;
+  uint64_t* full_b = full_a + TC_STAGES;
+  uint64_t* empty = full_b + TC_STAGES;
+  uint64_t* plan_full = empty + TC_STAGES;
+  uint64_t* plan_empty = plan_full + TC_PLAN_SLOTS;
+  uint64_t* tmem_full = plan_empty + TC_PLAN_SLOTS;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -82,6 +108,10 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const TcFwdParams prm) 
       ptx::mbar_init(&full_a[s], TC_GATHER_THREADS);
       ptx::mbar_init(&full_b[s], 1);
       ptx::mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < TC_PLAN_SLOTS; ++s) {
+      ptx::mbar_init(&plan_full[s], TC_BM);
+      ptx::mbar_init(&plan_empty[s], TC_GATHER_THREADS);
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tmem_full[s], 1);
@@ -107,12 +137,12 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const TcFwdParams prm) 
         const int rest = t / prm.m_tiles;
         const int nt = rest % prm.n_tiles, grp = rest / prm.n_tiles;
         const int row0 = grp * g.Cog + nt * BN;
-        for (int kb = 0; kb < prm.kblocks; ++kb) {
+        for_each_kblock(prm, grp, [&](int cc, int tap, bool, int) {
           ptx::mbar_wait(&empty[s], ph ^ 1);
           ptx::mbar_arrive_expect_tx(&full_b[s], (uint32_t)BN * 128u);
-          ptx::tma_load_2d(sB + s * TC_B_BYTES, &tmap_w, &full_b[s], kb * TC_BK, row0);
+          ptx::tma_load_2d(sB + s * TC_B_BYTES, &tmap_w, &full_b[s], (cc * g.K + tap) * TC_BK, row0);
           if (++s == TC_STAGES) { s = 0; ph ^= 1; }
-        }
+        });
       }
     }
   } else if (warp == 1) {
@@ -184,52 +214,73 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const TcFwdParams prm) 
       ptx::mbar_arrive(&tmem_empty[as]);
       if (++as == 2) { as = 0; aph ^= 1; }
     }
-  } else if (warp >= 8) {
-    // ===================== gather producers =====================
-    const int gt = threadIdx.x - 256;  // 0..255
-    const int gw = gt >> 5;            // gather warp 0..7
+  } else if (warp >= TC_PLAN_WARP0 && warp < TC_GATHER_WARP0) {
+    // ===================== plan producers =====================
+    // One thread per tile row: the sampling plan of (row, tap) for the current deformable-group run
+    // (corner indices + weight*mask, reference src/mdeformable_conv.cu:59-83 computes this per
+    // channel), written into a ring of plan slots that runs ahead of the gather warps.
+    const int row = threadIdx.x - TC_PLAN_WARP0 * 32;
     const T* __restrict__ off = reinterpret_cast<const T*>(prm.off);
     const T* __restrict__ mask = reinterpret_cast<const T*>(prm.mask);
-    const uint4* __restrict__ xq = reinterpret_cast<const uint4*>(prm.xt);
     const int C8 = g.C >> 3;
-    int s = 0;
-    uint32_t ph = 0;
+    int ps = 0;
+    uint32_t pph = 0;
     for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x) {
       const int mt = t % prm.m_tiles;
       const int grp = (t / prm.m_tiles) / prm.n_tiles;
-      // row metadata for the plan threads (gt < 128 owns pixel row gt of the tile)
+      const long long gp = (long long)mt * TC_BM + row;
+      const bool v = gp < total_pix;
       RowCoord<ND> rc;
-      rc.valid = false;
-      if (gt < TC_BM) {
-        const long long gp = (long long)mt * TC_BM + gt;
-        const bool v = gp < total_pix;
-        tc::decode_row<ND>(g, v ? (int)(gp / g.P) : 0, v ? (int)(gp % g.P) : 0, v, rc);
-      }
-      for (int kb = 0; kb < prm.kblocks; ++kb) {
-        const int cc = kb / g.K, tap = kb - cc * g.K;
-        const int c0 = grp * g.Cg + cc * TC_BK;  // first channel of this K-block
-        const uint32_t plan_addr = ptx::smem_u32(sPlan + s * TC_BM);
-        if (gt < TC_BM) {
-          const PlanEntry<ND> e = tc::make_plan_entry<T, ND, MOD>(g, off, mask, rc, c0, tap, C8);
-          tc::store_plan<ND>(plan_addr + gt * (uint32_t)sizeof(PlanEntry<ND>), e);
+      tc::decode_row<ND>(g, v ? (int)(gp / g.P) : 0, v ? (int)(gp % g.P) : 0, v, rc);
+      for_each_kblock(prm, grp, [&](int cc, int tap, bool first, int) {
+        if (!first) return;
+        const PlanEntry<ND> e = tc::make_plan_entry<T, ND, MOD>(g, off, mask, rc, grp * g.Cg + cc * TC_BK, tap, C8);
+        ptx::mbar_wait(&plan_empty[ps], pph ^ 1);
+        tc::store_plan<ND>(ptx::smem_u32(sPlan + ps * TC_BM + row), e);
+        ptx::mbar_arrive(&plan_full[ps]);
+        if (++ps == TC_PLAN_SLOTS) { ps = 0; pph ^= 1; }
+      });
+    }
+  } else if (warp >= TC_GATHER_WARP0) {
+    // ===================== gather producers =====================
+    // 16 warps x 2 passes x 4 rows = 128 rows per K-block; 8 lanes x 16 bytes cover the 64 channels
+    // of one corner.  All 8 corner loads of a thread are issued before the first is consumed.
+    const int gw = warp - TC_GATHER_WARP0;
+    const int chunk = lane & 7;
+    const int row0 = gw * 8 + (lane >> 3);
+    const uint4* __restrict__ xq = reinterpret_cast<const uint4*>(prm.xt);
+    int s = 0, ps = 0;
+    uint32_t ph = 0, pph = 0;
+    for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x) {
+      const int grp = (t / prm.m_tiles) / prm.n_tiles;
+      uint32_t plan_addr = 0;
+      int left = 0;
+      for_each_kblock(prm, grp, [&](int cc, int, bool first, int nblk) {
+        if (first) {
+          ptx::mbar_wait(&plan_full[ps], pph);
+          plan_addr = ptx::smem_u32(sPlan + ps * TC_BM + row0);
+          left = nblk;
         }
-        ptx::named_bar_sync(1, TC_GATHER_THREADS);  // plan visible to all gather warps
-
+        const uint4* xc = xq + ((grp * g.Cg + cc * TC_BK) >> 3) + chunk;
         ptx::mbar_wait(&empty[s], ph ^ 1);          // MMA has finished reading A[s]
         const uint32_t a_addr = ptx::smem_u32(sA + s * TC_A_BYTES);
-        const int chunk = lane & 7;
-        const uint4* xc = xq + (c0 >> 3) + chunk;
+        PlanEntry<ND> e0 = tc::load_plan<ND>(plan_addr);
+        PlanEntry<ND> e1 = tc::load_plan<ND>(plan_addr + 4 * (uint32_t)sizeof(PlanEntry<ND>));
+        uint4 v0[1 << ND], v1[1 << ND];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int row = gw * 16 + j * 4 + (lane >> 3);
-          const PlanEntry<ND> e = tc::load_plan<ND>(plan_addr + row * (uint32_t)sizeof(PlanEntry<ND>));
-          const uint4 r = tc::gather8<T, ND>(xc, e);
-          tc::sts128(a_addr + tc::sw128(row, chunk), r);
-        }
+        for (int c = 0; c < (1 << ND); ++c) v0[c] = __ldg(xc + e0.idx[c]);
+#pragma unroll
+        for (int c = 0; c < (1 << ND); ++c) v1[c] = __ldg(xc + e1.idx[c]);
+        tc::sts128(a_addr + tc::sw128(row0, chunk), tc::interp8(v0, e0.w, 1 << ND, T()));
+        tc::sts128(a_addr + tc::sw128(row0 + 4, chunk), tc::interp8(v1, e1.w, 1 << ND, T()));
         ptx::fence_proxy_async_smem();
         ptx::mbar_arrive(&full_a[s]);
         if (++s == TC_STAGES) { s = 0; ph ^= 1; }
-      }
+        if (--left == 0) {                            // last K-block that uses this plan slot
+          ptx::mbar_arrive(&plan_empty[ps]);
+          if (++ps == TC_PLAN_SLOTS) { ps = 0; pph ^= 1; }
+        }
+      });
     }
   }
 
@@ -289,8 +340,8 @@ int pick_bn(const DevGeom& g) { return g.Cog <= TC_MAX_BN ? g.Cog : TC_MAX_BN; }
 
 template <int ND>
 size_t fwd_smem_bytes() {
-  return 1024 + (size_t)TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + (size_t)TC_STAGES * TC_BM * sizeof(PlanEntry<ND>) +
-         (3 * TC_STAGES + 4) * sizeof(uint64_t) + 16;
+  return 1024 + (size_t)TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + (size_t)TC_PLAN_SLOTS * TC_BM * sizeof(PlanEntry<ND>) +
+         (3 * TC_STAGES + 2 * TC_PLAN_SLOTS + 4) * sizeof(uint64_t) + 16;
 }
 
 template <typename T, int ND, bool MOD>
@@ -324,6 +375,7 @@ void tensor_forward_t(const DevGeom& g, const void* x, const void* w, const void
   prm.n_tiles = g.Cog / prm.BN;
   prm.total_tiles = prm.m_tiles * prm.n_tiles * g.g;
   prm.ccs = g.Cg / TC_BK;
+  prm.bpd = g.Cdg / TC_BK;
   prm.kblocks = prm.ccs * g.K;
 
   tc::PFN_encodeTiled enc = tc::get_encode_fn();
