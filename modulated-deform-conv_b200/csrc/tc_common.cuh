@@ -78,41 +78,64 @@ struct SamplePos {
   float m;
 };
 
+// Raw offset / mask values of one (row, deformable group, tap): the only global loads of a plan.
+// Split from the arithmetic so a producer can fetch the next plan's values while it builds this one.
+template <int ND>
+struct RawSample {
+  float o[ND];
+  float m;
+};
+
 template <typename T, int ND, bool MOD>
-__device__ __forceinline__ void sample_pos(const DevGeom& g, const T* __restrict__ off, const T* __restrict__ mask,
-                                           const RowCoord<ND>& rc, int dgi, int tap, SamplePos<ND>& sp) {
+__device__ __forceinline__ RawSample<ND> fetch_sample(const DevGeom& g, const T* __restrict__ off,
+                                                      const T* __restrict__ mask, const RowCoord<ND>& rc, int dgi,
+                                                      int tap) {
+  RawSample<ND> r;
+  const size_t ch = (size_t)rc.b * g.dg * g.K + (size_t)dgi * g.K + tap;
+  const T* op = off + ch * ND * g.P + rc.p;
+#pragma unroll
+  for (int a = 0; a < ND; ++a) r.o[a] = ld_as<float>(op + (size_t)a * g.P);
+  r.m = 1.f;
+  if (MOD) r.m = ld_as<float>(mask + ch * g.P + rc.p);
+  return r;
+}
+
+template <int ND>
+__device__ __forceinline__ void build_pos(const DevGeom& g, const RowCoord<ND>& rc, int tap, const RawSample<ND>& r,
+                                          SamplePos<ND>& sp) {
   int tt[3];
   if (ND == 2) {
     tt[1] = tap % g.k[1]; tt[0] = tap / g.k[1];
   } else {
     tt[2] = tap % g.k[2]; const int q = tap / g.k[2]; tt[1] = q % g.k[1]; tt[0] = q / g.k[1];
   }
-  const size_t ch = (size_t)rc.b * g.dg * g.K + (size_t)dgi * g.K + tap;
-  const T* op = off + ch * ND * g.P + rc.p;
   sp.in_range = true;
 #pragma unroll
   for (int a = 0; a < ND; ++a) {
-    const float pos = (float)(rc.base[a] + tt[a] * g.d[a]) + ld_as<float>(op + (size_t)a * g.P);
+    const float pos = (float)(rc.base[a] + tt[a] * g.d[a]) + r.o[a];
     const float fl = floorf(pos);
     sp.lo[a] = (int)fl;
     sp.fr[a] = pos - fl;
     sp.in_range = sp.in_range && (pos > -1.f) && (pos < (float)g.in[a]);
   }
-  sp.m = 1.f;
-  if (MOD) sp.m = ld_as<float>(mask + ch * g.P + rc.p);
+  sp.m = r.m;
 }
 
 template <typename T, int ND, bool MOD>
-__device__ __forceinline__ PlanEntry<ND> make_plan_entry(const DevGeom& g, const T* __restrict__ off,
-                                                         const T* __restrict__ mask, const RowCoord<ND>& rc, int c0,
-                                                         int tap, int C8) {
+__device__ __forceinline__ void sample_pos(const DevGeom& g, const T* __restrict__ off, const T* __restrict__ mask,
+                                           const RowCoord<ND>& rc, int dgi, int tap, SamplePos<ND>& sp) {
+  const RawSample<ND> r = fetch_sample<T, ND, MOD>(g, off, mask, rc, dgi, tap);
+  build_pos<ND>(g, rc, tap, r, sp);
+}
+
+// corner indices + weights of an already-located sample
+template <typename T, int ND>
+__device__ __forceinline__ PlanEntry<ND> plan_from_pos(const DevGeom& g, const RowCoord<ND>& rc,
+                                                       const SamplePos<ND>& sp, int C8) {
   PlanEntry<ND> e;
 #pragma unroll
   for (int c = 0; c < (1 << ND); ++c) { e.idx[c] = 0; e.w[c] = 0u; }
-  if (!rc.valid) return e;
-  SamplePos<ND> sp;
-  sample_pos<T, ND, MOD>(g, off, mask, rc, c0 / g.Cdg, tap, sp);
-  if (!sp.in_range) return e;
+  if (!rc.valid || !sp.in_range) return e;
 #pragma unroll
   for (int c = 0; c < (1 << ND); ++c) {
     float w = sp.m;
@@ -132,6 +155,16 @@ __device__ __forceinline__ PlanEntry<ND> make_plan_entry(const DevGeom& g, const
     }
   }
   return e;
+}
+
+template <typename T, int ND, bool MOD>
+__device__ __forceinline__ PlanEntry<ND> make_plan_entry(const DevGeom& g, const T* __restrict__ off,
+                                                         const T* __restrict__ mask, const RowCoord<ND>& rc, int c0,
+                                                         int tap, int C8) {
+  SamplePos<ND> sp;
+  sp.in_range = false;
+  if (rc.valid) sample_pos<T, ND, MOD>(g, off, mask, rc, c0 / g.Cdg, tap, sp);
+  return plan_from_pos<T, ND>(g, rc, sp, C8);
 }
 
 template <int ND>

@@ -17,9 +17,13 @@ namespace tc {
 
 namespace {
 
-constexpr int GW_THREADS = 512;
-constexpr int GW_GATHER_THREADS = 256;
+constexpr int GW_PLAN_WARP0 = 8;     // warps 8-11: plan producers
+constexpr int GW_GATHER_WARP0 = 12;  // warps 12-27: gather producers
+constexpr int GW_GATHER_WARPS = 16;
+constexpr int GW_GATHER_THREADS = GW_GATHER_WARPS * 32;
+constexpr int GW_THREADS = (GW_GATHER_WARP0 + GW_GATHER_WARPS) * 32;  // 896
 constexpr int GW_STAGES = 3;
+constexpr int GW_PLAN_SLOTS = 4;
 constexpr int GW_NB = 2;                       // 64-wide kk blocks per CTA tile (N = 128)
 constexpr int GW_GO_BYTES = 2 * 128 * 128;     // two M tiles of [128 co x 64 pos]
 constexpr int GW_COL_BYTES = GW_NB * 64 * 128; // NB blocks of [64 pos x 64 kk]
@@ -47,11 +51,13 @@ k_tc_grad_weight(const __grid_constant__ CUtensorMap tmap_go, const TcGwParams p
   uint8_t* sCol = sGo + GW_STAGES * GW_GO_BYTES;
   PlanEntry<ND>* sPlan = reinterpret_cast<PlanEntry<ND>*>(sCol + GW_STAGES * GW_COL_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sPlan) +
-                                               GW_STAGES * 128 * sizeof(PlanEntry<ND>));
+                                               GW_PLAN_SLOTS * 128 * sizeof(PlanEntry<ND>));
   uint64_t* full_go = bars;
-  uint64_t* full_col = bars + GW_STAGES;
-  uint64_t* empty = bars + 2 * GW_STAGES;
-  uint64_t* done = bars + 3 * GW_STAGES;
+  uint64_t* full_col = full_go + GW_STAGES;
+  uint64_t* empty = full_col + GW_STAGES;
+  uint64_t* plan_full = empty + GW_STAGES;
+  uint64_t* plan_empty = plan_full + GW_PLAN_SLOTS;
+  uint64_t* done = plan_empty + GW_PLAN_SLOTS;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done + 1);
 
   const DevGeom& g = prm.g;
@@ -76,6 +82,10 @@ k_tc_grad_weight(const __grid_constant__ CUtensorMap tmap_go, const TcGwParams p
       ptx::mbar_init(&full_go[s], 1);
       ptx::mbar_init(&full_col[s], GW_GATHER_THREADS);
       ptx::mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < GW_PLAN_SLOTS; ++s) {
+      ptx::mbar_init(&plan_full[s], 128);
+      ptx::mbar_init(&plan_empty[s], GW_GATHER_THREADS);
     }
     ptx::mbar_init(done, 1);
     ptx::fence_barrier_init();
@@ -151,53 +161,82 @@ k_tc_grad_weight(const __grid_constant__ CUtensorMap tmap_go, const TcGwParams p
         }
       }
     }
-  } else if (warp >= 8) {
-    // ===================== gather producers: column tiles =====================
-    const int gt = threadIdx.x - 256;
+  } else if (warp >= GW_PLAN_WARP0 && warp < GW_GATHER_WARP0) {
+    // ===================== plan producers =====================
+    // thread (blk, row): the sampling plan of position p0 + row for this CTA's kk block `blk`; the
+    // offset / mask values of the NEXT position block are fetched while this one is built.
+    const int pt = threadIdx.x - GW_PLAN_WARP0 * 32;
     const T* __restrict__ off = reinterpret_cast<const T*>(prm.off);
     const T* __restrict__ mask = reinterpret_cast<const T*>(prm.mask);
-    const uint4* __restrict__ xq = reinterpret_cast<const uint4*>(prm.xt);
     const int C8 = g.C >> 3;
-    // the (channel block, tap) of the block this thread plans for
-    const int prow = gt & 63, pblk = (gt >> 6) & 1;
+    const int prow = pt & 63, pblk = pt >> 6;
     const int kkb = nt * GW_NB + pblk;
     const int pcc = kkb / g.K, ptap = kkb - pcc * g.K;
-    const int pc0 = grp * g.Cg + pcc * BK;
-    int c0_blk[GW_NB];
-#pragma unroll
-    for (int j = 0; j < GW_NB; ++j) c0_blk[j] = grp * g.Cg + ((nt * GW_NB + j) / g.K) * BK;
-    int s = 0;
-    uint32_t ph = 0;
-    for (int pb = pb0; pb < pb1; ++pb) {
+    const int pdg = (grp * g.Cg + pcc * BK) / g.Cdg;
+    const bool active = pblk < nb;
+    auto coord = [&](int pb, RowCoord<ND>& rc) {
       const int b = pb / prm.pbi, p0 = (pb - b * prm.pbi) * 64;
-      const uint32_t plan_addr = ptx::smem_u32(sPlan + s * 128);
-      if (gt < 128) {
-        RowCoord<ND> rc;
-        const bool v = (pblk < nb) && (p0 + prow < g.P);
-        decode_row<ND>(g, b, p0 + prow, v, rc);
-        const PlanEntry<ND> e = make_plan_entry<T, ND, MOD>(g, off, mask, rc, pc0, ptap, C8);
-        store_plan<ND>(plan_addr + gt * (uint32_t)sizeof(PlanEntry<ND>), e);
+      decode_row<ND>(g, b, p0 + prow, active && (p0 + prow < g.P), rc);
+    };
+    RowCoord<ND> rc_next;
+    RawSample<ND> raw_next;
+    if (pb0 < pb1) {
+      coord(pb0, rc_next);
+      if (rc_next.valid) raw_next = fetch_sample<T, ND, MOD>(g, off, mask, rc_next, pdg, ptap);
+    }
+    int ps = 0;
+    uint32_t pph = 0;
+    for (int pb = pb0; pb < pb1; ++pb) {
+      const RowCoord<ND> rc = rc_next;
+      const RawSample<ND> raw = raw_next;
+      if (pb + 1 < pb1) {
+        coord(pb + 1, rc_next);
+        if (rc_next.valid) raw_next = fetch_sample<T, ND, MOD>(g, off, mask, rc_next, pdg, ptap);
       }
-      ptx::named_bar_sync(1, GW_GATHER_THREADS);
+      SamplePos<ND> sp;
+      sp.in_range = false;
+      if (rc.valid) build_pos<ND>(g, rc, ptap, raw, sp);
+      const PlanEntry<ND> e = plan_from_pos<T, ND>(g, rc, sp, C8);
+      ptx::mbar_wait(&plan_empty[ps], pph ^ 1);
+      store_plan<ND>(ptx::smem_u32(sPlan + ps * 128 + pt), e);
+      ptx::mbar_arrive(&plan_full[ps]);
+      if (++ps == GW_PLAN_SLOTS) { ps = 0; pph ^= 1; }
+    }
+  } else if (warp >= GW_GATHER_WARP0) {
+    // ===================== gather producers: column tiles =====================
+    // 128 plan rows = NB blocks x 64 positions; warp gw owns rows gw*8 .. gw*8+7 (two passes of 4).
+    const int gw = warp - GW_GATHER_WARP0;
+    const int chunk = lane & 7;
+    const int q0 = gw * 8 + (lane >> 3);     // plan row of pass 0 (pass 1: +4)
+    const int jb = q0 >> 6;                  // kk block of this warp
+    const int r0 = q0 & 63;                  // position row inside the block
+    const uint4* __restrict__ xq = reinterpret_cast<const uint4*>(prm.xt);
+    const int c0_blk = grp * g.Cg + ((nt * GW_NB + jb) / g.K) * BK;
+    const uint4* xc = xq + (c0_blk >> 3) + chunk;
+    const bool active = jb < nb;
+    int s = 0, ps = 0;
+    uint32_t ph = 0, pph = 0;
+    for (int pb = pb0; pb < pb1; ++pb) {
+      ptx::mbar_wait(&plan_full[ps], pph);
       ptx::mbar_wait(&empty[s], ph ^ 1);
-      const uint32_t col_addr = ptx::smem_u32(sCol + s * GW_COL_BYTES);
-      const int chunk = gt & 7;
+      if (active) {
+        const uint32_t plan_addr = ptx::smem_u32(sPlan + ps * 128 + q0);
+        const uint32_t col_addr = ptx::smem_u32(sCol + s * GW_COL_BYTES) + jb * 8192;
+        const PlanEntry<ND> e0 = load_plan<ND>(plan_addr);
+        const PlanEntry<ND> e1 = load_plan<ND>(plan_addr + 4 * (uint32_t)sizeof(PlanEntry<ND>));
+        uint4 v0[1 << ND], v1[1 << ND];
 #pragma unroll
-      for (int j = 0; j < GW_NB; ++j) {
-        if (j < nb) {
-          const uint4* xc = xq + (c0_blk[j] >> 3) + chunk;
+        for (int c = 0; c < (1 << ND); ++c) v0[c] = __ldg(xc + e0.idx[c]);
 #pragma unroll
-          for (int pass = 0; pass < 2; ++pass) {
-            const int row = pass * 32 + (gt >> 3);
-            const PlanEntry<ND> e = load_plan<ND>(plan_addr + (j * 64 + row) * (uint32_t)sizeof(PlanEntry<ND>));
-            const uint4 r = gather8<T, ND>(xc, e);
-            sts128(col_addr + j * 8192 + sw128(row, chunk), r);
-          }
-        }
+        for (int c = 0; c < (1 << ND); ++c) v1[c] = __ldg(xc + e1.idx[c]);
+        sts128(col_addr + sw128(r0, chunk), interp8(v0, e0.w, 1 << ND, T()));
+        sts128(col_addr + sw128(r0 + 4, chunk), interp8(v1, e1.w, 1 << ND, T()));
       }
       ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(&full_col[s]);
+      ptx::mbar_arrive(&plan_empty[ps]);
       if (++s == GW_STAGES) { s = 0; ph ^= 1; }
+      if (++ps == GW_PLAN_SLOTS) { ps = 0; pph ^= 1; }
     }
   }
 
@@ -238,8 +277,8 @@ int gw_splits(const DevGeom& g) {
 
 template <int ND>
 size_t gw_smem_bytes() {
-  return 1024 + (size_t)GW_STAGES * (GW_GO_BYTES + GW_COL_BYTES) + (size_t)GW_STAGES * 128 * sizeof(PlanEntry<ND>) +
-         (3 * GW_STAGES + 1) * sizeof(uint64_t) + 16;
+  return 1024 + (size_t)GW_STAGES * (GW_GO_BYTES + GW_COL_BYTES) + (size_t)GW_PLAN_SLOTS * 128 * sizeof(PlanEntry<ND>) +
+         (3 * GW_STAGES + 2 * GW_PLAN_SLOTS + 1) * sizeof(uint64_t) + 16;
 }
 
 template <typename T, int ND, bool MOD>

@@ -30,11 +30,25 @@ namespace {
 
 constexpr int GI_BM = 128;
 constexpr int GI_STAGES = 3;
+constexpr int GI_PLAN_SLOTS = 2;
 constexpr int GI_MAX_BN = 256;
-constexpr int GI_THREADS = 512;
-constexpr int GI_GATHER_THREADS = 256;
+constexpr int GI_PLAN_WARP0 = 8;      // warps 8-11: plan producers (bin heads -> smem)
+constexpr int GI_GATHER_WARP0 = 12;   // warps 12-27: gather producers
+constexpr int GI_GATHER_WARPS = 16;
+constexpr int GI_GATHER_THREADS = GI_GATHER_WARPS * 32;
+constexpr int GI_THREADS = (GI_GATHER_WARP0 + GI_GATHER_WARPS) * 32;  // 896
 constexpr int GI_A_BYTES = GI_BM * 128;
 constexpr int GI_B_BYTES = GI_MAX_BN * 128;
+constexpr int GI_NE = 8;  // bin entries staged per (position, tap); longer bins continue from global memory
+
+// One (input position, tap) of the tile: the first GI_NE entries of its bin, ready for the gather.
+struct __align__(16) GiPlanRow {
+  int idx[GI_NE];      // uint4 index of the entry's 8-channel vector in channels-last grad_output (chunk excluded)
+  __half w[GI_NE];     // interpolation weight x mask (values in [0, max|mask|]; fp16 keeps 11 bits)
+  int n;               // entries in the bin
+  int e0;              // index of the bin's first entry (for bins longer than GI_NE)
+};
+static_assert(sizeof(GiPlanRow) == 64, "GiPlanRow must be 64 bytes");
 
 struct BinEntry {
   int row;   // b * P + output position: row of the channels-last grad_output
@@ -128,8 +142,9 @@ template <> struct Acc8<__half> {
 #pragma unroll
     for (int i = 0; i < 4; ++i) a[i] = __float2half2_rn(0.f);
   }
-  __device__ __forceinline__ void fma(const uint4& v, float w) {
-    const __half2 wh = __float2half2_rn(w);
+  __device__ __forceinline__ void fma(const uint4& v, float w) { fma(v, __float2half_rn(w)); }
+  __device__ __forceinline__ void fma(const uint4& v, __half w) {
+    const __half2 wh = __half2half2(w);
     const __half2* h = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
     for (int i = 0; i < 4; ++i) a[i] = __hfma2(wh, h[i], a[i]);
@@ -148,6 +163,7 @@ template <> struct Acc8<__nv_bfloat16> {
 #pragma unroll
     for (int i = 0; i < 8; ++i) a[i] = 0.f;
   }
+  __device__ __forceinline__ void fma(const uint4& v, __half w) { fma(v, __half2float(w)); }
   __device__ __forceinline__ void fma(const uint4& v, float w) {
     const uint32_t* u = reinterpret_cast<const uint32_t*>(&v);
 #pragma unroll
@@ -168,8 +184,6 @@ template <> struct Acc8<__nv_bfloat16> {
   }
 };
 
-constexpr int GI_NE = 8;  // bin entries fetched as one batch (loads issued together); longer bins loop
-
 template <typename T>
 __global__ void __launch_bounds__(GI_THREADS, 1)
 k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const TcGiParams prm) {
@@ -177,11 +191,14 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const TcGiParams pr
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = sA + GI_STAGES * GI_A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + GI_STAGES * GI_B_BYTES);
+  GiPlanRow* sPlan = reinterpret_cast<GiPlanRow*>(sB + GI_STAGES * GI_B_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sPlan + GI_PLAN_SLOTS * GI_BM);
   uint64_t* full_a = bars;
-  uint64_t* full_b = bars + GI_STAGES;
-  uint64_t* empty = bars + 2 * GI_STAGES;
-  uint64_t* tmem_full = bars + 3 * GI_STAGES;
+  uint64_t* full_b = full_a + GI_STAGES;
+  uint64_t* empty = full_b + GI_STAGES;
+  uint64_t* plan_full = empty + GI_STAGES;
+  uint64_t* plan_empty = plan_full + GI_PLAN_SLOTS;
+  uint64_t* tmem_full = plan_empty + GI_PLAN_SLOTS;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -195,6 +212,10 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const TcGiParams pr
       ptx::mbar_init(&full_a[s], GI_GATHER_THREADS);
       ptx::mbar_init(&full_b[s], 1);
       ptx::mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < GI_PLAN_SLOTS; ++s) {
+      ptx::mbar_init(&plan_full[s], GI_BM);
+      ptx::mbar_init(&plan_empty[s], GI_GATHER_THREADS);
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tmem_full[s], 1);
@@ -288,69 +309,105 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const TcGiParams pr
       ptx::mbar_arrive(&tmem_empty[as]);
       if (++as == 2) { as = 0; aph ^= 1; }
     }
-  } else if (warp >= 8) {
-    // ===================== gather producers =====================
-    const int gt = threadIdx.x - 256;
-    const int gw = gt >> 5;
-    const int chunk = lane & 7;
-    const uint4* __restrict__ gq = reinterpret_cast<const uint4*>(prm.got);
+  } else if (warp >= GI_PLAN_WARP0 && warp < GI_GATHER_WARP0) {
+    // ===================== plan producers =====================
+    // thread = tile row (input position): per tap, copy the head of the bin into shared memory; the
+    // bin bounds of the next tap are fetched while this tap's entries are in flight.
+    const int row = threadIdx.x - GI_PLAN_WARP0 * 32;
     const int* __restrict__ bin_start = prm.bin_start;
-    const BinEntry* __restrict__ entries = prm.entries;
+    const int4* __restrict__ entries4 = reinterpret_cast<const int4*>(prm.entries);
+    const int2* __restrict__ entries2 = reinterpret_cast<const int2*>(prm.entries);
     const int Co8 = g.Co >> 3;
-    int s = 0;
-    uint32_t ph = 0;
+    int ps = 0;
+    uint32_t pph = 0;
     for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x) {
       const int mt = t % prm.m_tiles;
       const int nt = t / prm.m_tiles;
-      const int c0 = nt * BN;
-      const int grp = c0 / g.Cg;
-      const int dgi = c0 / g.Cdg;
-      // first bin (tap 0) of this thread's four rows
-      long long bin0[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const long long gp = (long long)mt * GI_BM + gw * 16 + j * 4 + (lane >> 3);
-        if (gp < total_pos) {
-          const long long b = gp / g.IN, pix = gp - b * g.IN;
-          bin0[j] = ((b * g.dg + dgi) * g.IN + pix) * g.K;
-        } else {
-          bin0[j] = -1;
-        }
+      const int dgi = (nt * BN) / g.Cdg;
+      const long long gp = (long long)mt * GI_BM + row;
+      long long bin0 = -1;
+      if (gp < total_pos) {
+        const long long b = gp / g.IN, pix = gp - b * g.IN;
+        bin0 = ((b * g.dg + dgi) * g.IN + pix) * g.K;
       }
-      for (int kb = 0; kb < prm.kblocks; ++kb) {
-        const int tap = kb / prm.cobs, cob = kb - tap * prm.cobs;
-        const uint4* gc = gq + ((grp * g.Cog + cob * 64) >> 3) + chunk;
-        ptx::mbar_wait(&empty[s], ph ^ 1);
-        const uint32_t a_addr = ptx::smem_u32(sA + s * GI_A_BYTES);
+      int e_lo = 0, e_hi = 0;
+      if (bin0 >= 0) { e_lo = __ldg(bin_start + bin0); e_hi = __ldg(bin_start + bin0 + 1); }
+      for (int tap = 0; tap < g.K; ++tap) {
+        const int e0 = e_lo, n = e_hi - e_lo;
+        e_lo = e_hi;
+        if (bin0 >= 0 && tap + 1 < g.K) e_hi = __ldg(bin_start + bin0 + tap + 2);
+        GiPlanRow r;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int row = gw * 16 + j * 4 + (lane >> 3);
-          Acc8<T> acc;
-          acc.clear();
-          if (bin0[j] >= 0) {
-            const int e0 = __ldg(bin_start + bin0[j] + tap), e1 = __ldg(bin_start + bin0[j] + tap + 1);
-            const int n = e1 - e0;
-            const int2* ep = reinterpret_cast<const int2*>(entries) + e0;
-            int2 ev[GI_NE];
+        for (int i = 0; i < GI_NE; ++i) { r.idx[i] = 0; r.w[i] = __float2half_rn(0.f); }
+        r.n = n;
+        r.e0 = e0;
+        // entries are 8 bytes; read pairs with 16-byte loads when the bin start is even
 #pragma unroll
-            for (int i = 0; i < GI_NE; ++i) ev[i] = i < n ? __ldg(ep + i) : make_int2(0, 0);
+        for (int i = 0; i < GI_NE; ++i) {
+          if (i < n) {
+            const int2 ev = __ldg(entries2 + e0 + i);
+            r.idx[i] = ev.x * Co8;
+            r.w[i] = __float2half_rn(__int_as_float(ev.y));
+          }
+        }
+        (void)entries4;
+        ptx::mbar_wait(&plan_empty[ps], pph ^ 1);
+        const uint32_t pa = ptx::smem_u32(sPlan + ps * GI_BM + row);
+        const uint4* q = reinterpret_cast<const uint4*>(&r);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sts128(pa + 16 * i, q[i]);
+        ptx::mbar_arrive(&plan_full[ps]);
+        if (++ps == GI_PLAN_SLOTS) { ps = 0; pph ^= 1; }
+      }
+    }
+  } else if (warp >= GI_GATHER_WARP0) {
+    // ===================== gather producers =====================
+    const int gw = warp - GI_GATHER_WARP0;
+    const int chunk = lane & 7;
+    const int row0 = gw * 8 + (lane >> 3);
+    const uint4* __restrict__ gq = reinterpret_cast<const uint4*>(prm.got);
+    const int2* __restrict__ entries2 = reinterpret_cast<const int2*>(prm.entries);
+    const int Co8 = g.Co >> 3;
+    int s = 0, ps = 0;
+    uint32_t ph = 0, pph = 0;
+    for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x) {
+      const int nt = t / prm.m_tiles;
+      const int grp = (nt * BN) / g.Cg;
+      for (int tap = 0; tap < g.K; ++tap) {
+        ptx::mbar_wait(&plan_full[ps], pph);
+        const uint32_t plan_addr = ptx::smem_u32(sPlan + ps * GI_BM + row0);
+        for (int cob = 0; cob < prm.cobs; ++cob) {
+          const uint4* gc = gq + ((grp * g.Cog + cob * 64) >> 3) + chunk;
+          ptx::mbar_wait(&empty[s], ph ^ 1);
+          const uint32_t a_addr = ptx::smem_u32(sA + s * GI_A_BYTES);
+#pragma unroll
+          for (int pass = 0; pass < 2; ++pass) {
+            const uint32_t pa = plan_addr + pass * 4 * (uint32_t)sizeof(GiPlanRow);
+            const uint4 i0 = lds128(pa), i1 = lds128(pa + 16), wv = lds128(pa + 32), meta = lds128(pa + 48);
+            const int idx[GI_NE] = {(int)i0.x, (int)i0.y, (int)i0.z, (int)i0.w, (int)i1.x, (int)i1.y, (int)i1.z, (int)i1.w};
+            const __half* wh = reinterpret_cast<const __half*>(&wv);
+            const int n = (int)meta.x;
             uint4 v[GI_NE];
 #pragma unroll
             for (int i = 0; i < GI_NE; ++i)
-              if (i < n) v[i] = __ldg(gc + (size_t)ev[i].x * Co8);
+              if (i < n) v[i] = __ldg(gc + idx[i]);
+            Acc8<T> acc;
+            acc.clear();
 #pragma unroll
             for (int i = 0; i < GI_NE; ++i)
-              if (i < n) acc.fma(v[i], __int_as_float(ev[i].y));
-            for (int e = GI_NE; e < n; ++e) {
-              const int2 ee = __ldg(ep + e);
+              if (i < n) acc.fma(v[i], wh[i]);
+            for (int e = GI_NE; e < n; ++e) {   // rare: bins longer than the staged head
+              const int2 ee = __ldg(entries2 + (int)meta.y + e);
               acc.fma(__ldg(gc + (size_t)ee.x * Co8), __int_as_float(ee.y));
             }
+            sts128(a_addr + sw128(row0 + pass * 4, chunk), acc.pack());
           }
-          sts128(a_addr + sw128(row, chunk), acc.pack());
+          ptx::fence_proxy_async_smem();
+          ptx::mbar_arrive(&full_a[s]);
+          if (++s == GI_STAGES) { s = 0; ph ^= 1; }
         }
-        ptx::fence_proxy_async_smem();
-        ptx::mbar_arrive(&full_a[s]);
-        if (++s == GI_STAGES) { s = 0; ph ^= 1; }
+        ptx::mbar_arrive(&plan_empty[ps]);
+        if (++ps == GI_PLAN_SLOTS) { ps = 0; pph ^= 1; }
       }
     }
   }
@@ -376,7 +433,8 @@ __global__ void k_transpose_weight(const T* __restrict__ w, T* __restrict__ wt, 
 }
 
 size_t smem_bytes_gi() {
-  return 1024 + (size_t)GI_STAGES * (GI_A_BYTES + GI_B_BYTES) + (3 * GI_STAGES + 4) * sizeof(uint64_t) + 16;
+  return 1024 + (size_t)GI_STAGES * (GI_A_BYTES + GI_B_BYTES) + (size_t)GI_PLAN_SLOTS * GI_BM * sizeof(GiPlanRow) +
+         (3 * GI_STAGES + 2 * GI_PLAN_SLOTS + 4) * sizeof(uint64_t) + 16;
 }
 
 int pick_bn_gi(const DevGeom& g) {
