@@ -105,18 +105,51 @@ __global__ void __launch_bounds__(256) k_bin_entries(const DevGeom g, const T* _
 }
 
 // Sort each bin by output position so the summation order (and the result) is run-to-run identical.
+// Bins of up to 8 entries (almost all) are sorted in registers with a fixed compare-exchange network
+// on 64-bit keys (row in the high word; rows are unique inside a bin); longer ones by insertion.
+__device__ __forceinline__ void cswap(unsigned long long& a, unsigned long long& b) {
+  const unsigned long long lo = a < b ? a : b, hi = a < b ? b : a;
+  a = lo; b = hi;
+}
 __global__ void __launch_bounds__(256) k_bin_sort(const int* __restrict__ start, BinEntry* __restrict__ entries,
                                                   size_t nbins) {
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(entries);  // {row (low word), w} -> swap on use
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nbins; i += (size_t)gridDim.x * blockDim.x) {
     const int s = start[i], e = start[i + 1];
-    for (int a = s + 1; a < e; ++a) {
-      const BinEntry v = entries[a];
-      int k = a - 1;
-      while (k >= s && entries[k].row > v.row) {
-        entries[k + 1] = entries[k];
-        --k;
+    const int n = e - s;
+    if (n < 2) continue;
+    if (n <= 8) {
+      unsigned long long k[8];
+#pragma unroll
+      for (int a = 0; a < 8; ++a) {
+        if (a < n) {
+          const unsigned long long v = keys[s + a];
+          k[a] = (v << 32) | (v >> 32);  // row into the high word
+        } else {
+          k[a] = ~0ull;
+        }
       }
-      entries[k + 1] = v;
+      // 19-comparator sorting network for 8 keys
+      cswap(k[0], k[1]); cswap(k[2], k[3]); cswap(k[4], k[5]); cswap(k[6], k[7]);
+      cswap(k[0], k[2]); cswap(k[1], k[3]); cswap(k[4], k[6]); cswap(k[5], k[7]);
+      cswap(k[1], k[2]); cswap(k[5], k[6]); cswap(k[0], k[4]); cswap(k[3], k[7]);
+      cswap(k[1], k[5]); cswap(k[2], k[6]);
+      cswap(k[1], k[4]); cswap(k[3], k[6]);
+      cswap(k[2], k[4]); cswap(k[3], k[5]);
+      cswap(k[3], k[4]);
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+        if (a < n) keys[s + a] = (k[a] << 32) | (k[a] >> 32);
+    } else {
+      for (int a = s + 1; a < e; ++a) {
+        const BinEntry v = entries[a];
+        int q = a - 1;
+        while (q >= s && entries[q].row > v.row) {
+          entries[q + 1] = entries[q];
+          --q;
+        }
+        entries[q + 1] = v;
+      }
     }
   }
 }

@@ -12,16 +12,17 @@
 // so neither gcol nor the columns exist in HBM, there are no atomics, and every output element is
 // written exactly once in a fixed summation order (deterministic).
 //
-//   warp 0      TMA producer: grad_output tile (MN-major A operand, straight from NCHW) and
-//               weight slices (MN-major B operand) -> 3-slot smem ring
-//   warp 1      MMA issuer, M=128 positions x N=64*nb channels of one tap, K = output channels
-//   warp 2      TMEM allocator (2 accumulator stages x 256 columns)
-//   warps 4-7   "movers": compute the per-(position, tap) sampling entry (corner indices, fractions,
-//               mask) for the next phase; tcgen05.ld the accumulator and re-lay it out in shared
-//               memory as [position][64 channels] fp32 (swizzled) for the dot warps
-//   warps 8-15  dot warps: 8 lanes per position, 16-byte channels-last loads of the corner values,
-//               fp32 dot products against gcol, warp-shuffle reduction over the 8 lanes, final
-//               combine and store of grad_offset / grad_mask
+//   warp 0       TMA producer: grad_output tile (MN-major A operand, straight from NCHW) and weight
+//                slices (MN-major B operand), 32 output channels per K-block -> 4-slot smem ring
+//   warp 1       MMA issuer, M=128 positions x N=64*nb channels of one tap, K = output channels
+//   warp 2       TMEM allocator (2 accumulator stages x 256 columns)
+//   warps 4-7    "movers": compute the per-(position, tap) sampling entry (corner indices, fractions,
+//                mask) for the next phase; tcgen05.ld the accumulator, round it to the storage dtype and
+//                re-lay it out in shared memory as [position][64 channels] (128B-swizzled rows)
+//   warps 8-23   dot warps: 8 lanes per position, 16-byte channels-last loads of the corner values
+//                (all in flight together), dot products against gcol (HFMA2 quads folded into fp32 for
+//                fp16, fp32 FMAs for bf16), warp-shuffle reduction over the 8 lanes, final combine and
+//                store of grad_offset / grad_mask
 #include "tc_common.cuh"
 
 namespace mdconv {
@@ -29,11 +30,15 @@ namespace tc {
 
 namespace {
 
-constexpr int GS_THREADS = 512;
-constexpr int GS_STAGES = 3;
-constexpr int GS_A_BYTES = 2 * 8192;      // two [64 co x 64 pos] blocks
-constexpr int GS_B_BYTES = 4 * 8192;      // up to four [64 co x 64 kk] blocks
-constexpr int GS_T_BYTES = 128 * 64 * 4;  // one [128 pos x 64 ch] fp32 block
+constexpr int GS_DOT_WARP0 = 8;
+constexpr int GS_DOT_WARPS = 16;
+constexpr int GS_DOT_THREADS = GS_DOT_WARPS * 32;
+constexpr int GS_THREADS = (GS_DOT_WARP0 + GS_DOT_WARPS) * 32;  // 768
+constexpr int GS_STAGES = 4;
+constexpr int GS_KCO = 32;                // output channels per K-block
+constexpr int GS_A_BYTES = 2 * GS_KCO * 128;  // two [32 co x 64 pos] blocks
+constexpr int GS_B_BYTES = 4 * GS_KCO * 128;  // up to four [32 co x 64 kk] blocks
+constexpr int GS_T_BYTES = 128 * 128;     // one [128 pos x 64 ch] block in the storage dtype
 
 template <int ND>
 struct __align__(16) SampleEntry {
@@ -52,39 +57,41 @@ struct TcGsParams {
   void* gmask;
   int nb;            // 64-channel blocks per accumulator stage (1, 2 or 4)
   int nsub;          // stages per (deformable group, tap) = Cdg / 64 / nb
-  int kblocks;       // K blocks per stage = Cog / 64
+  int kblocks;       // K blocks per stage = Cog / 32
   int pbi;           // 64-position blocks per sample
   int total_pb;      // B * pbi
   int m_tiles;       // ceil(total_pb / 2)
 };
 
-template <typename T>
-__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]);
-template <>
-__device__ __forceinline__ void unpack8<__half>(const uint4& v, float (&f)[8]) {
-  const __half2* h = reinterpret_cast<const __half2*>(&v);
+// dot product of two 8-element vectors stored in the tensor dtype
+__device__ __forceinline__ float dot8(const uint4& a, const uint4& b, __half) {
+  const __half2* x = reinterpret_cast<const __half2*>(&a);
+  const __half2* y = reinterpret_cast<const __half2*>(&b);
+  __half2 p = __hmul2(x[0], y[0]);
+  p = __hfma2(x[1], y[1], p);
+  p = __hfma2(x[2], y[2], p);
+  p = __hfma2(x[3], y[3], p);
+  const float2 f = __half22float2(p);
+  return f.x + f.y;
+}
+__device__ __forceinline__ float dot8(const uint4& a, const uint4& b, __nv_bfloat16) {
+  const uint32_t* x = reinterpret_cast<const uint32_t*>(&a);
+  const uint32_t* y = reinterpret_cast<const uint32_t*>(&b);
+  float acc = 0.f;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float2 t = __half22float2(h[i]);
-    f[2 * i] = t.x; f[2 * i + 1] = t.y;
+    acc = fmaf(__uint_as_float(x[i] << 16), __uint_as_float(y[i] << 16), acc);
+    acc = fmaf(__uint_as_float(x[i] & 0xFFFF0000u), __uint_as_float(y[i] & 0xFFFF0000u), acc);
   }
+  return acc;
 }
-template <>
-__device__ __forceinline__ void unpack8<__nv_bfloat16>(const uint4& v, float (&f)[8]) {
-  const uint32_t* u = reinterpret_cast<const uint32_t*>(&v);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    f[2 * i] = __uint_as_float(u[i] << 16);
-    f[2 * i + 1] = __uint_as_float(u[i] & 0xFFFF0000u);
-  }
+__device__ __forceinline__ uint32_t pack2(float a, float b, __half) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
 }
-
-// position of 16-byte quad q (4 channels) of row `row` inside a [128][64] fp32 block: lane j of a
-// dot group reads quads 2j and 2j+1 (channels 8j..8j+7); they are stored at chunk slots j and 8+j
-// so both the row-parallel writers and the chunk-parallel readers are bank-conflict free.
-__device__ __forceinline__ uint32_t t_off(int row, int q) {
-  const int slot = (q >> 1) | ((q & 1) << 3);
-  return (uint32_t)(row * 256 + ((slot ^ (row & 7)) << 4));
+__device__ __forceinline__ uint32_t pack2(float a, float b, __nv_bfloat16) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
 }
 
 template <typename T, int ND, bool MOD>
@@ -124,9 +131,9 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
       ptx::mbar_init(&tmem_full[s], 1);
       ptx::mbar_init(&tmem_empty[s], 128);
       ptx::mbar_init(&t_full[s], 128);
-      ptx::mbar_init(&t_empty[s], 256);
+      ptx::mbar_init(&t_empty[s], GS_DOT_THREADS);
       ptx::mbar_init(&plan_full[s], 128);
-      ptx::mbar_init(&plan_empty[s], 256);
+      ptx::mbar_init(&plan_empty[s], GS_DOT_THREADS);
     }
     ptx::fence_barrier_init();
   }
@@ -161,14 +168,15 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
             const int grp = blk0 / bpg;
             const int ccl0 = blk0 - grp * bpg;      // block index inside the conv group
             for (int kb = 0; kb < prm.kblocks; ++kb) {
-              const int co0 = grp * g.Cog + kb * 64;
+              const int co0 = grp * g.Cog + kb * GS_KCO;
               ptx::mbar_wait(&empty[s], ph ^ 1);
-              ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)(GS_A_BYTES + nb * 8192));
+              ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)(GS_A_BYTES + nb * GS_KCO * 128));
 #pragma unroll
               for (int h = 0; h < 2; ++h)
-                ptx::tma_load_3d(sA + s * GS_A_BYTES + h * 8192, &tmap_go, &full[s], pb_p0[h], co0, pb_b[h]);
+                ptx::tma_load_3d(sA + s * GS_A_BYTES + h * (GS_KCO * 128), &tmap_go, &full[s], pb_p0[h], co0, pb_b[h]);
               for (int j = 0; j < nb; ++j)
-                ptx::tma_load_2d(sB + s * GS_B_BYTES + j * 8192, &tmap_w, &full[s], ((ccl0 + j) * g.K + tap) * 64, co0);
+                ptx::tma_load_2d(sB + s * GS_B_BYTES + j * (GS_KCO * 128), &tmap_w, &full[s],
+                                 ((ccl0 + j) * g.K + tap) * 64, co0);
               if (++s == GS_STAGES) { s = 0; ph ^= 1; }
             }
           }
@@ -194,9 +202,9 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
             const uint32_t a_addr = ptx::smem_u32(sA + s * GS_A_BYTES);
             const uint32_t b_addr = ptx::smem_u32(sB + s * GS_B_BYTES);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {  // 16 output channels per MMA
-              const uint64_t ad = ptx::umma_smem_desc_sw128(a_addr + k * 2048, 8192, 1024);
-              const uint64_t bd = ptx::umma_smem_desc_sw128(b_addr + k * 2048, 8192, 1024);
+            for (int k = 0; k < GS_KCO / 16; ++k) {  // 16 output channels per MMA
+              const uint64_t ad = ptx::umma_smem_desc_sw128(a_addr + k * 2048, GS_KCO * 128, 1024);
+              const uint64_t bd = ptx::umma_smem_desc_sw128(b_addr + k * 2048, GS_KCO * 128, 1024);
               ptx::umma_f16(d_tmem, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
             }
             ptx::umma_commit(&empty[s]);
@@ -283,8 +291,14 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
               ptx::tmem_ld_32x32(taddr + j * 64 + hlf * 32, v);
               ptx::tmem_ld_wait();
 #pragma unroll
-              for (int q = 0; q < 8; ++q)
-                sts128(tb + t_off(row, hlf * 8 + q), make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+              for (int q = 0; q < 4; ++q) {  // 8 channels = one 16-byte chunk
+                uint4 o;
+                o.x = pack2(__uint_as_float(v[8 * q]), __uint_as_float(v[8 * q + 1]), T());
+                o.y = pack2(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3]), T());
+                o.z = pack2(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5]), T());
+                o.w = pack2(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7]), T());
+                sts128(tb + sw128(row, hlf * 4 + q), o);
+              }
             }
             ptx::mbar_arrive(&t_full[ts]);
             if (++ts == 2) { ts = 0; tph ^= 1; }
@@ -295,12 +309,12 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
         }
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= GS_DOT_WARP0) {
     // ===================== dot warps =====================
-    const int dt = threadIdx.x - 256;
-    const int dw = dt >> 5;
+    const int dw = warp - GS_DOT_WARP0;
     const int rq = lane >> 3;  // row inside a pass
     const int j = lane & 7;    // 8-channel chunk
+    const int row0 = dw * 8 + rq;  // pass 0 row (pass 1: +4)
     const uint4* __restrict__ xq = reinterpret_cast<const uint4*>(prm.xt);
     T* __restrict__ goff = reinterpret_cast<T*>(prm.goff);
     T* __restrict__ gmask = reinterpret_cast<T*>(prm.gmask);
@@ -311,44 +325,41 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
         const int dgi = phs / g.K, tap = phs - dgi * g.K;
         ptx::mbar_wait(&plan_full[ps], pph);
         const uint32_t plan_addr = ptx::smem_u32(sPlan + ps * 128);
-        float S[4][NC];
+        // corner indices of this thread's two rows (fixed for the whole phase)
+        int idx[2][NC];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 2; ++i) {
+          const uint32_t ea = plan_addr + (row0 + 4 * i) * (uint32_t)sizeof(SampleEntry<ND>);
+#pragma unroll
+          for (int c4 = 0; c4 < NC / 4; ++c4) {
+            const uint4 iv = lds128(ea + 16 * c4);
+            idx[i][4 * c4] = (int)iv.x; idx[i][4 * c4 + 1] = (int)iv.y;
+            idx[i][4 * c4 + 2] = (int)iv.z; idx[i][4 * c4 + 3] = (int)iv.w;
+          }
+        }
+        float S[2][NC];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
 #pragma unroll
           for (int c = 0; c < NC; ++c) S[i][c] = 0.f;
         for (int sub = 0; sub < nsub; ++sub) {
           for (int jb = 0; jb < nb; ++jb) {
             const int c0 = (dgi * bpd + sub * nb + jb) * 64;  // first channel of this block
             const uint4* xc = xq + (c0 >> 3) + j;
+            // the corner values do not depend on the accumulator: issue the loads before waiting for it
+            uint4 xv[2][NC];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+              for (int c = 0; c < NC; ++c)
+                xv[i][c] = idx[i][c] >= 0 ? __ldg(xc + idx[i][c]) : make_uint4(0u, 0u, 0u, 0u);
             ptx::mbar_wait(&t_full[ts], tph);
             const uint32_t tb = ptx::smem_u32(sT + ts * GS_T_BYTES);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int row = dw * 16 + i * 4 + rq;
-              const uint32_t ea = plan_addr + row * (uint32_t)sizeof(SampleEntry<ND>);
-              int idx[NC];
+            for (int i = 0; i < 2; ++i) {
+              const uint4 gc = lds128(tb + sw128(row0 + 4 * i, j));
 #pragma unroll
-              for (int c4 = 0; c4 < NC / 4; ++c4) {
-                const uint4 iv = lds128(ea + 16 * c4);
-                idx[4 * c4] = (int)iv.x; idx[4 * c4 + 1] = (int)iv.y; idx[4 * c4 + 2] = (int)iv.z; idx[4 * c4 + 3] = (int)iv.w;
-              }
-              const uint4 g0 = lds128(tb + t_off(row, 2 * j));
-              const uint4 g1 = lds128(tb + t_off(row, 2 * j + 1));
-              const float gc[8] = {__uint_as_float(g0.x), __uint_as_float(g0.y), __uint_as_float(g0.z),
-                                   __uint_as_float(g0.w), __uint_as_float(g1.x), __uint_as_float(g1.y),
-                                   __uint_as_float(g1.z), __uint_as_float(g1.w)};
-              uint4 xv[NC];
-#pragma unroll
-              for (int c = 0; c < NC; ++c) xv[c] = idx[c] >= 0 ? __ldg(xc + idx[c]) : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-              for (int c = 0; c < NC; ++c) {
-                float xf[8];
-                unpack8<T>(xv[c], xf);
-                float acc = S[i][c];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) acc = fmaf(gc[k], xf[k], acc);
-                S[i][c] = acc;
-              }
+              for (int c = 0; c < NC; ++c) S[i][c] += dot8(gc, xv[i][c], T());
             }
             ptx::mbar_arrive(&t_empty[ts]);
             if (++ts == 2) { ts = 0; tph ^= 1; }
@@ -356,7 +367,7 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
         }
         // ---- reduce over the 8 lanes of each row, combine, store ----
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 2; ++i)
 #pragma unroll
           for (int c = 0; c < NC; ++c) {
             float v = S[i][c];
@@ -365,18 +376,12 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
             v += __shfl_xor_sync(0xffffffffu, v, 4);
             S[i][c] = v;
           }
-        if (j < 4) {
+        if (j < 2) {
           // lane j of a row group finishes pass j (all 8 lanes hold the same totals)
           float Sc[NC];
 #pragma unroll
-          for (int c = 0; c < NC; ++c) {
-            float v = S[0][c];
-            v = j == 1 ? S[1][c] : v;
-            v = j == 2 ? S[2][c] : v;
-            v = j == 3 ? S[3][c] : v;
-            Sc[c] = v;
-          }
-          const int row = dw * 16 + j * 4 + rq;
+          for (int c = 0; c < NC; ++c) Sc[c] = j == 1 ? S[1][c] : S[0][c];
+          const int row = row0 + 4 * j;
           const uint32_t ea = plan_addr + row * (uint32_t)sizeof(SampleEntry<ND>) + 16 * (NC / 4);
           const uint4 tail = lds128(ea);  // fr[ND], m, flags (2D)  /  fr[3], m (3D)
           float fr[3];
@@ -460,7 +465,7 @@ void launch_grad_sample(const CUtensorMap& tmap_go, const CUtensorMap& tmap_w, c
 }  // namespace
 
 bool grad_sample_supported(const DevGeom& g) {
-  return g.Cog % 64 == 0 && g.P % 8 == 0 && g.Cg % 64 == 0 && g.Cdg % 64 == 0;
+  return g.Cog % GS_KCO == 0 && g.P % 8 == 0 && g.Cg % 64 == 0 && g.Cdg % 64 == 0;
 }
 
 // xt: channels-last input; wr: weight re-ordered to [Co][(channel-block, tap, 64 channels)].
@@ -475,7 +480,7 @@ void tensor_grad_sample(const DevGeom& g, const T* xt, const T* wr, const void* 
   while (nb > 1 && (bpd % nb != 0 || bpg % nb != 0)) nb >>= 1;
   prm.nb = nb;
   prm.nsub = bpd / nb;
-  prm.kblocks = g.Cog / 64;
+  prm.kblocks = g.Cog / GS_KCO;
   prm.pbi = (g.P + 63) / 64;
   prm.total_pb = g.B * prm.pbi;
   prm.m_tiles = (prm.total_pb + 1) / 2;
@@ -489,7 +494,7 @@ void tensor_grad_sample(const DevGeom& g, const T* xt, const T* wr, const void* 
   {
     const cuuint64_t dims[3] = {(cuuint64_t)g.P, (cuuint64_t)g.Co, (cuuint64_t)g.B};
     const cuuint64_t strides[2] = {(cuuint64_t)g.P * sizeof(T), (cuuint64_t)g.Co * g.P * sizeof(T)};
-    const cuuint32_t box[3] = {64, 64, 1};
+    const cuuint32_t box[3] = {64, GS_KCO, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = enc(&tmap_go, tmap_dtype<T>(), 3, const_cast<void*>(go), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -502,7 +507,7 @@ void tensor_grad_sample(const DevGeom& g, const T* xt, const T* wr, const void* 
   {
     const cuuint64_t dims[2] = {(cuuint64_t)g.Kg, (cuuint64_t)g.Co};
     const cuuint64_t strides[1] = {(cuuint64_t)g.Kg * sizeof(T)};
-    const cuuint32_t box[2] = {64, 64};
+    const cuuint32_t box[2] = {64, GS_KCO};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = enc(&tmap_w, tmap_dtype<T>(), 2, const_cast<T*>(wr), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
