@@ -63,6 +63,10 @@ int resolve(const mdconv_geom_t* in, DevGeom& g) {
   g.modulated = in->modulated ? 1 : 0;
   g.rule = in->grad_rule ? 1 : 0;
   g.with_bias = in->with_bias ? 1 : 0;
+  for (int a = 0; a < 3; ++a) {
+    g.fd_out[a] = make_fastdiv(g.out[a]);
+    g.fd_k[a] = make_fastdiv(g.k[a]);
+  }
   return MDCONV_OK;
 }
 

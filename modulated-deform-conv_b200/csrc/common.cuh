@@ -15,6 +15,29 @@ namespace mdconv {
 
 constexpr float kEps = 1.1920929e-7f;  // FLT_EPSILON, reference src/config.h:18
 
+// n / d for 0 <= n < 2^31 without the ~30-instruction integer-division sequence (the sampling-plan
+// producers decode a position and a tap per plan).  q = umulhi(n, mul) >> shr, mul = ceil(2^(32+shr) / d).
+struct FastDiv {
+  uint32_t mul, shr;
+  int d;
+};
+inline FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  f.d = d;
+  f.mul = 0; f.shr = 0;
+  if (d > 1) {
+    int lg = 0;
+    while ((1ll << lg) < d) ++lg;  // ceil(log2 d)
+    const unsigned long long m = ((1ull << (31 + lg)) + (unsigned long long)d - 1) / (unsigned long long)d;
+    f.mul = (uint32_t)m;
+    f.shr = (uint32_t)(lg - 1);
+  }
+  return f;
+}
+__device__ __forceinline__ int fdiv(int n, const FastDiv& f) {
+  return f.d == 1 ? n : (int)(__umulhi((uint32_t)n, f.mul) >> f.shr);
+}
+
 // Fully resolved geometry, passed to kernels by value.
 struct DevGeom {
   int nd, B, C, Co;
@@ -26,6 +49,7 @@ struct DevGeom {
   int Cg, Cog, Cdg;
   int Kg;   // Cg * K, reduction length of the per-group contraction
   int modulated, rule, with_bias;
+  FastDiv fd_out[3], fd_k[3];  // divisors out[a], k[a]
 };
 
 // ---- storage <-> compute conversions --------------------------------------------------------

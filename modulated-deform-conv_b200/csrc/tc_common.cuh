@@ -55,9 +55,10 @@ __device__ __forceinline__ void decode_row(const DevGeom& g, int b, int p, bool 
   rc.valid = valid;
   int o[3];
   if (ND == 2) {
-    o[1] = rc.p % g.out[1]; o[0] = rc.p / g.out[1];
+    o[0] = fdiv(rc.p, g.fd_out[1]); o[1] = rc.p - o[0] * g.out[1];
   } else {
-    o[2] = rc.p % g.out[2]; const int r2 = rc.p / g.out[2]; o[1] = r2 % g.out[1]; o[0] = r2 / g.out[1];
+    const int r2 = fdiv(rc.p, g.fd_out[2]); o[2] = rc.p - r2 * g.out[2];
+    o[0] = fdiv(r2, g.fd_out[1]); o[1] = r2 - o[0] * g.out[1];
   }
 #pragma unroll
   for (int a = 0; a < ND; ++a) rc.base[a] = o[a] * g.s[a] - g.p[a];
@@ -105,9 +106,10 @@ __device__ __forceinline__ void build_pos(const DevGeom& g, const RowCoord<ND>& 
                                           SamplePos<ND>& sp) {
   int tt[3];
   if (ND == 2) {
-    tt[1] = tap % g.k[1]; tt[0] = tap / g.k[1];
+    tt[0] = fdiv(tap, g.fd_k[1]); tt[1] = tap - tt[0] * g.k[1];
   } else {
-    tt[2] = tap % g.k[2]; const int q = tap / g.k[2]; tt[1] = q % g.k[1]; tt[0] = q / g.k[1];
+    const int q = fdiv(tap, g.fd_k[2]); tt[2] = tap - q * g.k[2];
+    tt[0] = fdiv(q, g.fd_k[1]); tt[1] = q - tt[0] * g.k[1];
   }
   sp.in_range = true;
 #pragma unroll

@@ -174,14 +174,17 @@ k_tc_grad_weight(const __grid_constant__ CUtensorMap tmap_go, const TcGwParams p
     const int pcc = kkb / g.K, ptap = kkb - pcc * g.K;
     const int pdg = (grp * g.Cg + pcc * BK) / g.Cdg;
     const bool active = pblk < nb;
-    auto coord = [&](int pb, RowCoord<ND>& rc) {
-      const int b = pb / prm.pbi, p0 = (pb - b * prm.pbi) * 64;
-      decode_row<ND>(g, b, p0 + prow, active && (p0 + prow < g.P), rc);
+    // (sample, first position) of the block being fetched, advanced incrementally (no division per block)
+    int nb_b = pb0 / prm.pbi, nb_p0 = (pb0 - nb_b * prm.pbi) * 64;
+    auto coord = [&](RowCoord<ND>& rc) {
+      decode_row<ND>(g, nb_b, nb_p0 + prow, active && (nb_p0 + prow < g.P), rc);
+      nb_p0 += 64;
+      if (nb_p0 >= prm.pbi * 64) { nb_p0 = 0; ++nb_b; }
     };
     RowCoord<ND> rc_next;
     RawSample<ND> raw_next;
     if (pb0 < pb1) {
-      coord(pb0, rc_next);
+      coord(rc_next);
       if (rc_next.valid) raw_next = fetch_sample<T, ND, MOD>(g, off, mask, rc_next, pdg, ptap);
     }
     int ps = 0;
@@ -190,7 +193,7 @@ k_tc_grad_weight(const __grid_constant__ CUtensorMap tmap_go, const TcGwParams p
       const RowCoord<ND> rc = rc_next;
       const RawSample<ND> raw = raw_next;
       if (pb + 1 < pb1) {
-        coord(pb + 1, rc_next);
+        coord(rc_next);
         if (rc_next.valid) raw_next = fetch_sample<T, ND, MOD>(g, off, mask, rc_next, pdg, ptap);
       }
       SamplePos<ND> sp;
