@@ -42,6 +42,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// For roles that are far off the critical path (epilogue, plan producers, TMA issue): back off between
+// polls so their try_wait traffic does not crowd the barrier unit the gather / MMA warps depend on.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t ns = 256) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
 
 // generic-proxy writes to smem -> visible to the async proxy (UMMA / TMA reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
@@ -146,6 +151,16 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr, uin
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int ab_format, int a_mn_major, int b_mn_major, int M, int N) {
   return (1u << 4) | ((uint32_t)ab_format << 7) | ((uint32_t)ab_format << 10) | ((uint32_t)a_mn_major << 15) |
          ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// Register re-balancing between warp roles (whole warpgroup = 4 consecutive warps must execute it).
+template <uint32_t kRegs>
+__device__ __forceinline__ void reg_dealloc() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs));
+}
+template <uint32_t kRegs>
+__device__ __forceinline__ void reg_alloc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs));
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {

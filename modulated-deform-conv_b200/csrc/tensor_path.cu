@@ -78,6 +78,44 @@ __device__ __forceinline__ void for_each_kblock(const TcFwdParams& prm, int grp,
   }
 }
 
+// The same sequence as for_each_kblock, but as an explicit iterator over (tile, run, tap, channel
+// block) so the gather warps can look one K-block ahead (loads of K-block k+1 are issued before
+// K-block k is interpolated).
+struct KbIter {
+  int t, grp, run0, run_end, tap, cc;
+  bool valid;
+  __device__ __forceinline__ void set_run(const TcFwdParams& prm, int c0) {
+    run0 = c0;
+    const int room = prm.bpd - (grp * prm.ccs + c0) % prm.bpd;
+    run_end = c0 + room < prm.ccs ? c0 + room : prm.ccs;
+  }
+  __device__ __forceinline__ void set_tile(const TcFwdParams& prm, int tile) {
+    t = tile;
+    valid = tile < prm.total_tiles;
+    grp = valid ? (tile / prm.m_tiles) / prm.n_tiles : 0;
+    tap = 0;
+    set_run(prm, 0);
+    cc = 0;
+  }
+  __device__ __forceinline__ void advance(const TcFwdParams& prm, int tile_stride) {
+    if (++cc < run_end) return;
+    if (++tap < prm.g.K) { cc = run0; return; }
+    tap = 0;
+    if (run_end < prm.ccs) { set_run(prm, run_end); cc = run0; return; }
+    set_tile(prm, t + tile_stride);
+  }
+  __device__ __forceinline__ bool first() const { return cc == run0; }
+  __device__ __forceinline__ bool last() const { return cc == run_end - 1; }
+};
+
+// Register budget after setmaxnreg: the CTA owns TC_THREADS x 72 registers (what it is launched with);
+// the control / epilogue / plan warpgroups give some back, the gather warpgroups take them.
+constexpr uint32_t TC_REGS_LAUNCH = 72;
+constexpr uint32_t TC_REGS_CTL = 32, TC_REGS_EPI = 48, TC_REGS_PLAN = 48, TC_REGS_GATHER = 88;
+static_assert(128 * (TC_REGS_CTL + TC_REGS_EPI + TC_REGS_PLAN) + TC_GATHER_THREADS * TC_REGS_GATHER <=
+                  TC_THREADS * TC_REGS_LAUNCH,
+              "setmaxnreg.inc would wait forever: the CTA does not own that many registers");
+
 template <typename T, int ND, bool MOD>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const TcFwdParams prm) {
@@ -128,6 +166,8 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const TcFwdParams prm) 
   const int BN = prm.BN;
   const long long total_pix = (long long)g.B * g.P;
 
+  if (warp < 4) {
+    ptx::reg_dealloc<TC_REGS_CTL>();
   if (warp == 0) {
     // ===================== TMA producer: weight K-slices =====================
     if (lane == 0) {
@@ -138,7 +178,7 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const TcFwdParams prm) 
         const int nt = rest % prm.n_tiles, grp = rest / prm.n_tiles;
         const int row0 = grp * g.Cog + nt * BN;
         for_each_kblock(prm, grp, [&](int cc, int tap, bool, int) {
-          ptx::mbar_wait(&empty[s], ph ^ 1);
+          ptx::mbar_wait_relaxed(&empty[s], ph ^ 1, 64);
           ptx::mbar_arrive_expect_tx(&full_b[s], (uint32_t)BN * 128u);
           ptx::tma_load_2d(sB + s * TC_B_BYTES, &tmap_w, &full_b[s], (cc * g.K + tap) * TC_BK, row0);
           if (++s == TC_STAGES) { s = 0; ph ^= 1; }
@@ -177,8 +217,10 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const TcFwdParams prm) 
         if (++as == 2) { as = 0; aph ^= 1; }
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  }
+  } else if (warp < 8) {
     // ===================== epilogue =====================
+    ptx::reg_dealloc<TC_REGS_EPI>();
     const int ew = warp & 3;
     T* __restrict__ y = reinterpret_cast<T*>(prm.y);
     const T* __restrict__ bias = reinterpret_cast<const T*>(prm.bias);
@@ -194,16 +236,16 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const TcFwdParams prm) 
       const int p = valid ? (int)(gp % g.P) : 0;
       const int co0 = grp * g.Cog + nt * BN;
       T* yrow = y + ((size_t)b * g.Co + co0) * g.P + p;
-      ptx::mbar_wait(&tmem_full[as], aph);
+      ptx::mbar_wait_relaxed(&tmem_full[as], aph);
       ptx::tc_fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * TC_MAX_BN);
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(taddr + c0, v);
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        uint32_t v[16];
+        ptx::tmem_ld_32x16(taddr + c0, v);
         ptx::tmem_ld_wait();
         if (valid) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
+          for (int j = 0; j < 16; ++j) {
             float f = __uint_as_float(v[j]);
             if (g.with_bias) f += ld_as<float>(bias + co0 + c0 + j);
             yrow[(size_t)(c0 + j) * g.P] = cvt_to<T, float>(f);
@@ -214,8 +256,9 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const TcFwdParams prm) 
       ptx::mbar_arrive(&tmem_empty[as]);
       if (++as == 2) { as = 0; aph ^= 1; }
     }
-  } else if (warp >= TC_PLAN_WARP0 && warp < TC_GATHER_WARP0) {
+  } else if (warp < TC_GATHER_WARP0) {
     // ===================== plan producers =====================
+    ptx::reg_dealloc<TC_REGS_PLAN>();
     // One thread per tile row: the sampling plan of (row, tap) for the current deformable-group run
     // (corner indices + weight*mask, reference src/mdeformable_conv.cu:59-83 computes this per
     // channel), written into a ring of plan slots that runs ahead of the gather warps.
@@ -235,52 +278,98 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const TcFwdParams prm) 
       for_each_kblock(prm, grp, [&](int cc, int tap, bool first, int) {
         if (!first) return;
         const PlanEntry<ND> e = tc::make_plan_entry<T, ND, MOD>(g, off, mask, rc, grp * g.Cg + cc * TC_BK, tap, C8);
-        ptx::mbar_wait(&plan_empty[ps], pph ^ 1);
+        ptx::mbar_wait_relaxed(&plan_empty[ps], pph ^ 1);
         tc::store_plan<ND>(ptx::smem_u32(sPlan + ps * TC_BM + row), e);
         ptx::mbar_arrive(&plan_full[ps]);
         if (++ps == TC_PLAN_SLOTS) { ps = 0; pph ^= 1; }
       });
     }
-  } else if (warp >= TC_GATHER_WARP0) {
+  } else {
     // ===================== gather producers =====================
+    ptx::reg_alloc<TC_REGS_GATHER>();
     // 16 warps x 2 passes x 4 rows = 128 rows per K-block; 8 lanes x 16 bytes cover the 64 channels
-    // of one corner.  All 8 corner loads of a thread are issued before the first is consumed.
+    // of one corner.  Software-pipelined one K-block deep: the corner loads of K-block k+1 are in
+    // flight while K-block k is interpolated and stored (two register buffers, ping-pong).
+    constexpr int NC = 1 << ND;
     const int gw = warp - TC_GATHER_WARP0;
     const int chunk = lane & 7;
     const int row0 = gw * 8 + (lane >> 3);
     const uint4* __restrict__ xq = reinterpret_cast<const uint4*>(prm.xt);
-    int s = 0, ps = 0;
-    uint32_t ph = 0, pph = 0;
-    for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x) {
-      const int grp = (t / prm.m_tiles) / prm.n_tiles;
-      uint32_t plan_addr = 0;
-      int left = 0;
-      for_each_kblock(prm, grp, [&](int cc, int, bool first, int nblk) {
-        if (first) {
-          ptx::mbar_wait(&plan_full[ps], pph);
-          plan_addr = ptx::smem_u32(sPlan + ps * TC_BM + row0);
-          left = nblk;
-        }
-        const uint4* xc = xq + ((grp * g.Cg + cc * TC_BK) >> 3) + chunk;
-        ptx::mbar_wait(&empty[s], ph ^ 1);          // MMA has finished reading A[s]
-        const uint32_t a_addr = ptx::smem_u32(sA + s * TC_A_BYTES);
-        PlanEntry<ND> e0 = tc::load_plan<ND>(plan_addr);
-        PlanEntry<ND> e1 = tc::load_plan<ND>(plan_addr + 4 * (uint32_t)sizeof(PlanEntry<ND>));
-        uint4 v0[1 << ND], v1[1 << ND];
+    const uint32_t plan_row = ptx::smem_u32(sPlan + row0);
+    constexpr uint32_t kSlotBytes = TC_BM * (uint32_t)sizeof(PlanEntry<ND>);
+    constexpr uint32_t kRow4 = 4 * (uint32_t)sizeof(PlanEntry<ND>);
+    int s = 0;                 // operand ring position (consume side)
+    uint32_t ph = 0;
+    int ips = 0, cps = 0;      // plan ring positions: issue side / consume side
+    uint32_t ipph = 0;
+
+    // issue the corner loads of K-block `it` into (v0, v1)
+    auto issue = [&](const KbIter& it, uint4 (&v0)[NC], uint4 (&v1)[NC]) {
+      if (it.first()) ptx::mbar_wait(&plan_full[ips], ipph);
+      const uint32_t pa = plan_row + ips * kSlotBytes;
+      const uint4* xc = xq + ((it.grp * g.Cg + it.cc * TC_BK) >> 3) + chunk;
+      int i0[NC], i1[NC];
 #pragma unroll
-        for (int c = 0; c < (1 << ND); ++c) v0[c] = __ldg(xc + e0.idx[c]);
+      for (int q = 0; q < NC / 4; ++q) {
+        const uint4 a = tc::lds128(pa + 16 * q), b = tc::lds128(pa + kRow4 + 16 * q);
+        i0[4 * q] = (int)a.x; i0[4 * q + 1] = (int)a.y; i0[4 * q + 2] = (int)a.z; i0[4 * q + 3] = (int)a.w;
+        i1[4 * q] = (int)b.x; i1[4 * q + 1] = (int)b.y; i1[4 * q + 2] = (int)b.z; i1[4 * q + 3] = (int)b.w;
+      }
 #pragma unroll
-        for (int c = 0; c < (1 << ND); ++c) v1[c] = __ldg(xc + e1.idx[c]);
-        tc::sts128(a_addr + tc::sw128(row0, chunk), tc::interp8(v0, e0.w, 1 << ND, T()));
-        tc::sts128(a_addr + tc::sw128(row0 + 4, chunk), tc::interp8(v1, e1.w, 1 << ND, T()));
-        ptx::fence_proxy_async_smem();
-        ptx::mbar_arrive(&full_a[s]);
-        if (++s == TC_STAGES) { s = 0; ph ^= 1; }
-        if (--left == 0) {                            // last K-block that uses this plan slot
-          ptx::mbar_arrive(&plan_empty[ps]);
-          if (++ps == TC_PLAN_SLOTS) { ps = 0; pph ^= 1; }
-        }
-      });
+      for (int c = 0; c < NC; ++c) v0[c] = __ldg(xc + i0[c]);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) v1[c] = __ldg(xc + i1[c]);
+      if (it.last()) {
+        if (++ips == TC_PLAN_SLOTS) { ips = 0; ipph ^= 1; }
+      }
+    };
+    // interpolate K-block `it` from (v0, v1) into the A stage, publish it, release the plan slot
+    auto finish = [&](const KbIter& it, const uint4 (&v0)[NC], const uint4 (&v1)[NC]) {
+      const uint32_t pa = plan_row + cps * kSlotBytes + 4 * NC;  // weights follow the indices
+      uint32_t w0[NC], w1[NC];
+#pragma unroll
+      for (int q = 0; q < NC / 4; ++q) {
+        const uint4 a = tc::lds128(pa + 16 * q), b = tc::lds128(pa + kRow4 + 16 * q);
+        w0[4 * q] = a.x; w0[4 * q + 1] = a.y; w0[4 * q + 2] = a.z; w0[4 * q + 3] = a.w;
+        w1[4 * q] = b.x; w1[4 * q + 1] = b.y; w1[4 * q + 2] = b.z; w1[4 * q + 3] = b.w;
+      }
+      ptx::mbar_wait(&empty[s], ph ^ 1);            // MMA has finished reading A[s]
+      const uint32_t a_addr = ptx::smem_u32(sA + s * TC_A_BYTES);
+      tc::sts128(a_addr + tc::sw128(row0, chunk), tc::interp8(v0, w0, NC, T()));
+      tc::sts128(a_addr + tc::sw128(row0 + 4, chunk), tc::interp8(v1, w1, NC, T()));
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(&full_a[s]);
+      if (++s == TC_STAGES) { s = 0; ph ^= 1; }
+      if (it.last()) {
+        ptx::mbar_arrive(&plan_empty[cps]);
+        if (++cps == TC_PLAN_SLOTS) cps = 0;
+      }
+    };
+
+    KbIter ka, kb2;
+    ka.set_tile(prm, blockIdx.x);
+    if (ND == 2) {
+      uint4 a0[NC], a1[NC], b0[NC], b1[NC];
+      if (ka.valid) issue(ka, a0, a1);
+      while (ka.valid) {
+        kb2 = ka;
+        kb2.advance(prm, gridDim.x);
+        if (kb2.valid) issue(kb2, b0, b1);
+        finish(ka, a0, a1);
+        if (!kb2.valid) break;
+        ka = kb2;
+        ka.advance(prm, gridDim.x);
+        if (ka.valid) issue(ka, a0, a1);
+        finish(kb2, b0, b1);
+      }
+    } else {
+      // 3D: 16 corner loads per thread already fill the register budget; no look-ahead
+      uint4 a0[NC], a1[NC];
+      while (ka.valid) {
+        issue(ka, a0, a1);
+        finish(ka, a0, a1);
+        ka.advance(prm, gridDim.x);
+      }
     }
   }
 
