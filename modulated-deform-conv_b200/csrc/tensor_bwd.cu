@@ -27,6 +27,10 @@ constexpr int GW_PLAN_SLOTS = 4;
 constexpr int GW_NB = 2;                       // 64-wide kk blocks per CTA tile (N = 128)
 constexpr int GW_GO_BYTES = 2 * 128 * 128;     // two M tiles of [128 co x 64 pos]
 constexpr int GW_COL_BYTES = GW_NB * 64 * 128; // NB blocks of [64 pos x 64 kk]
+// registers after setmaxnreg (the CTA owns GW_THREADS x 72)
+constexpr uint32_t GW_REGS_CTL = 32, GW_REGS_EPI = 48, GW_REGS_PLAN = 56, GW_REGS_GATHER = 88;
+static_assert(128 * (GW_REGS_CTL + GW_REGS_EPI + GW_REGS_PLAN) + GW_GATHER_THREADS * GW_REGS_GATHER <= GW_THREADS * 72,
+              "setmaxnreg.inc would wait forever");
 
 struct TcGwParams {
   DevGeom g;
@@ -96,6 +100,8 @@ k_tc_grad_weight(const __grid_constant__ CUtensorMap tmap_go, const TcGwParams p
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
 
+  if (warp < 4) {
+    ptx::reg_dealloc<GW_REGS_CTL>();
   if (warp == 0) {
     // ===================== TMA producer: grad_output tiles =====================
     if (lane == 0) {
@@ -104,7 +110,7 @@ k_tc_grad_weight(const __grid_constant__ CUtensorMap tmap_go, const TcGwParams p
       const int co_base = grp * g.Cog + mp * 256;
       for (int pb = pb0; pb < pb1; ++pb) {
         const int b = pb / prm.pbi, p0 = (pb - b * prm.pbi) * 64;
-        ptx::mbar_wait(&empty[s], ph ^ 1);
+        ptx::mbar_wait_relaxed(&empty[s], ph ^ 1, 64);
         ptx::mbar_arrive_expect_tx(&full_go[s], (uint32_t)MT * 16384u);
         for (int mt = 0; mt < MT; ++mt)
           ptx::tma_load_3d(sGo + s * GW_GO_BYTES + mt * 16384, &tmap_go, &full_go[s], p0, co_base + mt * 128, b);
@@ -136,10 +142,12 @@ k_tc_grad_weight(const __grid_constant__ CUtensorMap tmap_go, const TcGwParams p
       }
       ptx::umma_commit(done);
     }
-  } else if (warp >= 4 && warp < 8) {
+  }
+  } else if (warp < 8) {
     // ===================== epilogue: TMEM -> fp32 partial =====================
+    ptx::reg_dealloc<GW_REGS_EPI>();
     const int ew = warp & 3;
-    ptx::mbar_wait(done, 0);
+    ptx::mbar_wait_relaxed(done, 0, 1024);
     ptx::tc_fence_after_sync();
     const int N = nb * 64;
     for (int mt = 0; mt < MT; ++mt) {
@@ -148,21 +156,22 @@ k_tc_grad_weight(const __grid_constant__ CUtensorMap tmap_go, const TcGwParams p
       float* dst = prm.part + ((size_t)split * g.Co + (size_t)grp * g.Cog + (valid ? co : 0)) * g.Kg +
                    (size_t)nt * GW_NB * 64;
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(mt * 128);
-      for (int c0 = 0; c0 < N; c0 += 32) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(taddr + c0, v);
+      for (int c0 = 0; c0 < N; c0 += 16) {
+        uint32_t v[16];
+        ptx::tmem_ld_32x16(taddr + c0, v);
         ptx::tmem_ld_wait();
         if (valid) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
+          for (int j = 0; j < 16; j += 4)
             *reinterpret_cast<float4*>(dst + c0 + j) =
                 make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
                             __uint_as_float(v[j + 3]));
         }
       }
     }
-  } else if (warp >= GW_PLAN_WARP0 && warp < GW_GATHER_WARP0) {
+  } else if (warp < GW_GATHER_WARP0) {
     // ===================== plan producers =====================
+    ptx::reg_dealloc<GW_REGS_PLAN>();
     // thread (blk, row): the sampling plan of position p0 + row for this CTA's kk block `blk`; the
     // offset / mask values of the NEXT position block are fetched while this one is built.
     const int pt = threadIdx.x - GW_PLAN_WARP0 * 32;
@@ -200,14 +209,18 @@ k_tc_grad_weight(const __grid_constant__ CUtensorMap tmap_go, const TcGwParams p
       sp.in_range = false;
       if (rc.valid) build_pos<ND>(g, rc, ptap, raw, sp);
       const PlanEntry<ND> e = plan_from_pos<T, ND>(g, rc, sp, C8);
-      ptx::mbar_wait(&plan_empty[ps], pph ^ 1);
+      ptx::mbar_wait_relaxed(&plan_empty[ps], pph ^ 1, 128);
       store_plan<ND>(ptx::smem_u32(sPlan + ps * 128 + pt), e);
       ptx::mbar_arrive(&plan_full[ps]);
       if (++ps == GW_PLAN_SLOTS) { ps = 0; pph ^= 1; }
     }
-  } else if (warp >= GW_GATHER_WARP0) {
+  } else {
     // ===================== gather producers: column tiles =====================
+    ptx::reg_alloc<GW_REGS_GATHER>();
     // 128 plan rows = NB blocks x 64 positions; warp gw owns rows gw*8 .. gw*8+7 (two passes of 4).
+    // One position block of look-ahead: the corner loads of block pb+1 are in flight while block pb is
+    // interpolated and stored (ping-pong register buffers; 3D has no room for the second buffer).
+    constexpr int NC = 1 << ND;
     const int gw = warp - GW_GATHER_WARP0;
     const int chunk = lane & 7;
     const int q0 = gw * 8 + (lane >> 3);     // plan row of pass 0 (pass 1: +4)
@@ -217,29 +230,70 @@ k_tc_grad_weight(const __grid_constant__ CUtensorMap tmap_go, const TcGwParams p
     const int c0_blk = grp * g.Cg + ((nt * GW_NB + jb) / g.K) * BK;
     const uint4* xc = xq + (c0_blk >> 3) + chunk;
     const bool active = jb < nb;
-    int s = 0, ps = 0;
-    uint32_t ph = 0, pph = 0;
-    for (int pb = pb0; pb < pb1; ++pb) {
-      ptx::mbar_wait(&plan_full[ps], pph);
+    const uint32_t plan_row = ptx::smem_u32(sPlan + q0);
+    constexpr uint32_t kSlotBytes = 128 * (uint32_t)sizeof(PlanEntry<ND>);
+    constexpr uint32_t kRow4 = 4 * (uint32_t)sizeof(PlanEntry<ND>);
+    int s = 0, ips = 0, cps = 0;
+    uint32_t ph = 0, ipph = 0;
+
+    auto issue = [&](uint4 (&v0)[NC], uint4 (&v1)[NC]) {
+      ptx::mbar_wait(&plan_full[ips], ipph);
+      if (active) {
+        const uint32_t pa = plan_row + ips * kSlotBytes;
+        int i0[NC], i1[NC];
+#pragma unroll
+        for (int q = 0; q < NC / 4; ++q) {
+          const uint4 a = lds128(pa + 16 * q), b = lds128(pa + kRow4 + 16 * q);
+          i0[4 * q] = (int)a.x; i0[4 * q + 1] = (int)a.y; i0[4 * q + 2] = (int)a.z; i0[4 * q + 3] = (int)a.w;
+          i1[4 * q] = (int)b.x; i1[4 * q + 1] = (int)b.y; i1[4 * q + 2] = (int)b.z; i1[4 * q + 3] = (int)b.w;
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) v0[c] = __ldg(xc + i0[c]);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) v1[c] = __ldg(xc + i1[c]);
+      }
+      if (++ips == GW_PLAN_SLOTS) { ips = 0; ipph ^= 1; }
+    };
+    auto finish = [&](const uint4 (&v0)[NC], const uint4 (&v1)[NC]) {
       ptx::mbar_wait(&empty[s], ph ^ 1);
       if (active) {
-        const uint32_t plan_addr = ptx::smem_u32(sPlan + ps * 128 + q0);
+        const uint32_t pa = plan_row + cps * kSlotBytes + 4 * NC;
+        uint32_t w0[NC], w1[NC];
+#pragma unroll
+        for (int q = 0; q < NC / 4; ++q) {
+          const uint4 a = lds128(pa + 16 * q), b = lds128(pa + kRow4 + 16 * q);
+          w0[4 * q] = a.x; w0[4 * q + 1] = a.y; w0[4 * q + 2] = a.z; w0[4 * q + 3] = a.w;
+          w1[4 * q] = b.x; w1[4 * q + 1] = b.y; w1[4 * q + 2] = b.z; w1[4 * q + 3] = b.w;
+        }
         const uint32_t col_addr = ptx::smem_u32(sCol + s * GW_COL_BYTES) + jb * 8192;
-        const PlanEntry<ND> e0 = load_plan<ND>(plan_addr);
-        const PlanEntry<ND> e1 = load_plan<ND>(plan_addr + 4 * (uint32_t)sizeof(PlanEntry<ND>));
-        uint4 v0[1 << ND], v1[1 << ND];
-#pragma unroll
-        for (int c = 0; c < (1 << ND); ++c) v0[c] = __ldg(xc + e0.idx[c]);
-#pragma unroll
-        for (int c = 0; c < (1 << ND); ++c) v1[c] = __ldg(xc + e1.idx[c]);
-        sts128(col_addr + sw128(r0, chunk), interp8(v0, e0.w, 1 << ND, T()));
-        sts128(col_addr + sw128(r0 + 4, chunk), interp8(v1, e1.w, 1 << ND, T()));
+        sts128(col_addr + sw128(r0, chunk), interp8(v0, w0, NC, T()));
+        sts128(col_addr + sw128(r0 + 4, chunk), interp8(v1, w1, NC, T()));
       }
       ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(&full_col[s]);
-      ptx::mbar_arrive(&plan_empty[ps]);
+      ptx::mbar_arrive(&plan_empty[cps]);
       if (++s == GW_STAGES) { s = 0; ph ^= 1; }
-      if (++ps == GW_PLAN_SLOTS) { ps = 0; pph ^= 1; }
+      if (++cps == GW_PLAN_SLOTS) cps = 0;
+    };
+
+    if (ND == 2) {
+      uint4 a0[NC], a1[NC], b0[NC], b1[NC];
+      int pb = pb0;
+      if (pb < pb1) issue(a0, a1);
+      while (pb < pb1) {
+        if (pb + 1 < pb1) issue(b0, b1);
+        finish(a0, a1);
+        if (++pb >= pb1) break;
+        if (pb + 1 < pb1) issue(a0, a1);
+        finish(b0, b1);
+        ++pb;
+      }
+    } else {
+      uint4 a0[NC], a1[NC];
+      for (int pb = pb0; pb < pb1; ++pb) {
+        issue(a0, a1);
+        finish(a0, a1);
+      }
     }
   }
 

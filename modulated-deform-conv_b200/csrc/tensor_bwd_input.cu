@@ -49,6 +49,10 @@ struct __align__(16) GiPlanRow {
   int e0;              // index of the bin's first entry (for bins longer than GI_NE)
 };
 static_assert(sizeof(GiPlanRow) == 64, "GiPlanRow must be 64 bytes");
+// registers after setmaxnreg (the CTA owns GI_THREADS x 72)
+constexpr uint32_t GI_REGS_CTL = 32, GI_REGS_EPI = 48, GI_REGS_PLAN = 56, GI_REGS_GATHER = 88;
+static_assert(128 * (GI_REGS_CTL + GI_REGS_EPI + GI_REGS_PLAN) + GI_GATHER_THREADS * GI_REGS_GATHER <= GI_THREADS * 72,
+              "setmaxnreg.inc would wait forever");
 
 struct BinEntry {
   int row;   // b * P + output position: row of the channels-last grad_output
@@ -265,6 +269,8 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const TcGiParams pr
   const int BN = prm.BN;
   const long long total_pos = (long long)g.B * g.IN;
 
+  if (warp < 4) {
+    ptx::reg_dealloc<GI_REGS_CTL>();
   if (warp == 0) {
     // ===================== TMA producer: W^T slices =====================
     if (lane == 0) {
@@ -274,7 +280,7 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const TcGiParams pr
         const int nt = t / prm.m_tiles;
         const int c0 = nt * BN;
         for (int kb = 0; kb < prm.kblocks; ++kb) {
-          ptx::mbar_wait(&empty[s], ph ^ 1);
+          ptx::mbar_wait_relaxed(&empty[s], ph ^ 1, 64);
           ptx::mbar_arrive_expect_tx(&full_b[s], (uint32_t)BN * 128u);
           ptx::tma_load_2d(sB + s * GI_B_BYTES, &tmap_wt, &full_b[s], kb * 64, c0);
           if (++s == GI_STAGES) { s = 0; ph ^= 1; }
@@ -312,8 +318,10 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const TcGiParams pr
         if (++as == 2) { as = 0; aph ^= 1; }
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  }
+  } else if (warp < 8) {
     // ===================== epilogue: TMEM -> grad_input (NCHW) =====================
+    ptx::reg_dealloc<GI_REGS_EPI>();
     const int ew = warp & 3;
     T* __restrict__ gx = reinterpret_cast<T*>(prm.gx);
     int as = 0;
@@ -326,24 +334,25 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const TcGiParams pr
       const int b = valid ? (int)(gp / g.IN) : 0;
       const int pix = valid ? (int)(gp % g.IN) : 0;
       T* xrow = gx + ((size_t)b * g.C + (size_t)nt * BN) * g.IN + pix;
-      ptx::mbar_wait(&tmem_full[as], aph);
+      ptx::mbar_wait_relaxed(&tmem_full[as], aph);
       ptx::tc_fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * GI_MAX_BN);
-      for (int cc = 0; cc < BN; cc += 32) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(taddr + cc, v);
+      for (int cc = 0; cc < BN; cc += 16) {
+        uint32_t v[16];
+        ptx::tmem_ld_32x16(taddr + cc, v);
         ptx::tmem_ld_wait();
         if (valid) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) xrow[(size_t)(cc + j) * g.IN] = cvt_to<T, float>(__uint_as_float(v[j]));
+          for (int j = 0; j < 16; ++j) xrow[(size_t)(cc + j) * g.IN] = cvt_to<T, float>(__uint_as_float(v[j]));
         }
       }
       ptx::tc_fence_before_sync();
       ptx::mbar_arrive(&tmem_empty[as]);
       if (++as == 2) { as = 0; aph ^= 1; }
     }
-  } else if (warp >= GI_PLAN_WARP0 && warp < GI_GATHER_WARP0) {
+  } else if (warp < GI_GATHER_WARP0) {
     // ===================== plan producers =====================
+    ptx::reg_dealloc<GI_REGS_PLAN>();
     // thread = tile row (input position): per tap, copy the head of the bin into shared memory; the
     // bin bounds of the next tap are fetched while this tap's entries are in flight.
     const int row = threadIdx.x - GI_PLAN_WARP0 * 32;
@@ -384,7 +393,7 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const TcGiParams pr
           }
         }
         (void)entries4;
-        ptx::mbar_wait(&plan_empty[ps], pph ^ 1);
+        ptx::mbar_wait_relaxed(&plan_empty[ps], pph ^ 1, 128);
         const uint32_t pa = ptx::smem_u32(sPlan + ps * GI_BM + row);
         const uint4* q = reinterpret_cast<const uint4*>(&r);
 #pragma unroll
@@ -393,8 +402,9 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const TcGiParams pr
         if (++ps == GI_PLAN_SLOTS) { ps = 0; pph ^= 1; }
       }
     }
-  } else if (warp >= GI_GATHER_WARP0) {
+  } else {
     // ===================== gather producers =====================
+    ptx::reg_alloc<GI_REGS_GATHER>();
     const int gw = warp - GI_GATHER_WARP0;
     const int chunk = lane & 7;
     const int row0 = gw * 8 + (lane >> 3);
