@@ -300,28 +300,61 @@ def main():
     h2d = sum(host[k].numel() * es for k in keys)
     out_host = None
 
-    def step_e2e():
-        nonlocal out_host
-        dd = {k: host[k].to(dev, non_blocking=True) for k in keys}
-        lv = {k: dd[k].requires_grad_() for k in keys if k != "grad_output"}
-        mod.weight.grad = None
-        y = fwd_bwd(lv["x"], lv["offset"], lv.get("mask"), dd["grad_output"])
-        res = [y.detach(), lv["x"].grad, lv["offset"].grad, mod.weight.grad] + ([lv["mask"].grad] if "mask" in lv else [])
-        if out_host is None:
-            out_host = [torch.empty(r.shape, dtype=r.dtype).pin_memory() for r in res]
-        for hbuf, r in zip(out_host, res):
-            hbuf.copy_(r, non_blocking=True)
-        return sum(r.numel() * r.element_size() for r in res)
+    # Pipelined over three streams with double-buffered device inputs: the H2D copy of step i+1 and the
+    # D2H read-back of step i-1 overlap the kernels of step i (PCIe is full duplex).  Every step still
+    # copies ITS inputs from pinned host memory and ITS results (output + all gradients) back to pinned
+    # host memory inside the timed region; the region ends when the last read-back has landed.
+    main = torch.cuda.current_stream()
+    s_h2d, s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
+    NBUF = 2
+    dbuf = [{k: torch.empty_like(host[k], device=dev) for k in keys} for _ in range(NBUF)]
+    ev_h2d = [torch.cuda.Event() for _ in range(NBUF)]
+    ev_comp = [torch.cuda.Event() for _ in range(NBUF)]
+    out_host = [None] * NBUF
+    keep = [None] * NBUF
+    d2h_bytes = [0]
 
-    d2h = 0
-    for _ in range(3):
-        d2h = step_e2e()
+    def issue_h2d(i):
+        b = i % NBUF
+        with torch.cuda.stream(s_h2d):
+            s_h2d.wait_event(ev_comp[b])       # the previous user of this buffer has finished computing
+            for k in keys:
+                dbuf[b][k].copy_(host[k], non_blocking=True)
+            ev_h2d[b].record(s_h2d)
+
+    def issue_step(i):
+        b = i % NBUF
+        main.wait_event(ev_h2d[b])
+        lv = {k: dbuf[b][k].detach().requires_grad_() for k in keys if k != "grad_output"}
+        mod.weight.grad = None
+        y = fwd_bwd(lv["x"], lv["offset"], lv.get("mask"), dbuf[b]["grad_output"])
+        res = [y.detach(), lv["x"].grad, lv["offset"].grad, mod.weight.grad] + ([lv["mask"].grad] if "mask" in lv else [])
+        ev_comp[b].record(main)
+        if out_host[b] is None:
+            out_host[b] = [torch.empty(r.shape, dtype=r.dtype).pin_memory() for r in res]
+        with torch.cuda.stream(s_d2h):
+            s_d2h.wait_event(ev_comp[b])
+            for hbuf, r in zip(out_host[b], res):
+                r.record_stream(s_d2h)
+                hbuf.copy_(r, non_blocking=True)
+        keep[b] = res
+        d2h_bytes[0] = sum(r.numel() * r.element_size() for r in res)
+
+    def run_e2e(n):
+        issue_h2d(0)
+        for i in range(n):
+            if i + 1 < n:
+                issue_h2d(i + 1)
+            issue_step(i)
+        main.wait_stream(s_d2h)
+
+    run_e2e(3)
     sync_all()
+    d2h = d2h_bytes[0]
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ke = max(3, min(K_steps, 10))
+    ke = max(3, K_steps)
     e2.record()
-    for _ in range(ke):
-        step_e2e()
+    run_e2e(ke)
     e3.record()
     sync_all()
     ms_e2e = e2.elapsed_time(e3)
@@ -386,7 +419,10 @@ def main():
                            "path": {0: "auto", 1: "generic", 2: "tensor"}[args.path],
                            "collective": "1 NCCL all-reduce(sum) of [grad_weight||grad_bias] per step" if world > 1 else "none"},
                 "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": ms_e2e / ke},
+                        "ms_per_step": ms_e2e / ke, "steps": ke,
+                        "how": "public Module API; per step: H2D of x/offset/mask/grad_output from pinned host memory, "
+                               "fwd+bwd, D2H of output and all gradients; copies of adjacent steps overlap the kernels "
+                               "(3 streams, double-buffered); fill and drain included"},
                 "gpu_launches": n_launch, "clocks": clocks.summary(), "roofline": roofline, "roofline_hbm": roofline_hbm,
                 "kernels_ms_per_step": kernels, "cpu_baseline": cpu_base, "reference_cuda": ref_cuda}
         print(json.dumps(line))

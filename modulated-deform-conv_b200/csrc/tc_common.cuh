@@ -249,6 +249,14 @@ constexpr int umma_fmt() {
   return std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
 }
 
+// Side stream of the current device (created on first use) + fork/join helpers: small independent
+// passes (the inverse-index build) run beside the layout passes of the main stream.
+struct SideStream {
+  cudaStream_t stream;
+  cudaEvent_t fork, join;
+};
+SideStream* side_stream();   // nullptr if it cannot be created (callers then stay on the main stream)
+
 // backward kernels (tensor_bwd.cu)
 template <typename T>
 void tensor_backward_t(const DevGeom& g, const void* x, const void* w, const void* off, const void* mask,
@@ -265,8 +273,9 @@ void tensor_grad_sample(const DevGeom& g, const T* xt, const T* wr, const void* 
 bool grad_input_supported(const DevGeom& g);
 size_t grad_input_workspace(const DevGeom& g);
 template <typename T>
-void tensor_grad_input(const DevGeom& g, const void* w, const void* off, const void* mask, const void* go, void* gx,
-                       void* ws, LaunchCtx& ctx);
+void tensor_grad_input_prepare(const DevGeom& g, const void* off, const void* mask, void* ws, LaunchCtx& ctx);
+template <typename T>
+void tensor_grad_input(const DevGeom& g, const void* w, const void* go, void* gx, void* ws, LaunchCtx& ctx);
 
 }  // namespace tc
 }  // namespace mdconv

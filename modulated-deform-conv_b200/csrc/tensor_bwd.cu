@@ -386,7 +386,11 @@ void tensor_backward_t(const DevGeom& g, const void* x, const void* w, const voi
   const int dtype = std::is_same<T, __half>::value ? MDCONV_F16 : MDCONV_BF16;
   const bool data_tc = data_on_tensor_cores(g);
 
+  // the inverse index of grad_input only needs offset/mask: build it on the side stream, beside the
+  // layout passes and ahead of the big kernels
+  if (data_tc) tensor_grad_input_prepare<T>(g, off, mask, data_ws, ctx);
   launch_to_channels_last<T>((const T*)x, xt, g.B, g.C, g.IN, ctx);
+  if (data_tc) launch_reorder_weight<T>((const T*)w, wr, g.Co, g.Cg, g.K, ctx);
 
   // ---- grad_weight first (it is what a data-parallel caller all-reduces) ----
   TcGwParams prm;
@@ -434,9 +438,8 @@ void tensor_backward_t(const DevGeom& g, const void* x, const void* w, const voi
 
   // ---- grad_offset / grad_mask / grad_input (+ grad_bias) ----
   if (data_tc) {
-    launch_reorder_weight<T>((const T*)w, wr, g.Co, g.Cg, g.K, ctx);
     tensor_grad_sample<T>(g, xt, wr, off, mask, go, goff, gmask, ctx);
-    tensor_grad_input<T>(g, w, off, mask, go, gx, data_ws, ctx);
+    tensor_grad_input<T>(g, w, go, gx, data_ws, ctx);
     generic_backward(g, dtype, x, w, off, mask, go, gx, gw, gb, goff, gmask, nullptr, ctx, GENERIC_BWD_BIAS);
   } else {
     generic_backward(g, dtype, x, w, off, mask, go, gx, gw, gb, goff, gmask, data_ws, ctx,

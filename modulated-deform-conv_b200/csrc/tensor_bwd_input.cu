@@ -556,9 +556,36 @@ size_t grad_input_workspace(const DevGeom& g) {
   return align256((size_t)g.B * g.Co * g.P * 2) + align256((size_t)g.Co * g.Kg * 2) + gi_layout(g).total;
 }
 
+// Stage 1 (can be issued early): the inverse index, on the side stream when there is one.  Returns with
+// the side stream forked from ctx.stream; tensor_grad_input() joins it before the GEMM kernel.
 template <typename T>
-void tensor_grad_input(const DevGeom& g, const void* w, const void* off, const void* mask, const void* go, void* gx,
-                       void* ws, LaunchCtx& ctx) {
+void tensor_grad_input_prepare(const DevGeom& g, const void* off, const void* mask, void* ws, LaunchCtx& ctx) {
+  char* base = reinterpret_cast<char*>(ws);
+  base += align256((size_t)g.B * g.Co * g.P * sizeof(T));
+  base += align256((size_t)g.Co * g.Kg * sizeof(T));
+  const GiLayout L = gi_layout(g);
+  SideStream* ss = side_stream();
+  cudaStream_t main_stream = ctx.stream;
+  if (ss) {
+    cudaEventRecord(ss->fork, main_stream);
+    cudaStreamWaitEvent(ss->stream, ss->fork, 0);
+    ctx.stream = ss->stream;
+  }
+  if (g.nd == 2) {
+    if (g.modulated) build_bins<T, 2, true>(g, off, mask, base, L, ctx);
+    else build_bins<T, 2, false>(g, off, mask, base, L, ctx);
+  } else {
+    if (g.modulated) build_bins<T, 3, true>(g, off, mask, base, L, ctx);
+    else build_bins<T, 3, false>(g, off, mask, base, L, ctx);
+  }
+  if (ss) {
+    cudaEventRecord(ss->join, ss->stream);
+    ctx.stream = main_stream;
+  }
+}
+
+template <typename T>
+void tensor_grad_input(const DevGeom& g, const void* w, const void* go, void* gx, void* ws, LaunchCtx& ctx) {
   char* base = reinterpret_cast<char*>(ws);
   T* got = reinterpret_cast<T*>(base);
   base += align256((size_t)g.B * g.Co * g.P * sizeof(T));
@@ -574,13 +601,7 @@ void tensor_grad_input(const DevGeom& g, const void* w, const void* off, const v
     k_transpose_weight<T><<<blocks, 256, 0, ctx.stream>>>((const T*)w, wt, g.Co, g.Cg, g.Cog, g.K);
     MDCONV_CHECK_LAUNCH(ctx);
   }
-  if (g.nd == 2) {
-    if (g.modulated) build_bins<T, 2, true>(g, off, mask, base, L, ctx);
-    else build_bins<T, 2, false>(g, off, mask, base, L, ctx);
-  } else {
-    if (g.modulated) build_bins<T, 3, true>(g, off, mask, base, L, ctx);
-    else build_bins<T, 3, false>(g, off, mask, base, L, ctx);
-  }
+  if (SideStream* ss = side_stream()) cudaStreamWaitEvent(ctx.stream, ss->join, 0);  // inverse index is ready
 
   TcGiParams prm;
   prm.g = g;
@@ -626,10 +647,10 @@ void tensor_grad_input(const DevGeom& g, const void* w, const void* off, const v
   MDCONV_CHECK_LAUNCH(ctx);
 }
 
-template void tensor_grad_input<__half>(const DevGeom&, const void*, const void*, const void*, const void*, void*,
-                                        void*, LaunchCtx&);
-template void tensor_grad_input<__nv_bfloat16>(const DevGeom&, const void*, const void*, const void*, const void*,
-                                               void*, void*, LaunchCtx&);
+template void tensor_grad_input<__half>(const DevGeom&, const void*, const void*, void*, void*, LaunchCtx&);
+template void tensor_grad_input<__nv_bfloat16>(const DevGeom&, const void*, const void*, void*, void*, LaunchCtx&);
+template void tensor_grad_input_prepare<__half>(const DevGeom&, const void*, const void*, void*, LaunchCtx&);
+template void tensor_grad_input_prepare<__nv_bfloat16>(const DevGeom&, const void*, const void*, void*, LaunchCtx&);
 
 }  // namespace tc
 }  // namespace mdconv

@@ -512,6 +512,28 @@ PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
+SideStream* side_stream() {
+  static SideStream per_dev[64];
+  static bool made[64] = {false};
+  static bool failed[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (failed[dev]) return nullptr;
+  if (!made[dev]) {
+    SideStream s;
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
+      failed[dev] = true;
+      (void)cudaGetLastError();
+      return nullptr;
+    }
+    per_dev[dev] = s;
+    made[dev] = true;
+  }
+  return &per_dev[dev];
+}
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {
