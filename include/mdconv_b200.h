@@ -118,6 +118,12 @@ long long mdconv_total_launch_count(void);
 int mdconv_profile_enable(int on);
 int mdconv_profile_read(char* buf, size_t cap);
 
+/* The backward builds its inverse index on an internal side stream (forked from / joined to the
+ * caller's stream with events) so it overlaps the layout passes.  on = 0 keeps every kernel on the
+ * caller's stream (use it with mdconv_profile_enable: a forked kernel's events also count the time it
+ * waits for free SMs).  Default on; MDCONV_B200_NO_SIDE_STREAM=1 in the environment also disables it. */
+int mdconv_side_stream_enable(int on);
+
 int mdconv_forward(const mdconv_geom_t* g, const void* input, const void* weight, const void* bias,
                    const void* offset, const void* mask, void* output, void* workspace,
                    size_t workspace_bytes, void* stream);

@@ -106,13 +106,17 @@ def library_path() -> str:
 
 _lib.mdconv_profile_enable.restype = _i
 _lib.mdconv_profile_enable.argtypes = [_i]
+_lib.mdconv_side_stream_enable.restype = _i
+_lib.mdconv_side_stream_enable.argtypes = [_i]
 _lib.mdconv_profile_read.restype = _i
 _lib.mdconv_profile_read.argtypes = [ctypes.c_char_p, _sz]
 
 
 def profile_enable(on: bool) -> None:
-    """Bracket every kernel this library launches with CUDA events (benchmark use)."""
+    """Bracket every kernel this library launches with CUDA events (benchmark use).  While profiling,
+    the backward's side stream is switched off so each kernel's time is its own."""
     _lib.mdconv_profile_enable(1 if on else 0)
+    _lib.mdconv_side_stream_enable(0 if on else 1)
 
 
 def profile_read():

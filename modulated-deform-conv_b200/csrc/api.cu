@@ -10,6 +10,7 @@
 
 #include "common.cuh"
 #include "tensor_path.cuh"
+#include "tc_common.cuh"
 
 using namespace mdconv;
 
@@ -138,6 +139,11 @@ int mdconv_profile_read(char* buf, size_t cap) {
     snprintf(buf, cap, "%s", out.c_str());
   }
   return n;
+}
+
+int mdconv_side_stream_enable(int on) {
+  mdconv::tc::set_side_stream_enabled(on != 0);
+  return MDCONV_OK;
 }
 
 int mdconv_abi_version(void) { return MDCONV_B200_ABI_VERSION; }

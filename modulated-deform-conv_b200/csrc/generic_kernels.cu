@@ -32,8 +32,14 @@ __global__ void __launch_bounds__(NT) k_generic_forward(const DevGeom g, const T
                                                         const T* __restrict__ w, const T* __restrict__ bias,
                                                         const T* __restrict__ off, const T* __restrict__ mask,
                                                         T* __restrict__ y) {
-  __shared__ F As[BK][BM + 4];  // col chunk   [kk][pix]
-  __shared__ F Bs[BK][BN + 4];  // weight chunk [kk][co]
+  constexpr int NC = 1 << ND;
+  __shared__ F As[BK][BM + 4];  // col chunk   [channel][pix]
+  __shared__ F Bs[BK][BN + 4];  // weight chunk [channel][co]
+  // sampling plan of the current (tap, deformable group): per pixel the corner indices and the
+  // interpolation weight x mask, computed ONCE and reused by every channel of the group (the
+  // reference recomputes it per channel, src/mdeformable_conv.cu:59-83)
+  __shared__ int Pi[NC][BM];
+  __shared__ F Pw[NC][BM];
 
   const int tilesP = (g.P + BM - 1) / BM;
   const int b = blockIdx.x / tilesP;
@@ -54,51 +60,93 @@ __global__ void __launch_bounds__(NT) k_generic_forward(const DevGeom g, const T
     for (int j = 0; j < 4; ++j) acc[i][j] = (F)0;
 
   const int lm = tid % BM;       // pixel handled in the col loader
-  const int lk0 = tid / BM;      // first kk row handled (stride 4)
-  const int wk = tid % BK;       // weight loader: kk
+  const int lk0 = tid / BM;      // first channel row handled (stride 4)
+  const int wk = tid % BK;       // weight loader: channel
   const int wn0 = tid / BK;      // weight loader: first co (stride 16)
 
-  for (int k0 = 0; k0 < g.Kg; k0 += BK) {
-    // ---- gather the col chunk ----
+  // channels of this conv group, walked in runs that share a deformable group
+  int cl0 = 0;
+  while (cl0 < g.Cg) {
+    const int cglob = grp * g.Cg + cl0;
+    const int dgi = cglob / g.Cdg;
+    const int room = (dgi + 1) * g.Cdg - cglob;
+    const int cl1 = cl0 + room < g.Cg ? cl0 + room : g.Cg;
+    for (int tap = 0; tap < g.K; ++tap) {
+      // ---- plan of (pixel, tap, dgi) ----
+      __syncthreads();  // previous users of Pi / Pw are done
+      if (tid < BM) {
+        const int p = p0 + tid;
 #pragma unroll
-    for (int i = 0; i < BK / 4; ++i) {
-      const int kk = k0 + lk0 + 4 * i;
-      const int p = p0 + lm;
-      F v = (F)0;
-      if (kk < g.Kg && p < g.P) {
-        const int cl = kk / g.K, tap = kk - cl * g.K;
-        const int c = grp * g.Cg + cl;
-        const int dgi = c / g.Cdg;
-        SamplePoint<ND, F> s;
-        make_sample_point<ND, T, F>(g, off_b, dgi, tap, p, s);
-        v = interp_forward<ND, T, F>(g, x_b + (size_t)c * g.IN, s);
-        if (MOD) v *= ld_as<F>(mask_b + (size_t)(dgi * g.K + tap) * g.P + p);
+        for (int c = 0; c < NC; ++c) { Pi[c][tid] = 0; Pw[c][tid] = (F)0; }
+        if (p < g.P) {
+          SamplePoint<ND, F> sp;
+          make_sample_point<ND, T, F>(g, off_b, dgi, tap, p, sp);
+          if (sp.in_range) {
+            F m = (F)1;
+            if (MOD) m = ld_as<F>(mask_b + (size_t)(dgi * g.K + tap) * g.P + p);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+              F wgt = m;
+              bool ok = true;
+              int idx = 0;
+#pragma unroll
+              for (int a = 0; a < ND; ++a) {
+                const int hi = (c >> a) & 1;
+                const int ia = sp.lo[a] + hi;
+                ok = ok && (hi ? (ia <= g.in[a] - 1) : (ia >= 0));
+                wgt *= hi ? sp.fr[a] : ((F)1 - sp.fr[a]);
+                idx = idx * g.in[a] + ia;
+              }
+              if (ok) { Pi[c][tid] = idx; Pw[c][tid] = wgt; }
+            }
+          }
+        }
       }
-      As[lk0 + 4 * i][lm] = v;
+      __syncthreads();
+      int pi[NC];
+      F pw[NC];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) { pi[c] = Pi[c][lm]; pw[c] = Pw[c][lm]; }
+
+      for (int c0 = cl0; c0 < cl1; c0 += BK) {
+        // ---- gather the col chunk: BK channels x BM pixels of this tap ----
+#pragma unroll
+        for (int i = 0; i < BK / 4; ++i) {
+          const int cl = c0 + lk0 + 4 * i;
+          F v = (F)0;
+          if (cl < cl1) {
+            const T* plane = x_b + (size_t)(grp * g.Cg + cl) * g.IN;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) v += pw[c] * ld_as<F>(plane + pi[c]);
+          }
+          As[lk0 + 4 * i][lm] = v;
+        }
+        // ---- weight chunk ----
+#pragma unroll
+        for (int i = 0; i < BN / 16; ++i) {
+          const int n = wn0 + 16 * i;
+          const int cl = c0 + wk;
+          F v = (F)0;
+          if (cl < cl1 && n0 + n < g.Cog) v = ld_as<F>(w + (size_t)(grp * g.Cog + n0 + n) * g.Kg + (size_t)cl * g.K + tap);
+          Bs[wk][n] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+          F a[4], bq[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) a[i] = As[kk][tx * 4 + i];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) bq[j] = Bs[kk][ty * 4 + j];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * bq[j];
+        }
+        __syncthreads();
+      }
     }
-    // ---- weight chunk ----
-#pragma unroll
-    for (int i = 0; i < BN / 16; ++i) {
-      const int n = wn0 + 16 * i;
-      const int kk = k0 + wk;
-      F v = (F)0;
-      if (kk < g.Kg && n0 + n < g.Cog) v = ld_as<F>(w + (size_t)(grp * g.Cog + n0 + n) * g.Kg + kk);
-      Bs[wk][n] = v;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < BK; ++kk) {
-      F a[4], bq[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[kk][tx * 4 + i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) bq[j] = Bs[kk][ty * 4 + j];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * bq[j];
-    }
-    __syncthreads();
+    cl0 = cl1;
   }
 
 #pragma unroll

@@ -255,7 +255,8 @@ struct SideStream {
   cudaStream_t stream;
   cudaEvent_t fork, join;
 };
-SideStream* side_stream();   // nullptr if it cannot be created (callers then stay on the main stream)
+SideStream* side_stream();   // nullptr if disabled or it cannot be created (callers then stay on the main stream)
+void set_side_stream_enabled(bool on);
 
 // backward kernels (tensor_bwd.cu)
 template <typename T>

@@ -144,6 +144,34 @@ __global__ void __launch_bounds__(256) k_bin_sort(const int* __restrict__ start,
 #pragma unroll
       for (int a = 0; a < 8; ++a)
         if (a < n) keys[s + a] = (k[a] << 32) | (k[a] >> 32);
+    } else if (n <= 16) {
+      unsigned long long k[16];
+#pragma unroll
+      for (int a = 0; a < 16; ++a) {
+        if (a < n) {
+          const unsigned long long v = keys[s + a];
+          k[a] = (v << 32) | (v >> 32);
+        } else {
+          k[a] = ~0ull;
+        }
+      }
+      // Batcher odd-even merge sort, 16 keys, 63 comparators (typical 3D bins hold ~8 entries)
+      cswap(k[0], k[1]); cswap(k[2], k[3]); cswap(k[0], k[2]); cswap(k[1], k[3]); cswap(k[1], k[2]);
+      cswap(k[4], k[5]); cswap(k[6], k[7]); cswap(k[4], k[6]); cswap(k[5], k[7]); cswap(k[5], k[6]);
+      cswap(k[0], k[4]); cswap(k[2], k[6]); cswap(k[2], k[4]); cswap(k[1], k[5]); cswap(k[3], k[7]);
+      cswap(k[3], k[5]); cswap(k[1], k[2]); cswap(k[3], k[4]); cswap(k[5], k[6]); cswap(k[8], k[9]);
+      cswap(k[10], k[11]); cswap(k[8], k[10]); cswap(k[9], k[11]); cswap(k[9], k[10]); cswap(k[12], k[13]);
+      cswap(k[14], k[15]); cswap(k[12], k[14]); cswap(k[13], k[15]); cswap(k[13], k[14]); cswap(k[8], k[12]);
+      cswap(k[10], k[14]); cswap(k[10], k[12]); cswap(k[9], k[13]); cswap(k[11], k[15]); cswap(k[11], k[13]);
+      cswap(k[9], k[10]); cswap(k[11], k[12]); cswap(k[13], k[14]); cswap(k[0], k[8]); cswap(k[4], k[12]);
+      cswap(k[4], k[8]); cswap(k[2], k[10]); cswap(k[6], k[14]); cswap(k[6], k[10]); cswap(k[2], k[4]);
+      cswap(k[6], k[8]); cswap(k[10], k[12]); cswap(k[1], k[9]); cswap(k[5], k[13]); cswap(k[5], k[9]);
+      cswap(k[3], k[11]); cswap(k[7], k[15]); cswap(k[7], k[11]); cswap(k[3], k[5]); cswap(k[7], k[9]);
+      cswap(k[11], k[13]); cswap(k[1], k[2]); cswap(k[3], k[4]); cswap(k[5], k[6]); cswap(k[7], k[8]);
+      cswap(k[9], k[10]); cswap(k[11], k[12]); cswap(k[13], k[14]);
+#pragma unroll
+      for (int a = 0; a < 16; ++a)
+        if (a < n) keys[s + a] = (k[a] << 32) | (k[a] >> 32);
     } else {
       for (int a = s + 1; a < e; ++a) {
         const BinEntry v = entries[a];

@@ -22,6 +22,10 @@
 // by two small pre-pass kernels into the caller's workspace.
 //
 // Replaces reference K1-K4 + G1 (src/mdeformable_conv.cu:38-87,172-184 and twins).
+#include <stdlib.h>
+
+#include <atomic>
+
 #include "tc_common.cuh"
 #include "tensor_path.cuh"
 
@@ -379,32 +383,64 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const TcFwdParams prm) 
 }
 
 // ---- pre-pass kernels ---------------------------------------------------------------------------
-// x [B][C][IN] -> xt [B][IN][C]
-template <typename T>
+// x [B][C][IN] -> xt [B][IN][C].  64 channels x 64 positions per block; 16-byte loads along the
+// positions, 16-byte stores along the channels, transposed through shared memory (row stride 66
+// elements = 33 words keeps both phases at most 2-way bank conflicted).  VEC == false is the scalar
+// form for sizes / pointers that are not 16-byte friendly.
+template <typename T, bool VEC>
 __global__ void __launch_bounds__(256) k_to_channels_last(const T* __restrict__ x, T* __restrict__ xt, int C, int IN) {
-  __shared__ T tile[64][66];
+  __shared__ __align__(16) T tile[64][66];  // [position][channel]
   const int b = blockIdx.z;
   const int c0 = blockIdx.y * 64, i0 = blockIdx.x * 64;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const T* xb = x + (size_t)b * C * IN;
   T* xtb = xt + (size_t)b * C * IN;
-#pragma unroll
-  for (int rr = 0; rr < 8; ++rr) {
-    const int c = ty + 8 * rr;
+  if (VEC) {
+    // load: thread -> (channel, 8-position chunk); 512 (channel, chunk) pairs, two per thread
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const int i = tx + 32 * h;
-      if (c0 + c < C && i0 + i < IN) tile[c][i] = xb[(size_t)(c0 + c) * IN + i0 + i];
+      const int q = threadIdx.x + 256 * h;
+      const int c = q >> 3, ch = q & 7;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (c0 + c < C && i0 + ch * 8 < IN) v = __ldg(reinterpret_cast<const uint4*>(xb + (size_t)(c0 + c) * IN + i0 + ch * 8));
+      const T* e = reinterpret_cast<const T*>(&v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) tile[ch * 8 + k][c] = e[k];
     }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int rr = 0; rr < 8; ++rr) {
-    const int i = ty + 8 * rr;
+    __syncthreads();
+    // store: thread -> (position, 8-channel chunk)
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const int c = tx + 32 * h;
-      if (c0 + c < C && i0 + i < IN) xtb[(size_t)(i0 + i) * C + c0 + c] = tile[c][i];
+      const int q = threadIdx.x + 256 * h;
+      const int i = q >> 3, ch = q & 7;
+      if (i0 + i < IN && c0 + ch * 8 < C) {
+        uint4 v;
+        uint32_t* o = reinterpret_cast<uint32_t*>(&v);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&tile[i][ch * 8]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] = src[k];
+        *reinterpret_cast<uint4*>(xtb + (size_t)(i0 + i) * C + c0 + ch * 8) = v;
+      }
+    }
+  } else {
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr) {
+      const int c = ty + 8 * rr;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = tx + 32 * h;
+        if (c0 + c < C && i0 + i < IN) tile[i][c] = xb[(size_t)(c0 + c) * IN + i0 + i];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr) {
+      const int i = ty + 8 * rr;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = tx + 32 * h;
+        if (c0 + c < C && i0 + i < IN) xtb[(size_t)(i0 + i) * C + c0 + c] = tile[i][c];
+      }
     }
   }
 }
@@ -512,10 +548,18 @@ PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
+static std::atomic<bool> g_side_stream_on{true};
+void set_side_stream_enabled(bool on) { g_side_stream_on = on; }
+
 SideStream* side_stream() {
+  if (!g_side_stream_on) return nullptr;
   static SideStream per_dev[64];
   static bool made[64] = {false};
   static bool failed[64] = {false};
+  // MDCONV_B200_NO_SIDE_STREAM=1 keeps everything on the caller's stream (per-kernel event timings are
+  // only meaningful that way: a forked kernel's events also count the time it waits for free SMs)
+  static const bool disabled = [] { const char* e = getenv("MDCONV_B200_NO_SIDE_STREAM"); return e && e[0] == '1'; }();
+  if (disabled) return nullptr;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
   if (failed[dev]) return nullptr;
@@ -549,7 +593,9 @@ template <typename T>
 void launch_to_channels_last(const T* x, T* xt, int B, int C, int IN, LaunchCtx& ctx) {
   ProfScope prof(ctx, "to_channels_last");
   dim3 grid((unsigned)((IN + 63) / 64), (unsigned)((C + 63) / 64), (unsigned)B);
-  k_to_channels_last<T><<<grid, 256, 0, ctx.stream>>>(x, xt, C, IN);
+  const bool vec = IN % 8 == 0 && C % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)xt & 15) == 0;
+  if (vec) k_to_channels_last<T, true><<<grid, 256, 0, ctx.stream>>>(x, xt, C, IN);
+  else k_to_channels_last<T, false><<<grid, 256, 0, ctx.stream>>>(x, xt, C, IN);
   MDCONV_CHECK_LAUNCH(ctx);
 }
 template <typename T>
