@@ -68,6 +68,8 @@ int resolve(const mdconv_geom_t* in, DevGeom& g) {
     g.fd_out[a] = make_fastdiv(g.out[a]);
     g.fd_k[a] = make_fastdiv(g.k[a]);
   }
+  g.fd_K = make_fastdiv(g.K);
+  g.fd_Cdg = make_fastdiv(g.Cdg);
   return MDCONV_OK;
 }
 

@@ -50,6 +50,7 @@ struct DevGeom {
   int Kg;   // Cg * K, reduction length of the per-group contraction
   int modulated, rule, with_bias;
   FastDiv fd_out[3], fd_k[3];  // divisors out[a], k[a]
+  FastDiv fd_K, fd_Cdg;        // divisors K (taps), Cdg (channels per deformable group)
 };
 
 // ---- storage <-> compute conversions --------------------------------------------------------
@@ -89,11 +90,13 @@ __device__ __forceinline__ void make_sample_point(const DevGeom& g, const T* __r
                                                   int p, SamplePoint<ND, F>& s) {
   int o[3], t[3];
   if (ND == 2) {
-    o[1] = p % g.out[1]; o[0] = p / g.out[1];
-    t[1] = tap % g.k[1]; t[0] = tap / g.k[1];
+    o[0] = fdiv(p, g.fd_out[1]); o[1] = p - o[0] * g.out[1];
+    t[0] = fdiv(tap, g.fd_k[1]); t[1] = tap - t[0] * g.k[1];
   } else {
-    o[2] = p % g.out[2]; int r = p / g.out[2]; o[1] = r % g.out[1]; o[0] = r / g.out[1];
-    t[2] = tap % g.k[2]; int q = tap / g.k[2]; t[1] = q % g.k[1]; t[0] = q / g.k[1];
+    const int r = fdiv(p, g.fd_out[2]); o[2] = p - r * g.out[2];
+    o[0] = fdiv(r, g.fd_out[1]); o[1] = r - o[0] * g.out[1];
+    const int q = fdiv(tap, g.fd_k[2]); t[2] = tap - q * g.k[2];
+    t[0] = fdiv(q, g.fd_k[1]); t[1] = q - t[0] * g.k[1];
   }
   const T* op = off_b + ((size_t)(dgi * g.K + tap) * ND) * g.P + p;
   bool ok = true;

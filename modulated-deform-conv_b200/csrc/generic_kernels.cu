@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(NT) k_generic_bwd_data(const DevGeom g, const 
     for (; cl * g.K + tap < kk_end; ++cl) {
       const int kk = cl * g.K + tap;
       const int c = grp * g.Cg + cl;
-      const int dgi = c / g.Cdg;
+      const int dgi = fdiv(c, g.fd_Cdg);
       if (dgi != cur_dg) {
         if (cur_dg >= 0) {  // flush sums of the previous deformable group
           if (cp.offset_grad) {
@@ -361,9 +361,9 @@ __global__ void __launch_bounds__(NT) k_generic_bwd_weight(const DevGeom g, cons
         if (n0 + r < g.Cog) gv = ld_as<F>(go_b + (size_t)(n0 + r) * g.P + p);
         const int kk = kk0 + r;
         if (kk < g.Kg) {
-          const int cl = kk / g.K, tap = kk - cl * g.K;
+          const int cl = fdiv(kk, g.fd_K), tap = kk - cl * g.K;
           const int c = grp * g.Cg + cl;
-          const int dgi = c / g.Cdg;
+          const int dgi = fdiv(c, g.fd_Cdg);
           SamplePoint<ND, F> s;
           make_sample_point<ND, T, F>(g, off_b, dgi, tap, p, s);
           cv = interp_forward<ND, T, F>(g, x_b + (size_t)c * g.IN, s);

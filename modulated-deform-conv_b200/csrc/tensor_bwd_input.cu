@@ -43,7 +43,7 @@ constexpr int GI_NE = 8;  // bin entries staged per (position, tap); longer bins
 
 // One (input position, tap) of the tile: the first GI_NE entries of its bin, ready for the gather.
 struct __align__(16) GiPlanRow {
-  int idx[GI_NE];      // uint4 index of the entry's 8-channel vector in channels-last grad_output (chunk excluded)
+  uint32_t idx[GI_NE]; // byte offset of the entry's row in the channels-last grad_output
   __half w[GI_NE];     // interpolation weight x mask (values in [0, max|mask|]; fp16 keeps 11 bits)
   int n;               // entries in the bin
   int e0;              // index of the bin's first entry (for bins longer than GI_NE)
@@ -408,7 +408,7 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const TcGiParams pr
         if (bin0 >= 0 && tap + 1 < g.K) e_hi = __ldg(bin_start + bin0 + tap + 2);
         GiPlanRow r;
 #pragma unroll
-        for (int i = 0; i < GI_NE; ++i) { r.idx[i] = 0; r.w[i] = __float2half_rn(0.f); }
+        for (int i = 0; i < GI_NE; ++i) { r.idx[i] = 0u; r.w[i] = __float2half_rn(0.f); }
         r.n = n;
         r.e0 = e0;
         // entries are 8 bytes; read pairs with 16-byte loads when the bin start is even
@@ -416,7 +416,7 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const TcGiParams pr
         for (int i = 0; i < GI_NE; ++i) {
           if (i < n) {
             const int2 ev = __ldg(entries2 + e0 + i);
-            r.idx[i] = ev.x * Co8;
+            r.idx[i] = (uint32_t)ev.x * (uint32_t)(g.Co * 2);
             r.w[i] = __float2half_rn(__int_as_float(ev.y));
           }
         }
@@ -448,20 +448,21 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const TcGiParams pr
         ptx::mbar_wait(&plan_full[ps], pph);
         const uint32_t plan_addr = ptx::smem_u32(sPlan + ps * GI_BM + row0);
         for (int cob = 0; cob < prm.cobs; ++cob) {
-          const uint4* gc = gq + ((grp * g.Cog + cob * 64) >> 3) + chunk;
+          // byte address of this lane's 8 channels in row 0; entries add a 32-bit row offset
+          const char* gcb = reinterpret_cast<const char*>(gq + ((grp * g.Cog + cob * 64) >> 3) + chunk);
           ptx::mbar_wait(&empty[s], ph ^ 1);
           const uint32_t a_addr = ptx::smem_u32(sA + s * GI_A_BYTES);
 #pragma unroll
           for (int pass = 0; pass < 2; ++pass) {
             const uint32_t pa = plan_addr + pass * 4 * (uint32_t)sizeof(GiPlanRow);
             const uint4 i0 = lds128(pa), i1 = lds128(pa + 16), wv = lds128(pa + 32), meta = lds128(pa + 48);
-            const int idx[GI_NE] = {(int)i0.x, (int)i0.y, (int)i0.z, (int)i0.w, (int)i1.x, (int)i1.y, (int)i1.z, (int)i1.w};
+            const uint32_t idx[GI_NE] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
             const __half* wh = reinterpret_cast<const __half*>(&wv);
             const int n = (int)meta.x;
             uint4 v[GI_NE];
 #pragma unroll
             for (int i = 0; i < GI_NE; ++i)
-              if (i < n) v[i] = __ldg(gc + idx[i]);
+              if (i < n) v[i] = __ldg(reinterpret_cast<const uint4*>(gcb + idx[i]));
             Acc8<T> acc;
             acc.clear();
 #pragma unroll
@@ -469,7 +470,8 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const TcGiParams pr
               if (i < n) acc.fma(v[i], wh[i]);
             for (int e = GI_NE; e < n; ++e) {   // rare: bins longer than the staged head
               const int2 ee = __ldg(entries2 + (int)meta.y + e);
-              acc.fma(__ldg(gc + (size_t)ee.x * Co8), __int_as_float(ee.y));
+              acc.fma(__ldg(reinterpret_cast<const uint4*>(gcb + (size_t)ee.x * (size_t)(g.Co * 2))),
+                      __int_as_float(ee.y));
             }
             sts128(a_addr + sw128(row0 + pass * 4, chunk), acc.pack());
           }
@@ -575,7 +577,7 @@ void build_bins(const DevGeom& g, const void* off, const void* mask, char* ws, c
 bool grad_input_supported(const DevGeom& g) {
   if (g.Cog % 64 != 0 || g.Cg % 64 != 0 || g.Cdg % 64 != 0 || g.Co % 8 != 0) return false;
   if (num_bins(g) + 1 > 2147483647ULL || max_entries(g) > 2147483647ULL) return false;
-  if ((long long)g.B * g.P * (g.Co / 8) > 2147483647LL) return false;
+  if ((long long)g.B * g.P * g.Co * 2 > 4294967295LL) return false;  // 32-bit byte offsets into grad_output
   return true;
 }
 
