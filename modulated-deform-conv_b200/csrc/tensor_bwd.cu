@@ -28,7 +28,7 @@ constexpr int GW_NB = 2;                       // 64-wide kk blocks per CTA tile
 constexpr int GW_GO_BYTES = 2 * 128 * 128;     // two M tiles of [128 co x 64 pos]
 constexpr int GW_COL_BYTES = GW_NB * 64 * 128; // NB blocks of [64 pos x 64 kk]
 // registers after setmaxnreg (the CTA owns GW_THREADS x 72)
-constexpr uint32_t GW_REGS_CTL = 32, GW_REGS_EPI = 48, GW_REGS_PLAN = 56, GW_REGS_GATHER = 88;
+constexpr uint32_t GW_REGS_CTL = 32, GW_REGS_EPI = 56, GW_REGS_PLAN = 56, GW_REGS_GATHER = 88;
 static_assert(128 * (GW_REGS_CTL + GW_REGS_EPI + GW_REGS_PLAN) + GW_GATHER_THREADS * GW_REGS_GATHER <= GW_THREADS * 72,
               "setmaxnreg.inc would wait forever");
 
@@ -143,76 +143,80 @@ k_tc_grad_weight(const __grid_constant__ CUtensorMap tmap_go, const TcGwParams p
       ptx::umma_commit(done);
     }
   }
-  } else if (warp < 8) {
-    // ===================== epilogue: TMEM -> fp32 partial =====================
-    ptx::reg_dealloc<GW_REGS_EPI>();
-    const int ew = warp & 3;
-    ptx::mbar_wait_relaxed(done, 0, 1024);
-    ptx::tc_fence_after_sync();
-    const int N = nb * 64;
-    for (int mt = 0; mt < MT; ++mt) {
-      const int co = mp * 256 + mt * 128 + ew * 32 + lane;  // within the group
-      const bool valid = co < g.Cog;
-      float* dst = prm.part + ((size_t)split * g.Co + (size_t)grp * g.Cog + (valid ? co : 0)) * g.Kg +
-                   (size_t)nt * GW_NB * 64;
-      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(mt * 128);
-      for (int c0 = 0; c0 < N; c0 += 16) {
-        uint32_t v[16];
-        ptx::tmem_ld_32x16(taddr + c0, v);
-        ptx::tmem_ld_wait();
-        if (valid) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4)
-            *reinterpret_cast<float4*>(dst + c0 + j) =
-                make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                            __uint_as_float(v[j + 3]));
-        }
-      }
-    }
   } else if (warp < GW_GATHER_WARP0) {
-    // ===================== plan producers =====================
+    // ===================== plan producers (warps 4-11), then epilogue (warps 4-7) =====================
+    // Two teams of 128 threads take alternate position blocks (team 0 = warps 8-11: even blocks, team 1 =
+    // warps 4-7: odd blocks), so two plans are always being built; a single in-order team is the
+    // bottleneck otherwise (a plan is ~150 dependent instructions and is consumed once).
     ptx::reg_dealloc<GW_REGS_PLAN>();
-    // thread (blk, row): the sampling plan of position p0 + row for this CTA's kk block `blk`; the
-    // offset / mask values of the NEXT position block are fetched while this one is built.
-    const int pt = threadIdx.x - GW_PLAN_WARP0 * 32;
-    const T* __restrict__ off = reinterpret_cast<const T*>(prm.off);
-    const T* __restrict__ mask = reinterpret_cast<const T*>(prm.mask);
-    const int C8 = g.C >> 3;
-    const int prow = pt & 63, pblk = pt >> 6;
-    const int kkb = nt * GW_NB + pblk;
-    const int pcc = kkb / g.K, ptap = kkb - pcc * g.K;
-    const int pdg = (grp * g.Cg + pcc * BK) / g.Cdg;
-    const bool active = pblk < nb;
-    // (sample, first position) of the block being fetched, advanced incrementally (no division per block)
-    int nb_b = pb0 / prm.pbi, nb_p0 = (pb0 - nb_b * prm.pbi) * 64;
-    auto coord = [&](RowCoord<ND>& rc) {
-      decode_row<ND>(g, nb_b, nb_p0 + prow, active && (nb_p0 + prow < g.P), rc);
-      nb_p0 += 64;
-      if (nb_p0 >= prm.pbi * 64) { nb_p0 = 0; ++nb_b; }
-    };
-    RowCoord<ND> rc_next;
-    RawSample<ND> raw_next;
-    if (pb0 < pb1) {
-      coord(rc_next);
-      if (rc_next.valid) raw_next = fetch_sample<T, ND, MOD>(g, off, mask, rc_next, pdg, ptap);
-    }
-    int ps = 0;
-    uint32_t pph = 0;
-    for (int pb = pb0; pb < pb1; ++pb) {
-      const RowCoord<ND> rc = rc_next;
-      const RawSample<ND> raw = raw_next;
-      if (pb + 1 < pb1) {
-        coord(rc_next);
+    {
+      const int team = warp < 8 ? 1 : 0;
+      const int pt = threadIdx.x & 127;
+      const T* __restrict__ off = reinterpret_cast<const T*>(prm.off);
+      const T* __restrict__ mask = reinterpret_cast<const T*>(prm.mask);
+      const int C8 = g.C >> 3;
+      const int prow = pt & 63, pblk = pt >> 6;
+      const int kkb = nt * GW_NB + pblk;
+      const int pcc = kkb / g.K, ptap = kkb - pcc * g.K;
+      const int pdg = (grp * g.Cg + pcc * BK) / g.Cdg;
+      const bool active = pblk < nb;
+      // thread (blk, row): the sampling plan of position p0 + row for this CTA's kk block `blk`; the
+      // offset / mask values of the team's NEXT position block are fetched while this one is built.
+      auto coord = [&](int pb, RowCoord<ND>& rc) {
+        const int b = pb / prm.pbi, p0 = (pb - b * prm.pbi) * 64;
+        decode_row<ND>(g, b, p0 + prow, active && (p0 + prow < g.P), rc);
+      };
+      RowCoord<ND> rc_next;
+      RawSample<ND> raw_next;
+      const int first = pb0 + team;
+      if (first < pb1) {
+        coord(first, rc_next);
         if (rc_next.valid) raw_next = fetch_sample<T, ND, MOD>(g, off, mask, rc_next, pdg, ptap);
       }
-      SamplePos<ND> sp;
-      sp.in_range = false;
-      if (rc.valid) build_pos<ND>(g, rc, ptap, raw, sp);
-      const PlanEntry<ND> e = plan_from_pos<T, ND>(g, rc, sp, C8);
-      ptx::mbar_wait_relaxed(&plan_empty[ps], pph ^ 1, 128);
-      store_plan<ND>(ptx::smem_u32(sPlan + ps * 128 + pt), e);
-      ptx::mbar_arrive(&plan_full[ps]);
-      if (++ps == GW_PLAN_SLOTS) { ps = 0; pph ^= 1; }
+      for (int pb = first; pb < pb1; pb += 2) {
+        const int it = pb - pb0;                      // iteration index -> ring slot and parity
+        const int ps = it % GW_PLAN_SLOTS;
+        const uint32_t pph = (uint32_t)(it / GW_PLAN_SLOTS) & 1u;
+        const RowCoord<ND> rc = rc_next;
+        const RawSample<ND> raw = raw_next;
+        if (pb + 2 < pb1) {
+          coord(pb + 2, rc_next);
+          if (rc_next.valid) raw_next = fetch_sample<T, ND, MOD>(g, off, mask, rc_next, pdg, ptap);
+        }
+        SamplePos<ND> sp;
+        sp.in_range = false;
+        if (rc.valid) build_pos<ND>(g, rc, ptap, raw, sp);
+        const PlanEntry<ND> e = plan_from_pos<T, ND>(g, rc, sp, C8);
+        ptx::mbar_wait_relaxed(&plan_empty[ps], pph ^ 1, 128);
+        store_plan<ND>(ptx::smem_u32(sPlan + ps * 128 + pt), e);
+        ptx::mbar_arrive(&plan_full[ps]);
+      }
+    }
+    if (warp < 8) {
+      // ---- epilogue: TMEM -> fp32 partial ----
+      const int ew = warp & 3;
+      ptx::mbar_wait_relaxed(done, 0, 1024);
+      ptx::tc_fence_after_sync();
+      const int N = nb * 64;
+      for (int mt = 0; mt < MT; ++mt) {
+        const int co = mp * 256 + mt * 128 + ew * 32 + lane;  // within the group
+        const bool valid = co < g.Cog;
+        float* dst = prm.part + ((size_t)split * g.Co + (size_t)grp * g.Cog + (valid ? co : 0)) * g.Kg +
+                     (size_t)nt * GW_NB * 64;
+        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(mt * 128);
+        for (int c0 = 0; c0 < N; c0 += 16) {
+          uint32_t v[16];
+          ptx::tmem_ld_32x16(taddr + c0, v);
+          ptx::tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              *reinterpret_cast<float4*>(dst + c0 + j) =
+                  make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                              __uint_as_float(v[j + 3]));
+          }
+        }
+      }
     }
   } else {
     // ===================== gather producers: column tiles =====================
