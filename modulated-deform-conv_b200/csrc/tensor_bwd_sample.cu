@@ -12,6 +12,10 @@
 // so neither gcol nor the columns exist in HBM, there are no atomics, and every output element is
 // written exactly once in a fixed summation order (deterministic).
 //
+// Work decomposition: one item = (tile of 128 positions, (deformable group, tap) phase); every phase writes its
+// own outputs, so the m_tiles * dg * K items are dealt to the persistent CTAs as equal contiguous ranges (a whole
+// number of tiles per CTA would leave the last wave 30 % full at cfg2: 784 tiles on 148 SMs).
+//
 //   warp 0       TMA producer: grad_output tile (MN-major A operand, straight from NCHW) and weight
 //                slices (MN-major B operand), 32 output channels per K-block -> 4-slot smem ring
 //   warp 1       MMA issuer, M=128 positions x N=64*nb channels of one tap, K = output channels
@@ -61,6 +65,7 @@ struct TcGsParams {
   int pbi;           // 64-position blocks per sample
   int total_pb;      // B * pbi
   int m_tiles;       // ceil(total_pb / 2)
+  long long items;   // m_tiles * dg * K (tile, phase) work items, split evenly over the CTAs
 };
 
 // dot product of two 8-element vectors stored in the tensor dtype
@@ -147,21 +152,31 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
   const int bpd = g.Cdg >> 6;            // 64-channel blocks per deformable group
   const int bpg = g.Cg >> 6;             // 64-channel blocks per conv group
   const int phases = g.dg * g.K;         // (deformable group, tap) phases per tile
+  // this CTA's contiguous range of (tile, phase) items; all roles walk it in the same order
+  const long long item0 = prm.items * blockIdx.x / gridDim.x;
+  const long long item1 = prm.items * (blockIdx.x + 1) / gridDim.x;
+  const int t_first = (int)(item0 / phases), phs_first = (int)(item0 - (long long)t_first * phases);
+  const int n_items = (int)(item1 - item0);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int t = blockIdx.x; t < prm.m_tiles; t += gridDim.x) {
-        int pb_b[2], pb_p0[2];
+      int t = t_first, phs = phs_first;
+      int pb_b[2] = {0, 0}, pb_p0[2] = {0, 0};
+      bool new_tile = true;
+      for (int it = 0; it < n_items; ++it) {
+        if (new_tile) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int pb = 2 * t + h;
-          pb_b[h] = pb < prm.total_pb ? pb / prm.pbi : g.B;  // b == B: fully out of bounds -> zero fill
-          pb_p0[h] = pb < prm.total_pb ? (pb % prm.pbi) * 64 : 0;
+          for (int h = 0; h < 2; ++h) {
+            const int pb = 2 * t + h;
+            pb_b[h] = pb < prm.total_pb ? pb / prm.pbi : g.B;  // b == B: fully out of bounds -> zero fill
+            pb_p0[h] = pb < prm.total_pb ? (pb % prm.pbi) * 64 : 0;
+          }
+          new_tile = false;
         }
-        for (int phs = 0; phs < phases; ++phs) {
+        {
           const int dgi = phs / g.K, tap = phs - dgi * g.K;
           for (int sub = 0; sub < nsub; ++sub) {
             const int blk0 = dgi * bpd + sub * nb;  // first 64-channel block (global numbering)
@@ -181,6 +196,7 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
             }
           }
         }
+        if (++phs == phases) { phs = 0; ++t; new_tile = true; }
       }
     }
   } else if (warp == 1) {
@@ -191,8 +207,8 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
       uint32_t ph = 0;
       int as = 0;
       uint32_t aph = 0;
-      for (int t = blockIdx.x; t < prm.m_tiles; t += gridDim.x) {
-        for (int st = 0; st < phases * nsub; ++st) {
+      {
+        for (int st = 0; st < n_items * nsub; ++st) {
           ptx::mbar_wait(&tmem_empty[as], aph ^ 1);
           ptx::tc_fence_after_sync();
           const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
@@ -224,13 +240,19 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
     const bool rule_b = g.rule != 0;
     int as = 0, ts = 0, ps = 0;
     uint32_t aph = 0, tph = 0, pph = 0;
-    for (int t = blockIdx.x; t < prm.m_tiles; t += gridDim.x) {
-      const int pb = 2 * t + (row >> 6);
-      const int p = (pb % prm.pbi) * 64 + (row & 63);
-      const bool valid = pb < prm.total_pb && p < g.P;
-      RowCoord<ND> rc;
-      decode_row<ND>(g, valid ? pb / prm.pbi : 0, p, valid, rc);
-      for (int phs = 0; phs < phases; ++phs) {
+    int t = t_first, phs = phs_first;
+    bool new_tile = true;
+    bool valid = false;
+    RowCoord<ND> rc;
+    for (int it = 0; it < n_items; ++it) {
+      if (new_tile) {
+        const int pb = 2 * t + (row >> 6);
+        const int p = (pb % prm.pbi) * 64 + (row & 63);
+        valid = pb < prm.total_pb && p < g.P;
+        decode_row<ND>(g, valid ? pb / prm.pbi : 0, p, valid, rc);
+        new_tile = false;
+      }
+      {
         const int dgi = phs / g.K, tap = phs - dgi * g.K;
         {
           // ---- sampling entry of (row, dgi, tap) ----
@@ -308,6 +330,7 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
           if (++as == 2) { as = 0; aph ^= 1; }
         }
       }
+      if (++phs == phases) { phs = 0; ++t; new_tile = true; }
     }
   } else if (warp >= GS_DOT_WARP0) {
     // ===================== dot warps =====================
@@ -320,8 +343,9 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
     T* __restrict__ gmask = reinterpret_cast<T*>(prm.gmask);
     int ts = 0, ps = 0;
     uint32_t tph = 0, pph = 0;
-    for (int t = blockIdx.x; t < prm.m_tiles; t += gridDim.x) {
-      for (int phs = 0; phs < phases; ++phs) {
+    int t = t_first, phs = phs_first;
+    for (int it = 0; it < n_items; ++it) {
+      {
         const int dgi = phs / g.K, tap = phs - dgi * g.K;
         ptx::mbar_wait(&plan_full[ps], pph);
         const uint32_t plan_addr = ptx::smem_u32(sPlan + ps * 128);
@@ -432,6 +456,7 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
         ptx::mbar_arrive(&plan_empty[ps]);
         if (++ps == 2) { ps = 0; pph ^= 1; }
       }
+      if (++phs == phases) { phs = 0; ++t; }
     }
   }
 
@@ -456,7 +481,7 @@ void launch_grad_sample(const CUtensorMap& tmap_go, const CUtensorMap& tmap_w, c
     if (e != cudaSuccess && ctx.err == cudaSuccess) ctx.err = e;
     configured = true;
   }
-  const int grid = prm.m_tiles < sm_count() ? prm.m_tiles : sm_count();
+  const int grid = prm.items < sm_count() ? (int)prm.items : sm_count();
   ProfScope prof(ctx, "tc_grad_sample");
   k_tc_grad_sample<T, ND, MOD><<<grid, GS_THREADS, smem, ctx.stream>>>(tmap_go, tmap_w, prm);
   MDCONV_CHECK_LAUNCH(ctx);
@@ -484,6 +509,7 @@ void tensor_grad_sample(const DevGeom& g, const T* xt, const T* wr, const void* 
   prm.pbi = (g.P + 63) / 64;
   prm.total_pb = g.B * prm.pbi;
   prm.m_tiles = (prm.total_pb + 1) / 2;
+  prm.items = (long long)prm.m_tiles * g.dg * g.K;
 
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) {

@@ -97,6 +97,40 @@ CASES_3D = [
 ]
 
 ALL_CASES = CASES_2D + CASES_3D
+
+# shapes the tcgen05 path accepts (channels per group / deformable group multiples of 64)
+TENSOR_CASES = [
+    Case("tc_m2d_c64", 2, True, B=2, C=64, Co=64, size=(12, 11), seed=50),
+    Case("tc_m2d_c128_co256_nobias", 2, True, B=3, C=128, Co=256, size=(8, 14), bias=False, seed=51),
+    Case("tc_m2d_stride2_dg2", 2, True, B=2, C=128, Co=128, size=(15, 13), s=(2, 2), dg=2, seed=52),
+    Case("tc_m2d_dil2_sigma4", 2, True, B=1, C=64, Co=64, size=(16, 16), p=(2, 2), d=(2, 2), sigma=4.0, seed=53),
+    Case("tc_m2d_integer_grid", 2, True, B=2, C=64, Co=64, size=(8, 9), sigma=0.0, seed=54),
+    Case("tc_m2d_half_grid", 2, True, B=2, C=64, Co=64, size=(8, 9), sigma=0.5, seed=55),
+    Case("tc_m2d_all_oob", 2, True, B=1, C=64, Co=64, size=(8, 8), offset_bias=1e4, seed=56),
+    Case("tc_m2d_g2", 2, True, B=2, C=128, Co=128, size=(10, 12), g=2, dg=2, seed=57),
+    Case("tc_d2d_c64", 2, False, B=2, C=64, Co=64, size=(12, 12), seed=60),
+    Case("tc_m2d_c256_multi_tile", 2, True, B=2, C=256, Co=256, size=(24, 20), bias=False, seed=63),
+    Case("tc_d2d_integer_grid", 2, False, B=2, C=64, Co=64, size=(8, 9), sigma=0.0, seed=61),
+    Case("tc_d2d_k1x3", 2, False, B=2, C=64, Co=64, size=(8, 9), k=(1, 3), p=(0, 1), seed=62),
+    Case("tc_m3d_c64", 3, True, B=1, C=64, Co=64, size=(4, 6, 5), k=(3, 3, 3), s=(1, 1, 1), p=(1, 1, 1),
+         d=(1, 1, 1), seed=70),
+    Case("tc_d3d_c64_half_grid", 3, False, B=1, C=64, Co=64, size=(4, 5, 6), k=(3, 3, 3), s=(1, 1, 1),
+         p=(1, 1, 1), d=(1, 1, 1), sigma=0.5, seed=71),
+    # deformable-group / group nesting of the backward kernels
+    Case("tc_m2d_dg4_c256", 2, True, B=2, C=256, Co=128, size=(8, 8), dg=4, seed=72),
+    Case("tc_m2d_g2_dg1", 2, True, B=2, C=128, Co=128, size=(8, 8), g=2, dg=1, seed=73),
+    Case("tc_m2d_g4_dg2", 2, True, B=1, C=256, Co=256, size=(8, 8), g=4, dg=2, seed=74),
+    Case("tc_d2d_c192_dg3", 2, False, B=2, C=192, Co=64, size=(8, 8), dg=3, seed=75),
+    Case("tc_m2d_c192_g3_dg1", 2, True, B=1, C=192, Co=192, size=(8, 8), g=3, dg=1, seed=76),
+    # Cog = 32: forward + grad_offset/grad_mask on tensor cores, grad_input falls back
+    Case("tc_m2d_co32", 2, True, B=2, C=64, Co=32, size=(8, 8), seed=77),
+    # ragged tails: B*P not a multiple of the 128-row tile, P not a multiple of 64
+    Case("tc_m2d_ragged", 2, True, B=3, C=64, Co=64, size=(10, 12), seed=78),
+    Case("tc_m2d_sigma8", 2, True, B=1, C=64, Co=64, size=(16, 16), sigma=8.0, seed=79),
+    Case("tc_m3d_dg2_stride2", 3, True, B=1, C=128, Co=64, size=(6, 8, 8), k=(3, 3, 3), s=(2, 2, 2), p=(1, 1, 1),
+         d=(1, 1, 1), dg=2, seed=80),
+]
+
 GENERIC_OFFSET_CASES = [c for c in ALL_CASES if c.sigma not in (0.0, 0.5)]
 
 
