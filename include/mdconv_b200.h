@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define MDCONV_B200_ABI_VERSION 1
+#define MDCONV_B200_ABI_VERSION 2
 
 enum mdconv_dtype { MDCONV_F32 = 0, MDCONV_F16 = 1, MDCONV_BF16 = 2, MDCONV_F64 = 3 };
 
@@ -133,6 +133,18 @@ int mdconv_backward(const mdconv_geom_t* g, const void* input, const void* weigh
                     const void* mask, const void* grad_output, void* grad_input, void* grad_weight,
                     void* grad_bias, void* grad_offset, void* grad_mask, void* workspace,
                     size_t workspace_bytes, void* stream);
+
+/* Forward -> backward hand-off of the internal layouts (ABI version 2).  The reference recomputes everything
+ * in its backward (it re-runs the im2col gather, src/mdeformable_conv.cu:421-433); here the tcgen05 path's
+ * forward leaves the channels-last input and the re-ordered weight in the first mdconv_saved_bytes() bytes of
+ * ITS workspace.  A caller that keeps that workspace untouched until the matching backward (same input, weight
+ * and geometry) passes it as `saved` and the backward skips both layout passes.  mdconv_saved_bytes() is 0
+ * when either direction would not run on the tensor path; saved == NULL is mdconv_backward(). */
+size_t mdconv_saved_bytes(const mdconv_geom_t* g);
+int mdconv_backward_saved(const mdconv_geom_t* g, const void* input, const void* weight, const void* offset,
+                          const void* mask, const void* grad_output, void* grad_input, void* grad_weight,
+                          void* grad_bias, void* grad_offset, void* grad_mask, void* workspace,
+                          size_t workspace_bytes, const void* saved, size_t saved_bytes, void* stream);
 
 /* ---- The reference's eight entry points, C ABI form --------------------------------------
  * Argument order follows the reference signatures; tensor handles become device pointers and the

@@ -56,6 +56,10 @@ _lib.mdconv_forward.restype = _i
 _lib.mdconv_forward.argtypes = [ctypes.POINTER(_Geom)] + [_vp] * 7 + [_sz, _vp]
 _lib.mdconv_backward.restype = _i
 _lib.mdconv_backward.argtypes = [ctypes.POINTER(_Geom)] + [_vp] * 11 + [_sz, _vp]
+_lib.mdconv_saved_bytes.restype = _sz
+_lib.mdconv_saved_bytes.argtypes = [ctypes.POINTER(_Geom)]
+_lib.mdconv_backward_saved.restype = _i
+_lib.mdconv_backward_saved.argtypes = [ctypes.POINTER(_Geom)] + [_vp] * 11 + [_sz, _vp, _sz, _vp]
 
 _TAIL = [_i, _vp, _sz, _vp]  # dtype, workspace, workspace_bytes, stream
 _G2 = [_i] * 17              # batch, channels, H, W, Cout, kh,kw, sh,sw, ph,pw, dh,dw, g, dg, in_step, with_bias
@@ -72,7 +76,7 @@ for _name, _nptr, _geo in (("deform_conv2d_forward_cuda", 5, _G2), ("deform_conv
 _lib.mdconv_legacy_workspace_bytes.restype = _sz
 _lib.mdconv_legacy_workspace_bytes.argtypes = [_i] * 25
 
-if _lib.mdconv_abi_version() != 1:
+if _lib.mdconv_abi_version() != 2:
     raise ImportError("MDCONV_CUDA: libmdconv_b200.so ABI version mismatch")
 
 _DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2, torch.float64: 3}
@@ -201,7 +205,22 @@ def _workspace(g, backward, device):
     return torch.empty(n, dtype=torch.uint8, device=device), n
 
 
-def _forward(input, weight, bias, offset, mask, output, kernel, stride, pad, dil, group, dgroup, with_bias):
+# Forward -> backward hand-off of the internal layouts (mdconv_saved_bytes / mdconv_backward_saved): the autograd
+# Functions of modulated_deform_conv.py keep the forward's workspace alive in their ctx and give it back to the
+# backward, which then skips the channels-last / weight re-order passes.  Costs the workspace's memory between
+# the two calls; MDCONV_B200_KEEP_LAYOUTS=0 (or set_keep_layouts(False)) turns it off.
+_keep_layouts = os.environ.get("MDCONV_B200_KEEP_LAYOUTS", "1") != "0"
+
+
+def set_keep_layouts(on: bool) -> None:
+    global _keep_layouts
+    _keep_layouts = bool(on)
+
+
+def _forward(input, weight, bias, offset, mask, output, kernel, stride, pad, dil, group, dgroup, with_bias,
+             keep=False):
+    """-> output, or (output, saved) when ``keep``: ``saved`` is the workspace tensor whose head holds the
+    layouts the matching backward can reuse (None when the tensor path does not run both directions)."""
     nd = len(kernel)
     modulated = mask is not None
     named = [("input", input), ("weight", weight), ("bias", bias), ("offset", offset)]
@@ -230,12 +249,16 @@ def _forward(input, weight, bias, offset, mask, output, kernel, stride, pad, dil
         rc = _lib.mdconv_forward(ctypes.byref(g), _ptr(input), _ptr(weight), _ptr(bias) if with_bias else None,
                                  _ptr(offset), _ptr(mask), _ptr(output), _ptr(ws), n, ctypes.c_void_p(stream))
     _check(rc, "mdconv_forward")
+    if keep:
+        nsave = int(_lib.mdconv_saved_bytes(ctypes.byref(g))) if (_keep_layouts and ws is not None) else 0
+        return output, ((ws, nsave, g.path) if nsave > 0 else None)
     return output
 
 
 def _backward(input, weight, bias, offset, mask, grad_output, grads, kernel, stride, pad, dil, group, dgroup,
-              with_bias):
-    """grads: None (allocate and return) or dict of caller-owned tensors (out-param style)."""
+              with_bias, saved=None):
+    """grads: None (allocate and return) or dict of caller-owned tensors (out-param style).
+    saved: what ``_forward(..., keep=True)`` returned for the same input / weight / geometry, or None."""
     nd = len(kernel)
     modulated = mask is not None
     named = [("input", input), ("weight", weight), ("bias", bias), ("offset", offset)]
@@ -261,13 +284,32 @@ def _backward(input, weight, bias, offset, mask, grad_output, grads, kernel, str
                 _expect(grads["grad_mask"], mask.shape, "grad_mask")
         ws, n = _workspace(g, True, input.device)
         stream = torch.cuda.current_stream().cuda_stream
-        rc = _lib.mdconv_backward(ctypes.byref(g), _ptr(input), _ptr(weight), _ptr(offset), _ptr(mask),
-                                  _ptr(grad_output), _ptr(grads["grad_input"]), _ptr(grads["grad_weight"]),
-                                  _ptr(grads["grad_bias"]) if with_bias else None, _ptr(grads["grad_offset"]),
-                                  _ptr(grads.get("grad_mask")) if modulated else None, _ptr(ws), n,
-                                  ctypes.c_void_p(stream))
+        sv_ptr, sv_n = None, 0
+        if saved is not None and saved[2] == g.path and saved[0].device == input.device and \
+                int(_lib.mdconv_saved_bytes(ctypes.byref(g))) == saved[1]:
+            sv_ptr, sv_n = _ptr(saved[0]), saved[1]
+        rc = _lib.mdconv_backward_saved(ctypes.byref(g), _ptr(input), _ptr(weight), _ptr(offset), _ptr(mask),
+                                        _ptr(grad_output), _ptr(grads["grad_input"]), _ptr(grads["grad_weight"]),
+                                        _ptr(grads["grad_bias"]) if with_bias else None, _ptr(grads["grad_offset"]),
+                                        _ptr(grads.get("grad_mask")) if modulated else None, _ptr(ws), n,
+                                        sv_ptr, sv_n, ctypes.c_void_p(stream))
     _check(rc, "mdconv_backward")
     return grads
+
+
+def forward_ex(input, weight, bias, offset, mask, output, kernel, stride, pad, dil, group, deformable_group,
+               with_bias, keep=False):
+    """Generic form of the four forwards (mask None = plain op; output None = allocate).  With ``keep`` it
+    returns (output, saved) for ``backward_ex``; used by the autograd Functions."""
+    return _forward(input, weight, bias, offset, mask, output, tuple(kernel), tuple(stride), tuple(pad), tuple(dil),
+                    group, deformable_group, with_bias, keep=keep)
+
+
+def backward_ex(input, weight, bias, offset, mask, grad_output, kernel, stride, pad, dil, group, deformable_group,
+                with_bias, saved=None):
+    """Generic form of the four backwards -> dict grad_input / grad_offset / grad_mask / grad_weight / grad_bias."""
+    return _backward(input, weight, bias, offset, mask, grad_output, None, tuple(kernel), tuple(stride), tuple(pad),
+                     tuple(dil), group, deformable_group, with_bias, saved=saved)
 
 
 # ---- the eight reference entry points ------------------------------------------------------------

@@ -214,9 +214,24 @@ int mdconv_forward(const mdconv_geom_t* gi, const void* input, const void* weigh
   return finish(ctx);
 }
 
+size_t mdconv_saved_bytes(const mdconv_geom_t* gi) {
+  DevGeom g;
+  if (resolve(gi, g) != MDCONV_OK) return 0;
+  if (pick_path(gi, g, 0) != MDCONV_PATH_TENSOR || pick_path(gi, g, 1) != MDCONV_PATH_TENSOR) return 0;
+  return tensor_saved_bytes(g, gi->dtype);
+}
+
 int mdconv_backward(const mdconv_geom_t* gi, const void* input, const void* weight, const void* offset,
                     const void* mask, const void* grad_output, void* grad_input, void* grad_weight, void* grad_bias,
                     void* grad_offset, void* grad_mask, void* workspace, size_t workspace_bytes, void* stream) {
+  return mdconv_backward_saved(gi, input, weight, offset, mask, grad_output, grad_input, grad_weight, grad_bias,
+                               grad_offset, grad_mask, workspace, workspace_bytes, nullptr, 0, stream);
+}
+
+int mdconv_backward_saved(const mdconv_geom_t* gi, const void* input, const void* weight, const void* offset,
+                          const void* mask, const void* grad_output, void* grad_input, void* grad_weight,
+                          void* grad_bias, void* grad_offset, void* grad_mask, void* workspace, size_t workspace_bytes,
+                          const void* saved, size_t saved_bytes, void* stream) {
   DevGeom g;
   int rc = resolve(gi, g);
   if (rc != MDCONV_OK) return rc;
@@ -232,9 +247,14 @@ int mdconv_backward(const mdconv_geom_t* gi, const void* input, const void* weig
     return MDCONV_ERR_WORKSPACE;
   LaunchCtx ctx{(cudaStream_t)stream, 0, cudaSuccess};
   (void)cudaGetLastError();
+  if (saved != nullptr) {
+    // only meaningful when both directions run on the tensor path; anything else is a caller error
+    const size_t want = mdconv_saved_bytes(gi);
+    if (want == 0 || saved_bytes < want || ((uintptr_t)saved & 255)) return MDCONV_ERR_WORKSPACE;
+  }
   if (path == MDCONV_PATH_TENSOR)
     tensor_backward(g, gi->dtype, input, weight, offset, mask, grad_output, grad_input, grad_weight, grad_bias,
-                    grad_offset, grad_mask, workspace, ctx);
+                    grad_offset, grad_mask, workspace, saved, ctx);
   else
     generic_backward(g, gi->dtype, input, weight, offset, mask, grad_output, grad_input, grad_weight, grad_bias,
                      grad_offset, grad_mask, workspace, ctx);

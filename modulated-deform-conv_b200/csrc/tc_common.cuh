@@ -261,7 +261,8 @@ void set_side_stream_enabled(bool on);
 // backward kernels (tensor_bwd.cu)
 template <typename T>
 void tensor_backward_t(const DevGeom& g, const void* x, const void* w, const void* off, const void* mask,
-                       const void* go, void* gx, void* gw, void* gb, void* goff, void* gmask, void* ws, LaunchCtx& ctx);
+                       const void* go, void* gx, void* gw, void* gb, void* goff, void* gmask, void* ws, const void* saved,
+                       LaunchCtx& ctx);
 size_t tensor_backward_workspace(const DevGeom& g);
 bool tensor_backward_supported(const DevGeom& g, int dtype);
 

@@ -377,12 +377,18 @@ size_t tensor_backward_workspace(const DevGeom& g) {
 
 template <typename T>
 void tensor_backward_t(const DevGeom& g, const void* x, const void* w, const void* off, const void* mask,
-                       const void* go, void* gx, void* gw, void* gb, void* goff, void* gmask, void* ws, LaunchCtx& ctx) {
+                       const void* go, void* gx, void* gw, void* gb, void* goff, void* gmask, void* ws, const void* saved,
+                       LaunchCtx& ctx) {
   char* base = reinterpret_cast<char*>(ws);
-  T* xt = reinterpret_cast<T*>(base);
+  const T* xt = reinterpret_cast<const T*>(base);
   base += align256((size_t)g.B * g.C * g.IN * sizeof(T));
-  T* wr = reinterpret_cast<T*>(base);
+  const T* wr = reinterpret_cast<const T*>(base);
   base += align256((size_t)g.Co * g.Kg * sizeof(T));
+  if (saved != nullptr) {
+    // the forward of this very call pair left both layouts in its workspace (same offsets: tensor_forward_t)
+    xt = reinterpret_cast<const T*>(saved);
+    wr = reinterpret_cast<const T*>(reinterpret_cast<const char*>(saved) + align256((size_t)g.B * g.C * g.IN * sizeof(T)));
+  }
   const int S = gw_splits(g);
   float* part = reinterpret_cast<float*>(base);
   base += align256((size_t)S * g.Co * g.Kg * sizeof(float));
@@ -393,8 +399,10 @@ void tensor_backward_t(const DevGeom& g, const void* x, const void* w, const voi
   // the inverse index of grad_input only needs offset/mask: build it on the side stream, beside the
   // layout passes and ahead of the big kernels
   if (data_tc) tensor_grad_input_prepare<T>(g, off, mask, data_ws, ctx);
-  launch_to_channels_last<T>((const T*)x, xt, g.B, g.C, g.IN, ctx);
-  if (data_tc) launch_reorder_weight<T>((const T*)w, wr, g.Co, g.Cg, g.K, ctx);
+  if (saved == nullptr) {
+    launch_to_channels_last<T>((const T*)x, const_cast<T*>(xt), g.B, g.C, g.IN, ctx);
+    if (data_tc) launch_reorder_weight<T>((const T*)w, const_cast<T*>(wr), g.Co, g.Cg, g.K, ctx);
+  }
 
   // ---- grad_weight first (it is what a data-parallel caller all-reduces) ----
   TcGwParams prm;
@@ -452,9 +460,10 @@ void tensor_backward_t(const DevGeom& g, const void* x, const void* w, const voi
 }
 
 template void tensor_backward_t<__half>(const DevGeom&, const void*, const void*, const void*, const void*,
-                                        const void*, void*, void*, void*, void*, void*, void*, LaunchCtx&);
+                                        const void*, void*, void*, void*, void*, void*, void*, const void*, LaunchCtx&);
 template void tensor_backward_t<__nv_bfloat16>(const DevGeom&, const void*, const void*, const void*, const void*,
-                                               const void*, void*, void*, void*, void*, void*, void*, LaunchCtx&);
+                                               const void*, void*, void*, void*, void*, void*, void*, const void*,
+                                               LaunchCtx&);
 
 }  // namespace tc
 }  // namespace mdconv

@@ -636,9 +636,16 @@ void tensor_forward(const DevGeom& g, int dtype, const void* x, const void* w, c
 }
 
 void tensor_backward(const DevGeom& g, int dtype, const void* x, const void* w, const void* off, const void* mask,
-                     const void* go, void* gx, void* gw, void* gb, void* goff, void* gmask, void* ws, LaunchCtx& ctx) {
-  if (dtype == MDCONV_F16) tc::tensor_backward_t<__half>(g, x, w, off, mask, go, gx, gw, gb, goff, gmask, ws, ctx);
-  else tc::tensor_backward_t<__nv_bfloat16>(g, x, w, off, mask, go, gx, gw, gb, goff, gmask, ws, ctx);
+                     const void* go, void* gx, void* gw, void* gb, void* goff, void* gmask, void* ws, const void* saved,
+                     LaunchCtx& ctx) {
+  if (dtype == MDCONV_F16) tc::tensor_backward_t<__half>(g, x, w, off, mask, go, gx, gw, gb, goff, gmask, ws, saved, ctx);
+  else tc::tensor_backward_t<__nv_bfloat16>(g, x, w, off, mask, go, gx, gw, gb, goff, gmask, ws, saved, ctx);
+}
+
+// forward workspace prefix the backward can reuse: [channels-last input | re-ordered weight]
+size_t tensor_saved_bytes(const DevGeom& g, int dtype) {
+  (void)dtype;
+  return align256((size_t)g.B * g.C * g.IN * 2) + align256((size_t)g.Co * g.Kg * 2);
 }
 
 }  // namespace mdconv

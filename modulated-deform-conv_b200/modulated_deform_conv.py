@@ -65,17 +65,36 @@ def _needs_grad(*tensors):
     return any(t is not None and t.requires_grad for t in tensors)
 
 
+# The Functions below go through MDCONV_CUDA.forward_ex / backward_ex -- the same C entry points the eight
+# reference-named functions bind (MDCONV_CUDA.*_forward_cuda / *_backward_cuda stay available and equivalent) --
+# because that form can hand the forward's internal layouts (channels-last input, re-ordered weight) to the
+# backward through ctx, which the reference's positional signatures (:28-34, :57-64) have no slot for.
+def _forward_op(ctx, input, weight, bias, offset, mask, keep):
+    out = MDCONV_CUDA.forward_ex(input, weight, bias, offset, mask, None, weight.shape[2:], ctx.stride, ctx.padding,
+                                 ctx.dilation, ctx.groups, ctx.deformable_groups, ctx.with_bias, keep=keep)
+    if keep:
+        out, ctx.layouts = out
+    return out
+
+
+def _backward_op(ctx, input, weight, bias, offset, mask, grad_output):
+    g = MDCONV_CUDA.backward_ex(input, weight, bias, offset, mask, grad_output, weight.shape[2:], ctx.stride,
+                                ctx.padding, ctx.dilation, ctx.groups, ctx.deformable_groups, ctx.with_bias,
+                                saved=getattr(ctx, "layouts", None))
+    ctx.layouts = None
+    return g
+
+
 class DeformConv2dFunction(Function):
     @staticmethod
     def forward(ctx, input, offset, weight, bias=None, stride=1, padding=0, dilation=1,
                 groups=1, deformable_groups=1, in_step=64):
         with_bias_tensor = bias
         bias = _setup(ctx, _pair, input, bias, stride, padding, dilation, groups, deformable_groups, in_step)
-        if _needs_grad(input, offset, weight, with_bias_tensor):
+        keep = _needs_grad(input, offset, weight, with_bias_tensor)
+        if keep:
             ctx.save_for_backward(input, offset, weight, bias)
-        output = input.new_empty(_infer_shape(input, weight, ctx.stride, ctx.padding, ctx.dilation))
-        MDCONV_CUDA.deform_conv2d_forward_cuda(input, weight, bias, offset, output, *_geometry_args(ctx, weight))
-        return output
+        return _forward_op(ctx, input, weight, bias, offset, None, keep)
 
     @staticmethod
     @once_differentiable
@@ -84,16 +103,9 @@ class DeformConv2dFunction(Function):
         if not grad_output.is_cuda:
             raise NotImplementedError
         input, offset, weight, bias = ctx.saved_tensors
-        grad_input = torch.empty_like(input)
-        grad_offset = torch.empty_like(offset)
-        grad_weight = torch.empty_like(weight)
-        grad_bias = torch.empty_like(bias)
-        MDCONV_CUDA.deform_conv2d_backward_cuda(
-            input, weight, bias, offset, grad_input, grad_weight, grad_bias, grad_offset, grad_output,
-            *_geometry_args(ctx, weight))
-        if not ctx.with_bias:
-            grad_bias = None
-        return grad_input, grad_offset, grad_weight, grad_bias, None, None, None, None, None, None
+        g = _backward_op(ctx, input, weight, bias, offset, None, grad_output)
+        return (g["grad_input"], g["grad_offset"], g["grad_weight"], g["grad_bias"] if ctx.with_bias else None,
+                None, None, None, None, None, None)
 
 
 class ModulatedDeformConv2dFunction(Function):
@@ -102,10 +114,10 @@ class ModulatedDeformConv2dFunction(Function):
                 groups=1, deformable_groups=1, in_step=64):
         with_bias_tensor = bias
         bias = _setup(ctx, _pair, input, bias, stride, padding, dilation, groups, deformable_groups, in_step)
-        if _needs_grad(input, offset, mask, weight, with_bias_tensor):
+        keep = _needs_grad(input, offset, mask, weight, with_bias_tensor)
+        if keep:
             ctx.save_for_backward(input, offset, mask, weight, bias)
-        return MDCONV_CUDA.modulated_deform_conv2d_forward_cuda(
-            input, weight, bias, offset, mask, *_geometry_args(ctx, weight))
+        return _forward_op(ctx, input, weight, bias, offset, mask, keep)
 
     @staticmethod
     @once_differentiable
@@ -114,12 +126,9 @@ class ModulatedDeformConv2dFunction(Function):
         if not grad_output.is_cuda:
             raise NotImplementedError
         input, offset, mask, weight, bias = ctx.saved_tensors
-        grad_input, grad_offset, grad_mask, grad_weight, grad_bias = \
-            MDCONV_CUDA.modulated_deform_conv2d_backward_cuda(
-                input, weight, bias, offset, mask, grad_output, *_geometry_args(ctx, weight))
-        if not ctx.with_bias:
-            grad_bias = None
-        return grad_input, grad_offset, grad_mask, grad_weight, grad_bias, None, None, None, None, None, None
+        g = _backward_op(ctx, input, weight, bias, offset, mask, grad_output)
+        return (g["grad_input"], g["grad_offset"], g["grad_mask"], g["grad_weight"],
+                g["grad_bias"] if ctx.with_bias else None, None, None, None, None, None, None)
 
 
 class DeformConv3dFunction(Function):
@@ -128,11 +137,10 @@ class DeformConv3dFunction(Function):
                 groups=1, deformable_groups=1, in_step=64):
         with_bias_tensor = bias
         bias = _setup(ctx, _triple, input, bias, stride, padding, dilation, groups, deformable_groups, in_step)
-        if _needs_grad(input, offset, weight, with_bias_tensor):
+        keep = _needs_grad(input, offset, weight, with_bias_tensor)
+        if keep:
             ctx.save_for_backward(input, offset, weight, bias)
-        output = input.new_empty(_infer_shape(input, weight, ctx.stride, ctx.padding, ctx.dilation))
-        MDCONV_CUDA.deform_conv3d_forward_cuda(input, weight, bias, offset, output, *_geometry_args(ctx, weight))
-        return output
+        return _forward_op(ctx, input, weight, bias, offset, None, keep)
 
     @staticmethod
     @once_differentiable
@@ -141,16 +149,9 @@ class DeformConv3dFunction(Function):
         if not grad_output.is_cuda:
             raise NotImplementedError
         input, offset, weight, bias = ctx.saved_tensors
-        grad_input = torch.empty_like(input)
-        grad_offset = torch.empty_like(offset)
-        grad_weight = torch.empty_like(weight)
-        grad_bias = torch.empty_like(bias)
-        MDCONV_CUDA.deform_conv3d_backward_cuda(
-            input, weight, bias, offset, grad_input, grad_weight, grad_bias, grad_offset, grad_output,
-            *_geometry_args(ctx, weight))
-        if not ctx.with_bias:
-            grad_bias = None
-        return grad_input, grad_offset, grad_weight, grad_bias, None, None, None, None, None, None
+        g = _backward_op(ctx, input, weight, bias, offset, None, grad_output)
+        return (g["grad_input"], g["grad_offset"], g["grad_weight"], g["grad_bias"] if ctx.with_bias else None,
+                None, None, None, None, None, None)
 
 
 class ModulatedDeformConv3dFunction(Function):
@@ -159,12 +160,10 @@ class ModulatedDeformConv3dFunction(Function):
                 groups=1, deformable_groups=1, in_step=64):
         with_bias_tensor = bias
         bias = _setup(ctx, _triple, input, bias, stride, padding, dilation, groups, deformable_groups, in_step)
-        if _needs_grad(input, offset, mask, weight, with_bias_tensor):
+        keep = _needs_grad(input, offset, mask, weight, with_bias_tensor)
+        if keep:
             ctx.save_for_backward(input, offset, mask, weight, bias)
-        output = input.new_empty(_infer_shape(input, weight, ctx.stride, ctx.padding, ctx.dilation))
-        MDCONV_CUDA.modulated_deform_conv3d_forward_cuda(
-            input, weight, bias, offset, mask, output, *_geometry_args(ctx, weight))
-        return output
+        return _forward_op(ctx, input, weight, bias, offset, mask, keep)
 
     @staticmethod
     @once_differentiable
@@ -173,17 +172,9 @@ class ModulatedDeformConv3dFunction(Function):
         if not grad_output.is_cuda:
             raise NotImplementedError
         input, offset, mask, weight, bias = ctx.saved_tensors
-        grad_input = torch.empty_like(input)
-        grad_offset = torch.empty_like(offset)
-        grad_mask = torch.empty_like(mask)
-        grad_weight = torch.empty_like(weight)
-        grad_bias = torch.empty_like(bias)
-        MDCONV_CUDA.modulated_deform_conv3d_backward_cuda(
-            input, weight, bias, offset, mask, grad_input, grad_weight, grad_bias, grad_offset, grad_mask,
-            grad_output, *_geometry_args(ctx, weight))
-        if not ctx.with_bias:
-            grad_bias = None
-        return grad_input, grad_offset, grad_mask, grad_weight, grad_bias, None, None, None, None, None, None
+        g = _backward_op(ctx, input, weight, bias, offset, mask, grad_output)
+        return (g["grad_input"], g["grad_offset"], g["grad_mask"], g["grad_weight"],
+                g["grad_bias"] if ctx.with_bias else None, None, None, None, None, None, None)
 
 
 deform_conv2d = DeformConv2dFunction.apply

@@ -205,6 +205,39 @@ def test_tensor_path_matches_oracle(case, dtype):
     _compare(ours, _oracle(case, t), TOL[dtype], f"{case.name}/{dtype} (bwd path {bwd})")
 
 
+def test_saved_layouts_hand_off_is_bit_identical_and_skips_two_passes():
+    """Forward -> backward hand-off of the channels-last input / re-ordered weight (mdconv_backward_saved): same
+    bits as the stateless backward, two launches fewer; the legacy-named stateless entry points stay equivalent."""
+    import MDCONV_CUDA
+    case = {c.name: c for c in TENSOR_CASES}["tc_m2d_c256_multi_tile"]
+    t = make_inputs(case, torch.float16)
+    res, launches = {}, {}
+    for keep in (True, False):
+        MDCONV_CUDA.set_keep_layouts(keep)
+        try:
+            n0 = MDCONV_CUDA.total_launch_count()
+            res[keep] = _run_ours(case, t, fwd_path=2, bwd_path=2)
+            launches[keep] = MDCONV_CUDA.total_launch_count() - n0
+        finally:
+            MDCONV_CUDA.set_keep_layouts(True)
+            MDCONV_CUDA.set_path(0)
+    for k in res[True]:
+        assert np.array_equal(res[True][k], res[False][k]), k
+    assert launches[False] - launches[True] == 2, launches
+    # the reference-named stateless pair on the same tensors
+    d = {k: (v.cuda() if v is not None else None) for k, v in t.items()}
+    y = MDCONV_CUDA.modulated_deform_conv2d_forward_cuda(d["x"], d["weight"], d["x"].new_empty(0), d["offset"],
+                                                         d["mask"], *case.k, *case.s, *case.p, *case.d, case.g,
+                                                         case.dg, 64, False)
+    g = MDCONV_CUDA.modulated_deform_conv2d_backward_cuda(d["x"], d["weight"], d["x"].new_empty(0), d["offset"],
+                                                          d["mask"], d["grad_output"], *case.k, *case.s, *case.p,
+                                                          *case.d, case.g, case.dg, 64, False)
+    torch.cuda.synchronize()
+    assert np.array_equal(y.double().cpu().numpy(), res[True]["y"])
+    assert np.array_equal(g[0].double().cpu().numpy(), res[True]["grad_input"])
+    assert np.array_equal(g[3].double().cpu().numpy(), res[True]["grad_weight"])
+
+
 def test_results_do_not_depend_on_in_step():
     import modulated_deform_conv as mdc
     case = ALL_CASES[1]
