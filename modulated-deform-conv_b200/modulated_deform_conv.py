@@ -177,10 +177,44 @@ class ModulatedDeformConv3dFunction(Function):
                 g["grad_bias"] if ctx.with_bias else None, None, None, None, None, None, None)
 
 
-deform_conv2d = DeformConv2dFunction.apply
-modulated_deform_conv2d = ModulatedDeformConv2dFunction.apply
-deform_conv3d = DeformConv3dFunction.apply
-modulated_deform_conv3d = ModulatedDeformConv3dFunction.apply
+def _amp(*tensors):
+    """Under ``torch.autocast('cuda')`` the op runs in the autocast dtype like the convolutions around it
+    (the reference has no custom_fwd/custom_bwd, so mixed fp32 offsets / fp16 activations hit its
+    same-dtype check).  The casts are ordinary differentiable ``.to()`` calls; outside autocast nothing changes."""
+    if not torch.is_autocast_enabled("cuda"):
+        return tensors
+    dt = torch.get_autocast_dtype("cuda")
+    return tuple(t if (t is None or not t.is_floating_point() or t.dtype == dt) else t.to(dt) for t in tensors)
+
+
+# The reference binds these four names to ``Function.apply`` (modulated_deform_conv.py:349-352); same call
+# signatures here, plus the autocast handling above.
+def deform_conv2d(input, offset, weight, bias=None, stride=1, padding=0, dilation=1, groups=1,
+                  deformable_groups=1, in_step=64):
+    input, offset, weight, bias = _amp(input, offset, weight, bias)
+    return DeformConv2dFunction.apply(input, offset, weight, bias, stride, padding, dilation, groups,
+                                      deformable_groups, in_step)
+
+
+def modulated_deform_conv2d(input, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1, groups=1,
+                            deformable_groups=1, in_step=64):
+    input, offset, mask, weight, bias = _amp(input, offset, mask, weight, bias)
+    return ModulatedDeformConv2dFunction.apply(input, offset, mask, weight, bias, stride, padding, dilation, groups,
+                                               deformable_groups, in_step)
+
+
+def deform_conv3d(input, offset, weight, bias=None, stride=1, padding=0, dilation=1, groups=1,
+                  deformable_groups=1, in_step=64):
+    input, offset, weight, bias = _amp(input, offset, weight, bias)
+    return DeformConv3dFunction.apply(input, offset, weight, bias, stride, padding, dilation, groups,
+                                      deformable_groups, in_step)
+
+
+def modulated_deform_conv3d(input, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1, groups=1,
+                            deformable_groups=1, in_step=64):
+    input, offset, mask, weight, bias = _amp(input, offset, mask, weight, bias)
+    return ModulatedDeformConv3dFunction.apply(input, offset, mask, weight, bias, stride, padding, dilation, groups,
+                                               deformable_groups, in_step)
 
 
 class _DeformConvNd(nn.Module):
@@ -275,6 +309,16 @@ def _make_producer(mod, channels_per_tap):
     return conv
 
 
+def _offset_and_mask(mod, x):
+    """conv_offset(x), conv_mask(x) of a modulated Pack as ONE convolution launch over the concatenated filters
+    (x is read once; parameters and state-dict keys stay the reference's two separate convs)."""
+    co, cm = mod.conv_offset, mod.conv_mask
+    f = torch.nn.functional.conv2d if x.dim() == 4 else torch.nn.functional.conv3d
+    both = f(x, torch.cat([co.weight, cm.weight], 0), torch.cat([co.bias, cm.bias], 0), co.stride, co.padding)
+    n = co.out_channels
+    return both[:, :n].contiguous(), both[:, n:].contiguous()
+
+
 class DeformConv2dPack(DeformConv2d):
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
@@ -292,7 +336,8 @@ class ModulatedDeformConv2dPack(ModulatedDeformConv2d):
 
     def forward(self, x):
         # as in the reference the mask is the raw conv output (no sigmoid), :781-785
-        return modulated_deform_conv2d(x, self.conv_offset(x), self.conv_mask(x), *self._conv_args())
+        offset, mask = _offset_and_mask(self, x)
+        return modulated_deform_conv2d(x, offset, mask, *self._conv_args())
 
 
 class DeformConv3dPack(DeformConv3d):
@@ -311,4 +356,5 @@ class ModulatedDeformConv3dPack(ModulatedDeformConv3d):
         self.conv_mask = _make_producer(self, 1)
 
     def forward(self, x):
-        return modulated_deform_conv3d(x, self.conv_offset(x), self.conv_mask(x), *self._conv_args())
+        offset, mask = _offset_and_mask(self, x)
+        return modulated_deform_conv3d(x, offset, mask, *self._conv_args())

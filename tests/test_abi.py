@@ -92,6 +92,32 @@ def test_python_surface_matches_reference_names():
             torch.ones(1, 9, 5, 5), 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 64, False)
 
 
+def test_dispatcher_ops_trace_with_fake_tensors():
+    """torch.library registration (mdconv_ops): shapes / dtypes propagate through FakeTensorMode without touching
+    a GPU, for the four op kinds; CPU tensors are refused (no CPU path)."""
+    import mdconv_ops  # noqa: F401
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    with FakeTensorMode():
+        for nd, modulated in ((2, True), (2, False), (3, True), (3, False)):
+            sp = (10, 12) if nd == 2 else (4, 6, 5)
+            K = 3 ** nd
+            x = torch.empty(2, 64, *sp, dtype=torch.float16, device="cuda")
+            w = torch.empty(32, 32, *([3] * nd), dtype=torch.float16, device="cuda")
+            b = torch.empty(32, dtype=torch.float16, device="cuda")
+            out_sp = tuple((i + 2 - 3) // 2 + 1 for i in sp)
+            off = torch.empty(2, 2 * nd * K, *out_sp, dtype=torch.float16, device="cuda")
+            m = torch.empty(2, 2 * K, *out_sp, dtype=torch.float16, device="cuda") if modulated else None
+            geo = ([2] * nd, [1] * nd, [1] * nd, 2, 2)
+            y = torch.ops.mdconv_b200.deform_conv(x, w, b, off, m, *geo)
+            assert tuple(y.shape) == (2, 32) + out_sp and y.dtype == torch.float16 and y.device.type == "cuda"
+            g = torch.ops.mdconv_b200.deform_conv_backward(x, w, b, off, m, y, *geo)
+            assert [tuple(t.shape) for t in g] == [tuple(x.shape), tuple(off.shape),
+                                                   tuple(m.shape) if modulated else (0,), tuple(w.shape), (32,)]
+    with pytest.raises(NotImplementedError):
+        torch.ops.mdconv_b200.deform_conv(torch.zeros(1, 4, 5, 5), torch.zeros(4, 4, 3, 3), None,
+                                          torch.zeros(1, 18, 5, 5), None, [1, 1], [1, 1], [1, 1], 1, 1)
+
+
 def test_product_package_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "modulated-deform-conv_b200")
     for dirpath, _, files in os.walk(pkg):

@@ -238,6 +238,73 @@ def test_saved_layouts_hand_off_is_bit_identical_and_skips_two_passes():
     assert np.array_equal(g[3].double().cpu().numpy(), res[True]["grad_weight"])
 
 
+def test_dispatcher_ops_match_functions_and_compile():
+    """mdconv_ops (torch.library): same bits as the autograd Functions, passes torch.library.opcheck, and a module
+    using it compiles with fullgraph=True (aot_eager: fake tensors + the registered autograd formula)."""
+    import mdconv_ops
+    import modulated_deform_conv as mdc
+    case = {c.name: c for c in TENSOR_CASES}["tc_m2d_c64"]
+    t = make_inputs(case, torch.float16)
+    d = {k: (v.cuda() if v is not None else None) for k, v in t.items()}
+    geo = (list(case.s), list(case.p), list(case.d), case.g, case.dg)
+
+    def run(fn):
+        lv = {k: d[k].clone().requires_grad_() for k in ("x", "weight", "bias", "offset", "mask")}
+        y = fn(lv)
+        y.backward(d["grad_output"])
+        return [y.detach()] + [lv[k].grad for k in ("x", "weight", "bias", "offset", "mask")]
+
+    ref = run(lambda lv: mdc.modulated_deform_conv2d(lv["x"], lv["offset"], lv["mask"], lv["weight"], lv["bias"],
+                                                     case.s, case.p, case.d, case.g, case.dg))
+    op = run(lambda lv: mdconv_ops.deform_conv(lv["x"], lv["weight"], lv["bias"], lv["offset"], lv["mask"], *geo))
+    assert torch.equal(ref[0], op[0])
+    for a, b in zip(ref[1:], op[1:]):   # this shape's backward runs on the SIMT kernels (atomics: order-dependent bits)
+        assert rel_err(b.float().cpu().numpy(), a.float().cpu().numpy()) < 2e-3
+    compiled = torch.compile(lambda x, w, b, o, m: mdconv_ops.deform_conv(x, w, b, o, m, *geo) * 2.0,
+                             backend="aot_eager", fullgraph=True)
+    cp = run(lambda lv: compiled(lv["x"], lv["weight"], lv["bias"], lv["offset"], lv["mask"]) / 2.0)
+    for a, b in zip(ref, cp):
+        assert rel_err(b.float().cpu().numpy(), a.float().cpu().numpy()) < 2e-3
+    # plain 3D op through the same entry (mask=None, 5-d input), small fp32 case on the SIMT kernels
+    c3 = {c.name: c for c in ALL_CASES}["d3d_base"]
+    t3 = make_inputs(c3, torch.float32)
+    d3 = {k: (v.cuda() if v is not None else None) for k, v in t3.items()}
+    y3 = mdconv_ops.deform_conv(d3["x"], d3["weight"], d3["bias"], d3["offset"], None, list(c3.s), list(c3.p),
+                                list(c3.d), c3.g, c3.dg)
+    assert rel_err(y3.double().cpu().numpy(), _oracle(c3, t3)["y"]) < 1e-4
+    torch.library.opcheck(mdconv_ops.deform_conv, (d3["x"], d3["weight"], d3["bias"], d3["offset"], None, list(c3.s),
+                                                    list(c3.p), list(c3.d), c3.g, c3.dg),
+                          test_utils=("test_schema", "test_faketensor"))
+
+
+def test_autocast_and_merged_pack_producers():
+    """Under torch.autocast the op runs in the autocast dtype (fp32 offsets / weights are cast like a conv's);
+    a modulated Pack's single merged offset+mask convolution equals the reference's two separate convs."""
+    import modulated_deform_conv as mdc
+    torch.manual_seed(3)
+    m = mdc.ModulatedDeformConv2d(64, 64, 3, padding=1, bias=True).cuda()          # fp32 parameters
+    x = torch.randn(2, 64, 9, 8, device="cuda")
+    off = torch.randn(2, 18, 9, 8, device="cuda")
+    msk = torch.sigmoid(torch.randn(2, 9, 9, 8, device="cuda"))
+    y32 = m(x, off, msk)
+    for dt in (torch.float16, torch.bfloat16):
+        with torch.autocast("cuda", dtype=dt):
+            y = m(x, off, msk)
+        assert y.dtype == dt
+        assert rel_err(y.detach().float().cpu().numpy(), y32.detach().cpu().numpy()) < TOL[dt]
+    y.float().sum().backward()
+    assert m.weight.grad is not None and m.weight.grad.dtype == torch.float32
+    pack = mdc.ModulatedDeformConv2dPack(8, 8, 3, padding=1, deformable_groups=2).cuda()
+    xs = torch.randn(2, 8, 7, 6, device="cuda")
+    o, k = mdc._offset_and_mask(pack, xs)
+    assert rel_err(o.detach().cpu().numpy(), pack.conv_offset(xs).detach().cpu().numpy()) < 1e-5
+    assert rel_err(k.detach().cpu().numpy(), pack.conv_mask(xs).detach().cpu().numpy()) < 1e-5
+    out = pack(xs)
+    out.sum().backward()
+    assert pack.conv_offset.weight.grad is not None and pack.conv_mask.bias.grad is not None
+    assert out.shape == (2, 8, 7, 6)
+
+
 def test_results_do_not_depend_on_in_step():
     import modulated_deform_conv as mdc
     case = ALL_CASES[1]
