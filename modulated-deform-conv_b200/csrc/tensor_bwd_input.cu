@@ -50,7 +50,7 @@ struct __align__(16) GiPlanRow {
 };
 static_assert(sizeof(GiPlanRow) == 64, "GiPlanRow must be 64 bytes");
 // registers after setmaxnreg (the CTA owns GI_THREADS x 72)
-constexpr uint32_t GI_REGS_CTL = 32, GI_REGS_EPI = 48, GI_REGS_PLAN = 56, GI_REGS_GATHER = 88;
+constexpr uint32_t GI_REGS_CTL = 32, GI_REGS_EPI = 40, GI_REGS_PLAN = 48, GI_REGS_GATHER = 96;
 static_assert(128 * (GI_REGS_CTL + GI_REGS_EPI + GI_REGS_PLAN) + GI_GATHER_THREADS * GI_REGS_GATHER <= GI_THREADS * 72,
               "setmaxnreg.inc would wait forever");
 
@@ -441,43 +441,60 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const TcGiParams pr
     const int Co8 = g.Co >> 3;
     int s = 0, ps = 0;
     uint32_t ph = 0, pph = 0;
+    // Software pipeline over the (output-channel block, pass) steps of one tap: the plan rows of this thread's
+    // two passes (bin heads: row offsets, weights, lengths) are read once per tap -- the cobs K-blocks of the tap
+    // share them -- and the loads of the next step are in flight while the current one is accumulated
+    // (ping-pong register buffers; the pipeline drains only at tap boundaries).
     for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x) {
       const int nt = t / prm.m_tiles;
       const int grp = (nt * BN) / g.Cg;
       for (int tap = 0; tap < g.K; ++tap) {
         ptx::mbar_wait(&plan_full[ps], pph);
         const uint32_t plan_addr = ptx::smem_u32(sPlan + ps * GI_BM + row0);
+        // byte address of this lane's 8 channels in row 0 of output-channel block 0; entries add a 32-bit
+        // row offset, every further block 128 bytes
+        const char* gcb = reinterpret_cast<const char*>(gq + ((grp * g.Cog) >> 3) + chunk);
+        uint4 va[GI_NE], vb[GI_NE];
+        // the row offsets are re-read from the plan row at every issue (two LDS.128) rather than held for the
+        // tap: two load buffers + both passes' offsets do not fit the gather warps' registers
+        auto issue = [&](uint4 (&v)[GI_NE], int pass, const char* base) {
+          const uint32_t pa = plan_addr + pass * 4 * (uint32_t)sizeof(GiPlanRow);
+          const uint4 i0 = lds128(pa), i1 = lds128(pa + 16), meta = lds128(pa + 48);
+          const uint32_t idx[GI_NE] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+          const int n = (int)meta.x;
+#pragma unroll
+          for (int i = 0; i < GI_NE; ++i)
+            if (i < n) v[i] = __ldg(reinterpret_cast<const uint4*>(base + idx[i]));
+        };
+        auto finish = [&](const uint4 (&v)[GI_NE], int pass, const char* base, uint32_t a_addr) {
+          const uint32_t pa = plan_addr + pass * 4 * (uint32_t)sizeof(GiPlanRow);
+          const uint4 wv = lds128(pa + 32), meta = lds128(pa + 48);
+          const __half* wh = reinterpret_cast<const __half*>(&wv);
+          const int n = (int)meta.x;
+          Acc8<T> acc;
+          acc.clear();
+#pragma unroll
+          for (int i = 0; i < GI_NE; ++i)
+            if (i < n) acc.fma(v[i], wh[i]);
+          for (int e = GI_NE; e < n; ++e) {   // rare: bins longer than the staged head
+            const int2 ee = __ldg(entries2 + (int)meta.y + e);
+            acc.fma(__ldg(reinterpret_cast<const uint4*>(base + (size_t)ee.x * (size_t)(g.Co * 2))),
+                    __int_as_float(ee.y));
+          }
+          sts128(a_addr + sw128(row0 + pass * 4, chunk), acc.pack());
+        };
+        issue(va, 0, gcb);
         for (int cob = 0; cob < prm.cobs; ++cob) {
-          // byte address of this lane's 8 channels in row 0; entries add a 32-bit row offset
-          const char* gcb = reinterpret_cast<const char*>(gq + ((grp * g.Cog + cob * 64) >> 3) + chunk);
+          issue(vb, 1, gcb);
           ptx::mbar_wait(&empty[s], ph ^ 1);
           const uint32_t a_addr = ptx::smem_u32(sA + s * GI_A_BYTES);
-#pragma unroll
-          for (int pass = 0; pass < 2; ++pass) {
-            const uint32_t pa = plan_addr + pass * 4 * (uint32_t)sizeof(GiPlanRow);
-            const uint4 i0 = lds128(pa), i1 = lds128(pa + 16), wv = lds128(pa + 32), meta = lds128(pa + 48);
-            const uint32_t idx[GI_NE] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
-            const __half* wh = reinterpret_cast<const __half*>(&wv);
-            const int n = (int)meta.x;
-            uint4 v[GI_NE];
-#pragma unroll
-            for (int i = 0; i < GI_NE; ++i)
-              if (i < n) v[i] = __ldg(reinterpret_cast<const uint4*>(gcb + idx[i]));
-            Acc8<T> acc;
-            acc.clear();
-#pragma unroll
-            for (int i = 0; i < GI_NE; ++i)
-              if (i < n) acc.fma(v[i], wh[i]);
-            for (int e = GI_NE; e < n; ++e) {   // rare: bins longer than the staged head
-              const int2 ee = __ldg(entries2 + (int)meta.y + e);
-              acc.fma(__ldg(reinterpret_cast<const uint4*>(gcb + (size_t)ee.x * (size_t)(g.Co * 2))),
-                      __int_as_float(ee.y));
-            }
-            sts128(a_addr + sw128(row0 + pass * 4, chunk), acc.pack());
-          }
+          finish(va, 0, gcb, a_addr);
+          if (cob + 1 < prm.cobs) issue(va, 0, gcb + 128);
+          finish(vb, 1, gcb, a_addr);
           ptx::fence_proxy_async_smem();
           ptx::mbar_arrive(&full_a[s]);
           if (++s == GI_STAGES) { s = 0; ph ^= 1; }
+          gcb += 128;
         }
         ptx::mbar_arrive(&plan_empty[ps]);
         if (++ps == GI_PLAN_SLOTS) { ps = 0; pph ^= 1; }
