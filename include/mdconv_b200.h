@@ -139,12 +139,17 @@ int mdconv_backward(const mdconv_geom_t* g, const void* input, const void* weigh
  * forward leaves the channels-last input and the re-ordered weight in the first mdconv_saved_bytes() bytes of
  * ITS workspace.  A caller that keeps that workspace untouched until the matching backward (same input, weight
  * and geometry) passes it as `saved` and the backward skips both layout passes.  mdconv_saved_bytes() is 0
- * when either direction would not run on the tensor path; saved == NULL is mdconv_backward(). */
+ * when either direction would not run on the tensor path; saved == NULL is mdconv_backward().
+ * weight_ready_event: NULL, or a cudaEvent_t the library records on `stream` as soon as grad_weight and grad_bias
+ * are final -- the tensor path computes them FIRST, so a data-parallel caller can run its all-reduce of the two
+ * parameter gradients (the only exchange of this path) on another stream while grad_offset / grad_mask /
+ * grad_input are still being computed. */
 size_t mdconv_saved_bytes(const mdconv_geom_t* g);
 int mdconv_backward_saved(const mdconv_geom_t* g, const void* input, const void* weight, const void* offset,
                           const void* mask, const void* grad_output, void* grad_input, void* grad_weight,
                           void* grad_bias, void* grad_offset, void* grad_mask, void* workspace,
-                          size_t workspace_bytes, const void* saved, size_t saved_bytes, void* stream);
+                          size_t workspace_bytes, const void* saved, size_t saved_bytes, void* weight_ready_event,
+                          void* stream);
 
 /* ---- The reference's eight entry points, C ABI form --------------------------------------
  * Argument order follows the reference signatures; tensor handles become device pointers and the

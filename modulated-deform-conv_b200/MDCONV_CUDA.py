@@ -59,7 +59,7 @@ _lib.mdconv_backward.argtypes = [ctypes.POINTER(_Geom)] + [_vp] * 11 + [_sz, _vp
 _lib.mdconv_saved_bytes.restype = _sz
 _lib.mdconv_saved_bytes.argtypes = [ctypes.POINTER(_Geom)]
 _lib.mdconv_backward_saved.restype = _i
-_lib.mdconv_backward_saved.argtypes = [ctypes.POINTER(_Geom)] + [_vp] * 11 + [_sz, _vp, _sz, _vp]
+_lib.mdconv_backward_saved.argtypes = [ctypes.POINTER(_Geom)] + [_vp] * 11 + [_sz, _vp, _sz, _vp, _vp]
 
 _TAIL = [_i, _vp, _sz, _vp]  # dtype, workspace, workspace_bytes, stream
 _G2 = [_i] * 17              # batch, channels, H, W, Cout, kh,kw, sh,sw, ph,pw, dh,dw, g, dg, in_step, with_bias
@@ -256,9 +256,11 @@ def _forward(input, weight, bias, offset, mask, output, kernel, stride, pad, dil
 
 
 def _backward(input, weight, bias, offset, mask, grad_output, grads, kernel, stride, pad, dil, group, dgroup,
-              with_bias, saved=None):
+              with_bias, saved=None, weight_ready=None):
     """grads: None (allocate and return) or dict of caller-owned tensors (out-param style).
-    saved: what ``_forward(..., keep=True)`` returned for the same input / weight / geometry, or None."""
+    saved: what ``_forward(..., keep=True)`` returned for the same input / weight / geometry, or None.
+    weight_ready: a ``torch.cuda.Event`` recorded on the current stream once grad_weight / grad_bias are final
+    (before the data gradients are computed on the tensor path), or None."""
     nd = len(kernel)
     modulated = mask is not None
     named = [("input", input), ("weight", weight), ("bias", bias), ("offset", offset)]
@@ -292,7 +294,9 @@ def _backward(input, weight, bias, offset, mask, grad_output, grads, kernel, str
                                         _ptr(grad_output), _ptr(grads["grad_input"]), _ptr(grads["grad_weight"]),
                                         _ptr(grads["grad_bias"]) if with_bias else None, _ptr(grads["grad_offset"]),
                                         _ptr(grads.get("grad_mask")) if modulated else None, _ptr(ws), n,
-                                        sv_ptr, sv_n, ctypes.c_void_p(stream))
+                                        sv_ptr, sv_n,
+                                        ctypes.c_void_p(weight_ready.cuda_event) if weight_ready is not None else None,
+                                        ctypes.c_void_p(stream))
     _check(rc, "mdconv_backward")
     return grads
 
@@ -306,10 +310,10 @@ def forward_ex(input, weight, bias, offset, mask, output, kernel, stride, pad, d
 
 
 def backward_ex(input, weight, bias, offset, mask, grad_output, kernel, stride, pad, dil, group, deformable_group,
-                with_bias, saved=None):
+                with_bias, saved=None, weight_ready=None):
     """Generic form of the four backwards -> dict grad_input / grad_offset / grad_mask / grad_weight / grad_bias."""
     return _backward(input, weight, bias, offset, mask, grad_output, None, tuple(kernel), tuple(stride), tuple(pad),
-                     tuple(dil), group, deformable_group, with_bias, saved=saved)
+                     tuple(dil), group, deformable_group, with_bias, saved=saved, weight_ready=weight_ready)
 
 
 # ---- the eight reference entry points ------------------------------------------------------------

@@ -225,13 +225,13 @@ int mdconv_backward(const mdconv_geom_t* gi, const void* input, const void* weig
                     const void* mask, const void* grad_output, void* grad_input, void* grad_weight, void* grad_bias,
                     void* grad_offset, void* grad_mask, void* workspace, size_t workspace_bytes, void* stream) {
   return mdconv_backward_saved(gi, input, weight, offset, mask, grad_output, grad_input, grad_weight, grad_bias,
-                               grad_offset, grad_mask, workspace, workspace_bytes, nullptr, 0, stream);
+                               grad_offset, grad_mask, workspace, workspace_bytes, nullptr, 0, nullptr, stream);
 }
 
 int mdconv_backward_saved(const mdconv_geom_t* gi, const void* input, const void* weight, const void* offset,
                           const void* mask, const void* grad_output, void* grad_input, void* grad_weight,
                           void* grad_bias, void* grad_offset, void* grad_mask, void* workspace, size_t workspace_bytes,
-                          const void* saved, size_t saved_bytes, void* stream) {
+                          const void* saved, size_t saved_bytes, void* weight_ready_event, void* stream) {
   DevGeom g;
   int rc = resolve(gi, g);
   if (rc != MDCONV_OK) return rc;
@@ -246,6 +246,7 @@ int mdconv_backward_saved(const mdconv_geom_t* gi, const void* input, const void
   if (need > 0 && (workspace == nullptr || workspace_bytes < need || ((uintptr_t)workspace & 255)))
     return MDCONV_ERR_WORKSPACE;
   LaunchCtx ctx{(cudaStream_t)stream, 0, cudaSuccess};
+  ctx.weight_ready = (cudaEvent_t)weight_ready_event;
   (void)cudaGetLastError();
   if (saved != nullptr) {
     // only meaningful when both directions run on the tensor path; anything else is a caller error
@@ -258,6 +259,7 @@ int mdconv_backward_saved(const mdconv_geom_t* gi, const void* input, const void
   else
     generic_backward(g, gi->dtype, input, weight, offset, mask, grad_output, grad_input, grad_weight, grad_bias,
                      grad_offset, grad_mask, workspace, ctx);
+  signal_weight_ready(ctx);   // paths that did not signal earlier: everything is enqueued by now
   return finish(ctx);
 }
 

@@ -207,7 +207,17 @@ struct LaunchCtx {
   cudaStream_t stream;
   int launches;
   cudaError_t err;
+  // backward only: recorded on `stream` as soon as grad_weight and grad_bias are final (nullptr: not wanted), so a
+  // data-parallel caller can start their all-reduce while the data gradients are still being computed
+  cudaEvent_t weight_ready = nullptr;
 };
+inline void signal_weight_ready(LaunchCtx& ctx) {
+  if (ctx.weight_ready != nullptr) {
+    cudaError_t e = cudaEventRecord(ctx.weight_ready, ctx.stream);
+    if (e != cudaSuccess && ctx.err == cudaSuccess) ctx.err = e;
+    ctx.weight_ready = nullptr;
+  }
+}
 
 #define MDCONV_CHECK_LAUNCH(ctx)                       \
   do {                                                 \

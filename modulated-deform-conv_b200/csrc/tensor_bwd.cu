@@ -448,14 +448,16 @@ void tensor_backward_t(const DevGeom& g, const void* x, const void* w, const voi
     MDCONV_CHECK_LAUNCH(ctx);
   }
 
-  // ---- grad_offset / grad_mask / grad_input (+ grad_bias) ----
+  // grad_bias next: with it both parameter gradients are final and the caller's all-reduce may start
+  generic_backward(g, dtype, x, w, off, mask, go, gx, gw, gb, goff, gmask, nullptr, ctx, GENERIC_BWD_BIAS);
+  signal_weight_ready(ctx);
+
+  // ---- grad_offset / grad_mask / grad_input ----
   if (data_tc) {
     tensor_grad_sample<T>(g, xt, wr, off, mask, go, goff, gmask, ctx);
     tensor_grad_input<T>(g, w, go, gx, data_ws, ctx);
-    generic_backward(g, dtype, x, w, off, mask, go, gx, gw, gb, goff, gmask, nullptr, ctx, GENERIC_BWD_BIAS);
   } else {
-    generic_backward(g, dtype, x, w, off, mask, go, gx, gw, gb, goff, gmask, data_ws, ctx,
-                     GENERIC_BWD_DATA | GENERIC_BWD_BIAS);
+    generic_backward(g, dtype, x, w, off, mask, go, gx, gw, gb, goff, gmask, data_ws, ctx, GENERIC_BWD_DATA);
   }
 }
 

@@ -84,6 +84,61 @@ class GradBucket:
             off += n
 
 
+class GradSync:
+    """Overlapped all-reduce of one module's parameter gradients, driven from inside the op's backward.
+
+    The tcgen05 backward computes grad_weight / grad_bias FIRST and records a CUDA event when they are final
+    (``mdconv_backward_saved(..., weight_ready_event)``).  ``reduce`` then runs ONE all-reduce(sum) of the two
+    tensors on a communication stream that waits for that event only, so the collective overlaps the
+    grad_offset / grad_mask / grad_input kernels; the compute stream re-joins before the backward returns, which
+    keeps autograd's accumulation into ``.grad`` ordered after the reduction.  Attach with ``attach(module, group)``;
+    the reduction is in the gradients' own dtype and in place (as DDP does), sum not mean.
+    On CPU tensors / a non-initialised process group it degrades to a plain (or no) all-reduce.
+    """
+
+    def __init__(self, group=None, device: Optional[torch.device] = None):
+        self.group = group
+        self._stream = None
+        self.event = None
+        if device is not None and device.type == "cuda":
+            self._stream = torch.cuda.Stream(device=device)
+            self.event = torch.cuda.Event()
+            self.event.record(torch.cuda.current_stream(device))   # force creation of the CUDA event handle
+
+    def active(self) -> bool:
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def reduce(self, tensors: Sequence[Optional[torch.Tensor]]) -> None:
+        ts = [t for t in tensors if t is not None and t.numel() > 0]
+        if not ts or not self.active():
+            return
+        if self._stream is None:
+            for t in ts:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            return
+        main = torch.cuda.current_stream(ts[0].device)
+        self._stream.wait_event(self.event)          # only grad_weight / grad_bias, not the whole backward
+        with torch.cuda.stream(self._stream):
+            flat = ts[0] if len(ts) == 1 else torch.cat([t.reshape(-1) for t in ts])
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            if len(ts) > 1:
+                off = 0
+                for t in ts:
+                    t.copy_(flat[off:off + t.numel()].reshape(t.shape))
+                    off += t.numel()
+            for t in ts:
+                t.record_stream(self._stream)
+        main.wait_stream(self._stream)
+
+
+def attach(module, group=None) -> "GradSync":
+    """Make ``module`` (a DeformConv*/ModulatedDeformConv* module of this package) all-reduce its weight / bias
+    gradients inside its own backward, overlapped with the data gradients.  Returns the GradSync."""
+    p = next(module.parameters())
+    module._grad_sync = GradSync(group, p.device)
+    return module._grad_sync
+
+
 def all_reduce_param_grads(params: Sequence[torch.Tensor], group=None) -> None:
     """One-shot helper: sum the gradients of `params` (weight, bias) over all ranks."""
     b = GradBucket(params)

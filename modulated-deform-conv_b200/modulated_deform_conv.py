@@ -78,17 +78,25 @@ def _forward_op(ctx, input, weight, bias, offset, mask, keep):
 
 
 def _backward_op(ctx, input, weight, bias, offset, mask, grad_output):
+    sync = getattr(ctx, "grad_sync", None)
+    if sync is not None and not sync.active():
+        sync = None
     g = MDCONV_CUDA.backward_ex(input, weight, bias, offset, mask, grad_output, weight.shape[2:], ctx.stride,
                                 ctx.padding, ctx.dilation, ctx.groups, ctx.deformable_groups, ctx.with_bias,
-                                saved=getattr(ctx, "layouts", None))
+                                saved=getattr(ctx, "layouts", None),
+                                weight_ready=sync.event if sync is not None else None)
     ctx.layouts = None
+    if sync is not None:
+        # data-parallel: ONE all-reduce of [grad_weight, grad_bias], overlapped with the data-gradient kernels
+        sync.reduce([g["grad_weight"], g["grad_bias"] if ctx.with_bias else None])
     return g
 
 
 class DeformConv2dFunction(Function):
     @staticmethod
     def forward(ctx, input, offset, weight, bias=None, stride=1, padding=0, dilation=1,
-                groups=1, deformable_groups=1, in_step=64):
+                groups=1, deformable_groups=1, in_step=64, grad_sync=None):
+        ctx.grad_sync = grad_sync
         with_bias_tensor = bias
         bias = _setup(ctx, _pair, input, bias, stride, padding, dilation, groups, deformable_groups, in_step)
         keep = _needs_grad(input, offset, weight, with_bias_tensor)
@@ -105,13 +113,14 @@ class DeformConv2dFunction(Function):
         input, offset, weight, bias = ctx.saved_tensors
         g = _backward_op(ctx, input, weight, bias, offset, None, grad_output)
         return (g["grad_input"], g["grad_offset"], g["grad_weight"], g["grad_bias"] if ctx.with_bias else None,
-                None, None, None, None, None, None)
+                None, None, None, None, None, None, None)
 
 
 class ModulatedDeformConv2dFunction(Function):
     @staticmethod
     def forward(ctx, input, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1,
-                groups=1, deformable_groups=1, in_step=64):
+                groups=1, deformable_groups=1, in_step=64, grad_sync=None):
+        ctx.grad_sync = grad_sync
         with_bias_tensor = bias
         bias = _setup(ctx, _pair, input, bias, stride, padding, dilation, groups, deformable_groups, in_step)
         keep = _needs_grad(input, offset, mask, weight, with_bias_tensor)
@@ -128,13 +137,14 @@ class ModulatedDeformConv2dFunction(Function):
         input, offset, mask, weight, bias = ctx.saved_tensors
         g = _backward_op(ctx, input, weight, bias, offset, mask, grad_output)
         return (g["grad_input"], g["grad_offset"], g["grad_mask"], g["grad_weight"],
-                g["grad_bias"] if ctx.with_bias else None, None, None, None, None, None, None)
+                g["grad_bias"] if ctx.with_bias else None, None, None, None, None, None, None, None)
 
 
 class DeformConv3dFunction(Function):
     @staticmethod
     def forward(ctx, input, offset, weight, bias=None, stride=1, padding=0, dilation=1,
-                groups=1, deformable_groups=1, in_step=64):
+                groups=1, deformable_groups=1, in_step=64, grad_sync=None):
+        ctx.grad_sync = grad_sync
         with_bias_tensor = bias
         bias = _setup(ctx, _triple, input, bias, stride, padding, dilation, groups, deformable_groups, in_step)
         keep = _needs_grad(input, offset, weight, with_bias_tensor)
@@ -151,13 +161,14 @@ class DeformConv3dFunction(Function):
         input, offset, weight, bias = ctx.saved_tensors
         g = _backward_op(ctx, input, weight, bias, offset, None, grad_output)
         return (g["grad_input"], g["grad_offset"], g["grad_weight"], g["grad_bias"] if ctx.with_bias else None,
-                None, None, None, None, None, None)
+                None, None, None, None, None, None, None)
 
 
 class ModulatedDeformConv3dFunction(Function):
     @staticmethod
     def forward(ctx, input, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1,
-                groups=1, deformable_groups=1, in_step=64):
+                groups=1, deformable_groups=1, in_step=64, grad_sync=None):
+        ctx.grad_sync = grad_sync
         with_bias_tensor = bias
         bias = _setup(ctx, _triple, input, bias, stride, padding, dilation, groups, deformable_groups, in_step)
         keep = _needs_grad(input, offset, mask, weight, with_bias_tensor)
@@ -174,7 +185,7 @@ class ModulatedDeformConv3dFunction(Function):
         input, offset, mask, weight, bias = ctx.saved_tensors
         g = _backward_op(ctx, input, weight, bias, offset, mask, grad_output)
         return (g["grad_input"], g["grad_offset"], g["grad_mask"], g["grad_weight"],
-                g["grad_bias"] if ctx.with_bias else None, None, None, None, None, None, None)
+                g["grad_bias"] if ctx.with_bias else None, None, None, None, None, None, None, None)
 
 
 def _amp(*tensors):
@@ -190,31 +201,31 @@ def _amp(*tensors):
 # The reference binds these four names to ``Function.apply`` (modulated_deform_conv.py:349-352); same call
 # signatures here, plus the autocast handling above.
 def deform_conv2d(input, offset, weight, bias=None, stride=1, padding=0, dilation=1, groups=1,
-                  deformable_groups=1, in_step=64):
+                  deformable_groups=1, in_step=64, grad_sync=None):
     input, offset, weight, bias = _amp(input, offset, weight, bias)
     return DeformConv2dFunction.apply(input, offset, weight, bias, stride, padding, dilation, groups,
-                                      deformable_groups, in_step)
+                                      deformable_groups, in_step, grad_sync)
 
 
 def modulated_deform_conv2d(input, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1, groups=1,
-                            deformable_groups=1, in_step=64):
+                            deformable_groups=1, in_step=64, grad_sync=None):
     input, offset, mask, weight, bias = _amp(input, offset, mask, weight, bias)
     return ModulatedDeformConv2dFunction.apply(input, offset, mask, weight, bias, stride, padding, dilation, groups,
-                                               deformable_groups, in_step)
+                                               deformable_groups, in_step, grad_sync)
 
 
 def deform_conv3d(input, offset, weight, bias=None, stride=1, padding=0, dilation=1, groups=1,
-                  deformable_groups=1, in_step=64):
+                  deformable_groups=1, in_step=64, grad_sync=None):
     input, offset, weight, bias = _amp(input, offset, weight, bias)
     return DeformConv3dFunction.apply(input, offset, weight, bias, stride, padding, dilation, groups,
-                                      deformable_groups, in_step)
+                                      deformable_groups, in_step, grad_sync)
 
 
 def modulated_deform_conv3d(input, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1, groups=1,
-                            deformable_groups=1, in_step=64):
+                            deformable_groups=1, in_step=64, grad_sync=None):
     input, offset, mask, weight, bias = _amp(input, offset, mask, weight, bias)
     return ModulatedDeformConv3dFunction.apply(input, offset, mask, weight, bias, stride, padding, dilation, groups,
-                                               deformable_groups, in_step)
+                                               deformable_groups, in_step, grad_sync)
 
 
 class _DeformConvNd(nn.Module):
@@ -260,8 +271,9 @@ class _DeformConvNd(nn.Module):
             self.bias.data.fill_(0)
 
     def _conv_args(self):
+        # the trailing element is the data-parallel gradient reducer (mdconv_dist.attach), None by default
         return (self.weight, self.bias, self.stride, self.padding, self.dilation, self.groups,
-                self.deformable_groups, self.in_step)
+                self.deformable_groups, self.in_step, getattr(self, "_grad_sync", None))
 
     def extra_repr(self):
         return ('{in_channels}, {out_channels}, kernel_size={kernel_size}, stride={stride}, padding={padding}, '

@@ -39,6 +39,13 @@ def _worker(rank, world, port, ret):
         b.grad = torch.from_numpy(loc["grad_bias"]).clone()
         mdconv_dist.all_reduce_param_grads([w, b])
         ok = rel_err(w.grad.numpy(), full["grad_weight"]) < 1e-6 and rel_err(b.grad.numpy(), full["grad_bias"]) < 1e-6
+        # the in-backward reducer (GradSync) on the same local gradients: CPU tensors -> plain all-reduce, in place
+        gw2 = torch.from_numpy(loc["grad_weight"]).clone()
+        gb2 = torch.from_numpy(loc["grad_bias"]).clone()
+        sync = mdconv_dist.GradSync(None, torch.device("cpu"))
+        ok = ok and sync.active()
+        sync.reduce([gw2, gb2, None])
+        ok = ok and rel_err(gw2.numpy(), full["grad_weight"]) < 1e-12 and rel_err(gb2.numpy(), full["grad_bias"]) < 1e-12
         ok = ok and rel_err(loc["grad_input"], full["grad_input"][lo:hi]) < 1e-12
         ok = ok and rel_err(loc["grad_offset"], full["grad_offset"][lo:hi]) < 1e-12
         ok = ok and rel_err(loc["grad_mask"], full["grad_mask"][lo:hi]) < 1e-12

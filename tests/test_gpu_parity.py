@@ -305,6 +305,35 @@ def test_autocast_and_merged_pack_producers():
     assert out.shape == (2, 8, 7, 6)
 
 
+def test_weight_ready_event_fires_before_the_data_gradients():
+    """mdconv_backward_saved(weight_ready_event): the event is recorded once grad_weight / grad_bias are final; a
+    stream that waits only for it must already see the finished parameter gradients, and the event completes
+    before the whole backward does (it sits in front of the two data-gradient kernels)."""
+    import MDCONV_CUDA
+    case = {c.name: c for c in TENSOR_CASES}["tc_m2d_c256_multi_tile"]
+    t = make_inputs(case, torch.float16)
+    d = {k: (v.cuda() if v is not None else None) for k, v in t.items()}
+    b0 = d["x"].new_empty(0)
+    ref = MDCONV_CUDA.backward_ex(d["x"], d["weight"], b0, d["offset"], d["mask"], d["grad_output"], case.k, case.s,
+                                  case.p, case.d, case.g, case.dg, False)
+    torch.cuda.synchronize()
+    ev, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start = torch.cuda.Event(enable_timing=True)
+    ev.record()                       # creates the CUDA event handle
+    side = torch.cuda.Stream()
+    start.record()
+    g = MDCONV_CUDA.backward_ex(d["x"], d["weight"], b0, d["offset"], d["mask"], d["grad_output"], case.k, case.s,
+                                case.p, case.d, case.g, case.dg, False, weight_ready=ev)
+    end.record()
+    side.wait_event(ev)
+    with torch.cuda.stream(side):
+        gw_seen = g["grad_weight"].clone()   # ordered after the event only
+    torch.cuda.synchronize()
+    assert torch.equal(gw_seen, ref["grad_weight"])
+    assert torch.equal(g["grad_input"], ref["grad_input"]) and torch.equal(g["grad_offset"], ref["grad_offset"])
+    assert start.elapsed_time(ev) < start.elapsed_time(end)
+
+
 def test_results_do_not_depend_on_in_step():
     import modulated_deform_conv as mdc
     case = ALL_CASES[1]
