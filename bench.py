@@ -272,11 +272,34 @@ def run_reference_arm(args, w):
             "cpu_baseline": {"value": val, "unit": "Msamples/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    _emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
+def _emit(line: dict) -> None:
+    """The ONE JSON line goes to the real stdout; everything else this process (or a library under it, e.g. NCCL's
+    version banner) writes to fd 1 has been routed to stderr by _quiet_stdout()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
+_REAL_STDOUT = None
+
+
+def _quiet_stdout() -> None:
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -531,7 +554,7 @@ def main():
                 "gpu_launches": n_launch, "clocks": clocks.summary(), "roofline": roofline, "roofline_kernels": roofline_kernels,
                 "roofline_hbm": roofline_hbm,
                 "kernels_ms_per_step": kernels, "cpu_baseline": cpu_base, "reference_cuda": ref_cuda}
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
