@@ -127,6 +127,12 @@ TENSOR_CASES = [
     # ragged tails: B*P not a multiple of the 128-row tile, P not a multiple of 64
     Case("tc_m2d_ragged", 2, True, B=3, C=64, Co=64, size=(10, 12), seed=78),
     Case("tc_m2d_sigma8", 2, True, B=1, C=64, Co=64, size=(16, 16), sigma=8.0, seed=79),
+    # more than one output-channel tile (Co = 512 > 256) and eight channel blocks (C = 512)
+    Case("tc_m2d_co512", 2, True, B=1, C=64, Co=512, size=(8, 8), seed=81),
+    Case("tc_d2d_c512_dg2", 2, False, B=1, C=512, Co=64, size=(8, 8), dg=2, seed=82),
+    # 1x1 kernel with stride 2 (a single tap), and a 5x5 kernel (25 taps, dilation 1, pad 2)
+    Case("tc_m2d_k1_s2", 2, True, B=2, C=64, Co=64, size=(9, 10), k=(1, 1), s=(2, 2), p=(0, 0), seed=83),
+    Case("tc_m2d_k5", 2, True, B=1, C=64, Co=64, size=(8, 8), k=(5, 5), p=(2, 2), seed=84),
     Case("tc_m3d_dg2_stride2", 3, True, B=1, C=128, Co=64, size=(6, 8, 8), k=(3, 3, 3), s=(2, 2, 2), p=(1, 1, 1),
          d=(1, 1, 1), dg=2, seed=80),
 ]
