@@ -210,6 +210,8 @@ struct LaunchCtx {
   // backward only: recorded on `stream` as soon as grad_weight and grad_bias are final (nullptr: not wanted), so a
   // data-parallel caller can start their all-reduce while the data gradients are still being computed
   cudaEvent_t weight_ready = nullptr;
+  // backward only: the join event of a side-stream fork made earlier in this call (nullptr: nothing forked)
+  cudaEvent_t side_join = nullptr;
 };
 inline void signal_weight_ready(LaunchCtx& ctx) {
   if (ctx.weight_ready != nullptr) {

@@ -611,7 +611,10 @@ void tensor_grad_input_prepare(const DevGeom& g, const void* off, const void* ma
   base += align256((size_t)g.B * g.Co * g.P * sizeof(T));
   base += align256((size_t)g.Co * g.Kg * sizeof(T));
   const GiLayout L = gi_layout(g);
-  SideStream* ss = side_stream();
+  // no fork while the caller's stream is being captured into a CUDA graph: the whole call then stays on that stream
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(ctx.stream, &cap) != cudaSuccess) { (void)cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
+  SideStream* ss = cap == cudaStreamCaptureStatusNone ? side_stream() : nullptr;
   cudaStream_t main_stream = ctx.stream;
   if (ss) {
     cudaEventRecord(ss->fork, main_stream);
@@ -628,6 +631,7 @@ void tensor_grad_input_prepare(const DevGeom& g, const void* off, const void* ma
   if (ss) {
     cudaEventRecord(ss->join, ss->stream);
     ctx.stream = main_stream;
+    ctx.side_join = ss->join;
   }
 }
 
@@ -648,7 +652,10 @@ void tensor_grad_input(const DevGeom& g, const void* w, const void* go, void* gx
     k_transpose_weight<T><<<blocks, 256, 0, ctx.stream>>>((const T*)w, wt, g.Co, g.Cg, g.Cog, g.K);
     MDCONV_CHECK_LAUNCH(ctx);
   }
-  if (SideStream* ss = side_stream()) cudaStreamWaitEvent(ctx.stream, ss->join, 0);  // inverse index is ready
+  if (ctx.side_join != nullptr) {   // inverse index is ready
+    cudaStreamWaitEvent(ctx.stream, ctx.side_join, 0);
+    ctx.side_join = nullptr;
+  }
 
   TcGiParams prm;
   prm.g = g;

@@ -334,6 +334,44 @@ def test_weight_ready_event_fires_before_the_data_gradients():
     assert start.elapsed_time(ev) < start.elapsed_time(end)
 
 
+def test_step_is_cuda_graph_capturable():
+    """A forward + backward of the module captured into ONE CUDA graph (torch.cuda.graph) and replayed gives the
+    eager bits: nothing in the library allocates, synchronises or touches another stream under capture (the
+    inverse-index fork onto the side stream is skipped while the caller's stream is capturing)."""
+    import modulated_deform_conv as mdc
+    torch.manual_seed(5)
+    m = mdc.ModulatedDeformConv2d(64, 64, 3, padding=1, bias=True).cuda().half()
+    x = torch.randn(2, 64, 12, 16, device="cuda").half().requires_grad_()
+    off = torch.randn(2, 18, 12, 16, device="cuda").half().requires_grad_()
+    msk = torch.sigmoid(torch.randn(2, 9, 12, 16, device="cuda")).half().requires_grad_()
+    go = torch.randn(2, 64, 12, 16, device="cuda").half()
+
+    def step():
+        for t in (x, off, msk, m.weight, m.bias):
+            t.grad = None
+        y = m(x, off, msk)
+        y.backward(go)
+        return y
+
+    y_ref = step().detach().clone()
+    ref = [t.grad.clone() for t in (x, off, msk, m.weight, m.bias)]
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            step()
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        y_static = step()
+    for _ in range(2):
+        g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(y_static, y_ref)
+    for t, r in zip((x, off, msk, m.weight, m.bias), ref):
+        assert torch.equal(t.grad, r)
+
+
 def test_results_do_not_depend_on_in_step():
     import modulated_deform_conv as mdc
     case = ALL_CASES[1]
