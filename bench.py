@@ -36,6 +36,9 @@ WORKLOADS = {
     "cfg2": dict(nd=2, modulated=True, B=32, C=256, Co=256, size=(56, 56), k=(3, 3), s=(1, 1), p=(1, 1), d=(1, 1),
                  g=1, dg=1, dtype="f16",
                  desc="cfg2: ModulatedDeformConv2d N=32/GPU C=256->256 56x56 k3 s1 p1 dg=1 fp16"),
+    "cfg2_bf16": dict(nd=2, modulated=True, B=32, C=256, Co=256, size=(56, 56), k=(3, 3), s=(1, 1), p=(1, 1),
+                      d=(1, 1), g=1, dg=1, dtype="bf16",
+                      desc="cfg2 shape in bf16: ModulatedDeformConv2d N=32/GPU C=256->256 56x56 k3 s1 p1 dg=1"),
     "cfg3": dict(nd=2, modulated=False, B=16, C=512, Co=512, size=(28, 28), k=(3, 3), s=(2, 2), p=(1, 1), d=(1, 1),
                  g=4, dg=4, dtype="f32", desc="cfg3: DeformConv2d N=16 C=512->512 28x28 k3 s2 p1 dg=4 g=4 fp32"),
     "cfg4": dict(nd=3, modulated=True, B=8, C=64, Co=128, size=(16, 32, 32), k=(3, 3, 3), s=(1, 1, 1), p=(1, 1, 1),
