@@ -9,7 +9,9 @@
 //     D = fp32 [co x kk] in TMEM, written once per CTA as a partial; a second kernel folds the
 //         partials in a fixed order (deterministic) and un-permutes kk -> (channel, tap).
 //
-// grad_input / grad_offset / grad_mask still run on the generic kernels in this revision.
+// This file also orchestrates the whole tensor-path backward (tensor_backward_t): grad_weight + grad_bias first
+// (the weight-ready event is recorded after them), then grad_offset / grad_mask (tensor_bwd_sample.cu) and
+// grad_input (tensor_bwd_input.cu); shapes those two refuse fall back to the generic data-gradient kernel.
 #include "tc_common.cuh"
 
 namespace mdconv {

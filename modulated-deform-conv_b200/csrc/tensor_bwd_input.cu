@@ -385,7 +385,6 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const TcGiParams pr
     // bin bounds of the next tap are fetched while this tap's entries are in flight.
     const int row = threadIdx.x - GI_PLAN_WARP0 * 32;
     const int* __restrict__ bin_start = prm.bin_start;
-    const int4* __restrict__ entries4 = reinterpret_cast<const int4*>(prm.entries);
     const int2* __restrict__ entries2 = reinterpret_cast<const int2*>(prm.entries);
     const int Co8 = g.Co >> 3;
     int ps = 0;
@@ -411,7 +410,6 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const TcGiParams pr
         for (int i = 0; i < GI_NE; ++i) { r.idx[i] = 0u; r.w[i] = __float2half_rn(0.f); }
         r.n = n;
         r.e0 = e0;
-        // entries are 8 bytes; read pairs with 16-byte loads when the bin start is even
 #pragma unroll
         for (int i = 0; i < GI_NE; ++i) {
           if (i < n) {
@@ -420,7 +418,6 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const TcGiParams pr
             r.w[i] = __float2half_rn(__int_as_float(ev.y));
           }
         }
-        (void)entries4;
         ptx::mbar_wait_relaxed(&plan_empty[ps], pph ^ 1, 128);
         const uint32_t pa = ptx::smem_u32(sPlan + ps * GI_BM + row);
         const uint4* q = reinterpret_cast<const uint4*>(&r);
