@@ -3,6 +3,7 @@ surface (modulated_deform_conv -> MDCONV_CUDA -> C ABI), against the CPU oracle 
 inputs.  Tolerances are BASELINE.json's: 1e-4 rel fp32, 1e-2 rel fp16 (rel = max|a-b| / max|b|),
 for the forward and all five gradients.  fp64 (1e-10) and bf16 (3e-2) are extra."""
 import glob
+import math
 import os
 
 import numpy as np
@@ -370,6 +371,52 @@ def test_step_is_cuda_graph_capturable():
     assert torch.equal(y_static, y_ref)
     for t, r in zip((x, off, msk, m.weight, m.bias), ref):
         assert torch.equal(t.grad, r)
+
+
+def _fuzz_cases(n2d=28, n3d=8):
+    """Seeded random geometries the tcgen05 path accepts (channels per group / deformable group multiples of 64)."""
+    import random
+    rng = random.Random(20261017)
+    out = []
+    for i in range(n2d + n3d):
+        nd = 2 if i < n2d else 3
+        g = rng.choice([1, 1, 2, 3])
+        dg = rng.choice([1, 1, 2])
+        # C: multiple of 64*g and of 64*dg
+        lcm = g * dg // math.gcd(g, dg)
+        C = 64 * lcm * rng.choice([1, 1, 2])
+        Co = g * rng.choice([32, 64, 96, 128]) if nd == 2 else g * rng.choice([32, 64])
+        if C > 384:
+            C = 64 * lcm
+        k = tuple(rng.choice([1, 3, 3]) for _ in range(nd)) if nd == 2 else tuple(rng.choice([1, 3]) for _ in range(nd))
+        s_ = tuple(rng.choice([1, 1, 2]) for _ in range(nd))
+        d_ = tuple(rng.choice([1, 1, 2]) for _ in range(nd))
+        p_ = tuple(rng.choice([0, 1, 2]) for _ in range(nd))
+        size = tuple(rng.randint(5, 14 if nd == 2 else 7) for _ in range(nd))
+        c = Case(f"fuzz{i}_{nd}d", nd, rng.random() < 0.6, B=rng.randint(1, 3), C=C, Co=Co, size=size, k=k, s=s_, p=p_,
+                 d=d_, g=g, dg=dg, sigma=rng.choice([0.0, 0.5, 1.0, 1.0, 3.0]), bias=rng.random() < 0.5, seed=500 + i)
+        if all(o >= 1 for o in c.out_size):
+            out.append(c)
+    return out
+
+
+@pytest.mark.parametrize("case", _fuzz_cases(), ids=lambda c: c.name)
+def test_fuzzed_geometries_tensor_path_matches_oracle(case):
+    """Random strides / dilations / paddings / kernel shapes / groups / deformable groups / ragged sizes: forward on
+    the tcgen05 path (mandatory), backward on it wherever it supports the shape, against the CPU oracle (fp16, 1e-2)."""
+    import ctypes
+    import MDCONV_CUDA
+    t = make_inputs(case, torch.float16)
+    g = MDCONV_CUDA._geom(t["x"], t["weight"], case.k, case.s, case.p, case.d, case.g, case.dg, case.modulated,
+                          case.bias)
+    g.path = 0
+    if MDCONV_CUDA._lib.mdconv_selected_path(ctypes.byref(g), 0) != 2:
+        pytest.skip("geometry not eligible for the tensor path")
+    try:
+        ours = _run_ours(case, t, fwd_path=2, bwd_path=0)
+    finally:
+        MDCONV_CUDA.set_path(0)
+    _compare(ours, _oracle(case, t), TOL[torch.float16], f"{case.name}: {case}")
 
 
 def test_results_do_not_depend_on_in_step():
