@@ -27,14 +27,17 @@ template <typename F> __device__ __forceinline__ void atomic_add(F* p, F v) { at
 // ------------------------------------------------------------------------------------------------
 // forward:  grid (B * ceil(P/BM), ceil(Cog/BN), groups)
 // ------------------------------------------------------------------------------------------------
-template <typename T, typename F, int ND, bool MOD>
+// BNT output channels per tile (64 or 128): each thread owns 4 pixels x BNT/16 channels; the wider tile does 32
+// FMAs per three 16-byte shared-memory reads instead of 16 per two, which is what paces this kernel.
+template <typename T, typename F, int ND, bool MOD, int BNT>
 __global__ void __launch_bounds__(NT) k_generic_forward(const DevGeom g, const T* __restrict__ x,
                                                         const T* __restrict__ w, const T* __restrict__ bias,
                                                         const T* __restrict__ off, const T* __restrict__ mask,
                                                         T* __restrict__ y) {
   constexpr int NC = 1 << ND;
   __shared__ F As[BK][BM + 4];  // col chunk   [channel][pix]
-  __shared__ F Bs[BK][BN + 4];  // weight chunk [channel][co]
+  constexpr int CJ = BNT / 16;  // output channels per thread
+  __shared__ F Bs[BK][BNT + 4];  // weight chunk [channel][co]
   // sampling plan of the current (tap, deformable group): per pixel the corner indices and the
   // interpolation weight x mask, computed ONCE and reused by every channel of the group (the
   // reference recomputes it per channel, src/mdeformable_conv.cu:59-83)
@@ -44,7 +47,7 @@ __global__ void __launch_bounds__(NT) k_generic_forward(const DevGeom g, const T
   const int tilesP = (g.P + BM - 1) / BM;
   const int b = blockIdx.x / tilesP;
   const int p0 = (blockIdx.x % tilesP) * BM;
-  const int n0 = blockIdx.y * BN;
+  const int n0 = blockIdx.y * BNT;
   const int grp = blockIdx.z;
   const int tid = threadIdx.x;
   const int tx = tid % 16, ty = tid / 16;
@@ -53,11 +56,11 @@ __global__ void __launch_bounds__(NT) k_generic_forward(const DevGeom g, const T
   const T* off_b = off + (size_t)b * g.dg * ND * g.K * g.P;
   const T* mask_b = MOD ? mask + (size_t)b * g.dg * g.K * g.P : nullptr;
 
-  F acc[4][4];
+  F acc[4][CJ];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = (F)0;
+    for (int j = 0; j < CJ; ++j) acc[i][j] = (F)0;
 
   const int lm = tid % BM;       // pixel handled in the col loader
   const int lk0 = tid / BM;      // first channel row handled (stride 4)
@@ -123,7 +126,7 @@ __global__ void __launch_bounds__(NT) k_generic_forward(const DevGeom g, const T
         }
         // ---- weight chunk ----
 #pragma unroll
-        for (int i = 0; i < BN / 16; ++i) {
+        for (int i = 0; i < BNT / 16; ++i) {
           const int n = wn0 + 16 * i;
           const int cl = c0 + wk;
           F v = (F)0;
@@ -133,15 +136,15 @@ __global__ void __launch_bounds__(NT) k_generic_forward(const DevGeom g, const T
         __syncthreads();
 #pragma unroll
         for (int kk = 0; kk < BK; ++kk) {
-          F a[4], bq[4];
+          F a[4], bq[CJ];
 #pragma unroll
           for (int i = 0; i < 4; ++i) a[i] = As[kk][tx * 4 + i];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) bq[j] = Bs[kk][ty * 4 + j];
+          for (int j = 0; j < CJ; ++j) bq[j] = Bs[kk][ty * CJ + j];
 #pragma unroll
           for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * bq[j];
+            for (int j = 0; j < CJ; ++j) acc[i][j] += a[i] * bq[j];
         }
         __syncthreads();
       }
@@ -150,8 +153,8 @@ __global__ void __launch_bounds__(NT) k_generic_forward(const DevGeom g, const T
   }
 
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int n = n0 + ty * 4 + j;
+  for (int j = 0; j < CJ; ++j) {
+    const int n = n0 + ty * CJ + j;
     if (n >= g.Cog) continue;
     const int co = grp * g.Cog + n;
     const F bv = g.with_bias ? ld_as<F>(bias + co) : (F)0;
@@ -444,10 +447,16 @@ template <typename T, typename F, int ND, bool MOD>
 void launch_forward(const DevGeom& g, const void* x, const void* w, const void* bias, const void* off,
                     const void* mask, void* y, LaunchCtx& ctx) {
   const int tilesP = (g.P + BM - 1) / BM;
-  dim3 grid((unsigned)(g.B * tilesP), (unsigned)((g.Cog + BN - 1) / BN), (unsigned)g.g);
   ProfScope prof(ctx, "generic_forward");
-  k_generic_forward<T, F, ND, MOD><<<grid, NT, 0, ctx.stream>>>(g, (const T*)x, (const T*)w, (const T*)bias,
-                                                                (const T*)off, (const T*)mask, (T*)y);
+  if (g.Cog >= 96 && sizeof(F) == 4) {   // wide tile: 128 output channels (the fp64 build keeps the 64-wide one)
+    dim3 grid((unsigned)(g.B * tilesP), (unsigned)((g.Cog + 127) / 128), (unsigned)g.g);
+    k_generic_forward<T, F, ND, MOD, 128><<<grid, NT, 0, ctx.stream>>>(g, (const T*)x, (const T*)w, (const T*)bias,
+                                                                       (const T*)off, (const T*)mask, (T*)y);
+  } else {
+    dim3 grid((unsigned)(g.B * tilesP), (unsigned)((g.Cog + BN - 1) / BN), (unsigned)g.g);
+    k_generic_forward<T, F, ND, MOD, BN><<<grid, NT, 0, ctx.stream>>>(g, (const T*)x, (const T*)w, (const T*)bias,
+                                                                      (const T*)off, (const T*)mask, (T*)y);
+  }
   MDCONV_CHECK_LAUNCH(ctx);
 }
 

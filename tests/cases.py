@@ -73,6 +73,7 @@ CASES_2D = [
     Case("m2d_all_oob", 2, True, offset_bias=1.0e4, seed=9),
     Case("m2d_b1_c64", 2, True, B=1, C=64, Co=64, size=(10, 12), seed=10),
     Case("m2d_odd_tiles", 2, True, B=2, C=6, Co=70, size=(11, 13), seed=11),
+    Case("m2d_co130_wide_tile", 2, True, B=1, C=6, Co=130, size=(9, 7), seed=12),   # 128-wide SIMT forward tile + tail
     Case("d2d_base", 2, False, g=2, dg=2, seed=20),
     Case("d2d_nobias", 2, False, B=1, bias=False, seed=21),
     Case("d2d_stride2_dg4", 2, False, C=16, Co=16, size=(10, 10), s=(2, 2), g=4, dg=4, seed=22),
