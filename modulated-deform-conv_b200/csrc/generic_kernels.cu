@@ -44,17 +44,23 @@ __global__ void __launch_bounds__(NT) k_generic_forward(const DevGeom g, const T
   __shared__ int Pi[NC][BM];
   __shared__ F Pw[NC][BM];
 
-  const int tilesP = (g.P + BM - 1) / BM;
-  const int b = blockIdx.x / tilesP;
-  const int p0 = (blockIdx.x % tilesP) * BM;
+  // pixel tiles run over the flattened (sample, position) index, so a tile may straddle two samples and no
+  // tile is partly empty except the very last one (P = 196 would otherwise waste 23 % of every 4th tile)
+  const long long total_pix = (long long)g.B * g.P;
+  const long long gp0 = (long long)blockIdx.x * BM;
   const int n0 = blockIdx.y * BNT;
   const int grp = blockIdx.z;
   const int tid = threadIdx.x;
   const int tx = tid % 16, ty = tid / 16;
 
-  const T* x_b = x + (size_t)b * g.C * g.IN;
-  const T* off_b = off + (size_t)b * g.dg * ND * g.K * g.P;
-  const T* mask_b = MOD ? mask + (size_t)b * g.dg * g.K * g.P : nullptr;
+  // the plan threads (tid < BM) own one pixel each: its sample, position and per-sample offset / mask bases
+  const long long my_gp = gp0 + (tid < BM ? tid : 0);
+  const bool my_valid = tid < BM && my_gp < total_pix;
+  const int my_b = my_valid ? (int)(my_gp / g.P) : 0;
+  const int my_p = my_valid ? (int)(my_gp - (long long)my_b * g.P) : 0;
+  const T* off_b = off + (size_t)my_b * g.dg * ND * g.K * g.P;
+  const T* mask_b = MOD ? mask + (size_t)my_b * g.dg * g.K * g.P : nullptr;
+  const int x_base = my_b * g.C * g.IN;   // folded into the corner indices (all tensors are < 2^31 elements)
 
   F acc[4][CJ];
 #pragma unroll
@@ -78,10 +84,10 @@ __global__ void __launch_bounds__(NT) k_generic_forward(const DevGeom g, const T
       // ---- plan of (pixel, tap, dgi) ----
       __syncthreads();  // previous users of Pi / Pw are done
       if (tid < BM) {
-        const int p = p0 + tid;
+        const int p = my_p;
 #pragma unroll
         for (int c = 0; c < NC; ++c) { Pi[c][tid] = 0; Pw[c][tid] = (F)0; }
-        if (p < g.P) {
+        if (my_valid) {
           SamplePoint<ND, F> sp;
           make_sample_point<ND, T, F>(g, off_b, dgi, tap, p, sp);
           if (sp.in_range) {
@@ -100,7 +106,7 @@ __global__ void __launch_bounds__(NT) k_generic_forward(const DevGeom g, const T
                 wgt *= hi ? sp.fr[a] : ((F)1 - sp.fr[a]);
                 idx = idx * g.in[a] + ia;
               }
-              if (ok) { Pi[c][tid] = idx; Pw[c][tid] = wgt; }
+              if (ok) { Pi[c][tid] = x_base + idx; Pw[c][tid] = wgt; }
             }
           }
         }
@@ -118,7 +124,7 @@ __global__ void __launch_bounds__(NT) k_generic_forward(const DevGeom g, const T
           const int cl = c0 + lk0 + 4 * i;
           F v = (F)0;
           if (cl < cl1) {
-            const T* plane = x_b + (size_t)(grp * g.Cg + cl) * g.IN;
+            const T* plane = x + (size_t)(grp * g.Cg + cl) * g.IN;
 #pragma unroll
             for (int c = 0; c < NC; ++c) v += pw[c] * ld_as<F>(plane + pi[c]);
           }
@@ -158,11 +164,14 @@ __global__ void __launch_bounds__(NT) k_generic_forward(const DevGeom g, const T
     if (n >= g.Cog) continue;
     const int co = grp * g.Cog + n;
     const F bv = g.with_bias ? ld_as<F>(bias + co) : (F)0;
-    T* yrow = y + ((size_t)b * g.Co + co) * g.P;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int p = p0 + tx * 4 + i;
-      if (p < g.P) yrow[p] = cvt_to<T, F>(acc[i][j] + bv);
+      const long long gp = gp0 + tx * 4 + i;
+      if (gp < total_pix) {
+        const int bb = (int)(gp / g.P);
+        const int p = (int)(gp - (long long)bb * g.P);
+        y[((size_t)bb * g.Co + co) * g.P + p] = cvt_to<T, F>(acc[i][j] + bv);
+      }
     }
   }
 }
@@ -446,14 +455,14 @@ BwdSizes bwd_sizes(const DevGeom& g) {
 template <typename T, typename F, int ND, bool MOD>
 void launch_forward(const DevGeom& g, const void* x, const void* w, const void* bias, const void* off,
                     const void* mask, void* y, LaunchCtx& ctx) {
-  const int tilesP = (g.P + BM - 1) / BM;
+  const unsigned tiles = (unsigned)(((long long)g.B * g.P + BM - 1) / BM);
   ProfScope prof(ctx, "generic_forward");
   if (g.Cog >= 96 && sizeof(F) == 4) {   // wide tile: 128 output channels (the fp64 build keeps the 64-wide one)
-    dim3 grid((unsigned)(g.B * tilesP), (unsigned)((g.Cog + 127) / 128), (unsigned)g.g);
+    dim3 grid(tiles, (unsigned)((g.Cog + 127) / 128), (unsigned)g.g);
     k_generic_forward<T, F, ND, MOD, 128><<<grid, NT, 0, ctx.stream>>>(g, (const T*)x, (const T*)w, (const T*)bias,
                                                                        (const T*)off, (const T*)mask, (T*)y);
   } else {
-    dim3 grid((unsigned)(g.B * tilesP), (unsigned)((g.Cog + BN - 1) / BN), (unsigned)g.g);
+    dim3 grid(tiles, (unsigned)((g.Cog + BN - 1) / BN), (unsigned)g.g);
     k_generic_forward<T, F, ND, MOD, BN><<<grid, NT, 0, ctx.stream>>>(g, (const T*)x, (const T*)w, (const T*)bias,
                                                                       (const T*)off, (const T*)mask, (T*)y);
   }
