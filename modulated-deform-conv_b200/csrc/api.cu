@@ -1,5 +1,6 @@
 // api.cu -- C ABI of libmdconv_b200.so (see include/mdconv_b200.h): validation, geometry
 // resolution, path selection and the reference's eight entry-point names.
+#include <stdlib.h>
 #include <stdio.h>
 #include <string.h>
 

@@ -212,12 +212,18 @@ struct LaunchCtx {
   cudaEvent_t weight_ready = nullptr;
   // backward only: the join event of a side-stream fork made earlier in this call (nullptr: nothing forked)
   cudaEvent_t side_join = nullptr;
+  // SMs the persistent kernels launched from now on leave free (set once the weight-ready event has been
+  // recorded: the caller's all-reduce kernel needs somewhere to run while the data gradients are computed)
+  int spare_sms = 0;
 };
+// SMs left to a concurrent collective after the weight-ready event (MDCONV_B200_COMM_SMS, default 8; api.cu)
+int comm_spare_sms();
 inline void signal_weight_ready(LaunchCtx& ctx) {
   if (ctx.weight_ready != nullptr) {
     cudaError_t e = cudaEventRecord(ctx.weight_ready, ctx.stream);
     if (e != cudaSuccess && ctx.err == cudaSuccess) ctx.err = e;
     ctx.weight_ready = nullptr;
+    ctx.spare_sms = comm_spare_sms();
   }
 }
 

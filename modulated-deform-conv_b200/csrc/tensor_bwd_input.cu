@@ -692,7 +692,8 @@ void tensor_grad_input(const DevGeom& g, const void* w, const void* go, void* gx
     if (e != cudaSuccess && ctx.err == cudaSuccess) ctx.err = e;
     configured = true;
   }
-  const int grid = prm.total_tiles < sm_count() ? prm.total_tiles : sm_count();
+  const int sms = sm_count() - ctx.spare_sms > 0 ? sm_count() - ctx.spare_sms : 1;
+  const int grid = prm.total_tiles < sms ? prm.total_tiles : sms;
   ProfScope prof(ctx, "tc_grad_input");
   k_tc_grad_input<T><<<grid, GI_THREADS, smem, ctx.stream>>>(tmap, prm);
   MDCONV_CHECK_LAUNCH(ctx);

@@ -481,7 +481,8 @@ void launch_grad_sample(const CUtensorMap& tmap_go, const CUtensorMap& tmap_w, c
     if (e != cudaSuccess && ctx.err == cudaSuccess) ctx.err = e;
     configured = true;
   }
-  const int grid = prm.items < sm_count() ? (int)prm.items : sm_count();
+  const int sms = sm_count() - ctx.spare_sms > 0 ? sm_count() - ctx.spare_sms : 1;
+  const int grid = prm.items < sms ? (int)prm.items : sms;
   ProfScope prof(ctx, "tc_grad_sample");
   k_tc_grad_sample<T, ND, MOD><<<grid, GS_THREADS, smem, ctx.stream>>>(tmap_go, tmap_w, prm);
   MDCONV_CHECK_LAUNCH(ctx);

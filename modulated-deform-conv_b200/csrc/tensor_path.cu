@@ -613,6 +613,15 @@ template void launch_reorder_weight<__nv_bfloat16>(const __nv_bfloat16*, __nv_bf
 
 }  // namespace tc
 
+int comm_spare_sms() {
+  static const int n = [] {
+    const char* e = getenv("MDCONV_B200_COMM_SMS");
+    const int v = e ? atoi(e) : 8;
+    return v < 0 ? 0 : (v > 64 ? 64 : v);
+  }();
+  return n;
+}
+
 bool tensor_path_supported(const DevGeom& g, int dtype, int backward) {
   if (dtype != MDCONV_F16 && dtype != MDCONV_BF16) return false;
   if (g.Cg % TC_BK != 0 || g.Cdg % TC_BK != 0) return false;
