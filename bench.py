@@ -470,6 +470,23 @@ def main():
     e2e_value = (B * world) / (ms_e2e / ke * 1e-3) / 1e6
     clocks.stop()
 
+    # ---- N > 1: the in-backward all-reduce must equal an explicit all-reduce of the local gradients ----
+    allreduce_check = None
+    if world > 1:
+        sync_obj = getattr(mod, "_grad_sync", None)
+        mod._grad_sync = None                       # local gradients only
+        step_resident()
+        expect = mod.weight.grad.detach().float().clone()
+        dist.all_reduce(expect, op=dist.ReduceOp.SUM)
+        mod._grad_sync = sync_obj
+        step_resident()
+        got = mod.weight.grad.detach().float()
+        torch.cuda.synchronize()
+        err = float((got - expect).abs().max() / expect.abs().max())
+        allreduce_check = {"rel_err_vs_explicit_allreduce": err, "ok": bool(err < 5e-3)}
+        if not allreduce_check["ok"]:
+            raise SystemExit(f"in-backward all-reduce differs from the explicit one: {err}")
+
     # ---- per-kernel durations (CUDA events on the launching stream, inside the library) ----
     MDCONV_CUDA.profile_enable(True)
     kt = {}
@@ -556,7 +573,8 @@ def main():
                                "(3 streams, double-buffered); fill and drain included"},
                 "gpu_launches": n_launch, "clocks": clocks.summary(), "roofline": roofline, "roofline_kernels": roofline_kernels,
                 "roofline_hbm": roofline_hbm,
-                "kernels_ms_per_step": kernels, "cpu_baseline": cpu_base, "reference_cuda": ref_cuda}
+                "kernels_ms_per_step": kernels, "cpu_baseline": cpu_base, "reference_cuda": ref_cuda,
+                "allreduce_check": allreduce_check}
         _emit(line)
     if world > 1:
         dist.barrier()
