@@ -4,6 +4,7 @@ names.  No compute calls here."""
 import ctypes
 import os
 import re
+import sys
 
 import pytest
 import torch
@@ -125,3 +126,17 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
+
+
+def test_bench_algorithmic_figures_match_the_survey():
+    """bench.py's per-launch algorithmic bytes / FLOPs are SURVEY 8(d)'s figures (cfg2: fwd 109.36 MB, bwd 167.34 MB,
+    118.38 GFLOP per contraction; cfg3 35.38 / 64.33 MB, 3.70 GFLOP; cfg4 79.09 / 124.62 MB, 57.98 GFLOP)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    want = {"cfg2": (109.36e6, 167.34e6, 118.38e9), "cfg3": (35.38e6, 64.33e6, 3.70e9), "cfg4": (79.09e6, 124.62e6, 57.98e9)}
+    for name, (bf, bb, fl) in want.items():
+        w = bench.WORKLOADS[name]
+        es = {"f16": 2, "f32": 4}[w["dtype"]]
+        got_bf, got_bb, got_ff, got_fb = bench.algorithmic(w, w["B"], es)
+        assert abs(got_bf - bf) / bf < 2e-3 and abs(got_bb - bb) / bb < 2e-3, (name, got_bf, got_bb)
+        assert abs(got_ff - fl) / fl < 2e-3 and got_fb == 2 * got_ff, (name, got_ff)
