@@ -33,14 +33,6 @@ __all__ = [
 ]
 
 
-def _infer_shape(input, weight, stride, padding, dilation):
-    """reference: modulated_deform_conv.py:83-91 / :250-260."""
-    spatial = tuple(
-        (i + 2 * p - (d * (k - 1) + 1)) // s + 1
-        for i, k, s, p, d in zip(input.shape[2:], weight.shape[2:], stride, padding, dilation))
-    return (input.size(0), weight.size(0)) + spatial
-
-
 def _setup(ctx, ntuple, input, bias, stride, padding, dilation, groups, deformable_groups, in_step):
     ctx.stride = ntuple(stride)
     ctx.padding = ntuple(padding)
@@ -54,11 +46,6 @@ def _setup(ctx, ntuple, input, bias, stride, padding, dilation, groups, deformab
     if not input.is_cuda:
         raise NotImplementedError
     return bias
-
-
-def _geometry_args(ctx, weight):
-    return (*weight.shape[2:], *ctx.stride, *ctx.padding, *ctx.dilation, ctx.groups, ctx.deformable_groups,
-            ctx.in_step, ctx.with_bias)
 
 
 def _needs_grad(*tensors):
