@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(NT) k_generic_forward(const DevGeom g, const T
       if (tid < BM) {
         const int p = my_p;
 #pragma unroll
-        for (int c = 0; c < NC; ++c) { Pi[c][tid] = 0; Pw[c][tid] = (F)0; }
+        for (int c = 0; c < NC; ++c) { Pi[c][tid] = -1; Pw[c][tid] = (F)0; }   // -1: absent corner, never loaded
         if (my_valid) {
           SamplePoint<ND, F> sp;
           make_sample_point<ND, T, F>(g, off_b, dgi, tap, p, sp);
@@ -126,7 +126,8 @@ __global__ void __launch_bounds__(NT) k_generic_forward(const DevGeom g, const T
           if (cl < cl1) {
             const T* plane = x + (size_t)(grp * g.Cg + cl) * g.IN;
 #pragma unroll
-            for (int c = 0; c < NC; ++c) v += pw[c] * ld_as<F>(plane + pi[c]);
+            for (int c = 0; c < NC; ++c)
+              if (pi[c] >= 0) v += pw[c] * ld_as<F>(plane + pi[c]);   // absent corners contribute an exact 0
           }
           As[lk0 + 4 * i][lm] = v;
         }

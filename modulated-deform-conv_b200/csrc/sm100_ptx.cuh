@@ -25,8 +25,31 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// Build-time tuning knobs (scripts/build_variants.sh measures them; the defaults are what the measurements chose):
+//   MDCONV_TRYWAIT_HINT_NS  suspend-time hint of mbarrier.try_wait: how long the hardware may keep the thread asleep
+//                           waiting for the phase before it returns false and the loop polls again (0: no hint)
+//   MDCONV_ELECT_ARRIVE     1: every multi-thread mbarrier is armed with one arrival per WARP (lane 0 arrives after
+//                           a __syncwarp), 0: one arrival per thread
+#ifndef MDCONV_TRYWAIT_HINT_NS
+#define MDCONV_TRYWAIT_HINT_NS 0
+#endif
+#ifndef MDCONV_ELECT_ARRIVE
+#define MDCONV_ELECT_ARRIVE 0
+#endif
+
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+#if MDCONV_TRYWAIT_HINT_NS > 0
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)MDCONV_TRYWAIT_HINT_NS)
+      : "memory");
+#else
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
@@ -36,7 +59,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
+#endif
   return ok != 0;
+}
+// Arrival of a WHOLE WARP on a barrier armed with arrivals(n_threads): either every lane arrives, or the lanes
+// synchronise (their shared-memory accesses and proxy fences are ordered before lane 0's release-arrive by
+// __syncwarp) and lane 0 arrives for all of them.  Must be executed by all 32 lanes (warp-uniform control flow).
+__host__ __device__ constexpr uint32_t arrivals(uint32_t n_threads) {
+#if MDCONV_ELECT_ARRIVE
+  return n_threads / 32;
+#else
+  return n_threads;
+#endif
+}
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar) {
+#if MDCONV_ELECT_ARRIVE
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+#else
+  mbar_arrive(bar);
+#endif
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {

@@ -1,6 +1,7 @@
 // tc_common.cuh -- pieces shared by the tcgen05 kernels (forward, grad-weight, grad-data):
 // the per-(pixel, tap) sampling plan, the 8-channel corner gather, and the pre-pass kernels.
 #pragma once
+#include <atomic>
 #include <type_traits>
 
 #include "common.cuh"
@@ -12,6 +13,12 @@ namespace tc {
 constexpr int BK = 64;  // K elements per block = 128 bytes = one 128B-swizzle row
 
 inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// Channels-last copy of the input: B*IN positions x C channels, plus ONE all-zero position at the end.  The sampling
+// plans point every absent corner (sample out of range, corner outside the input) at that position: the reference
+// returns an exact 0 there WITHOUT reading the input (src/mdeformable_conv.cu:19-29,80), so an Inf/NaN elsewhere in x
+// must not turn into 0 * Inf = NaN through a zero-weight load of some unrelated pixel.
+inline size_t xt_bytes(const DevGeom& g) { return align256(((size_t)g.B * g.IN + 1) * g.C * 2); }
 
 // ---- explicit shared-state-space accesses (generic LD/ST through a computed pointer is slower) ----
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
@@ -38,7 +45,7 @@ __device__ __forceinline__ uint32_t sw128(int row, int chunk) {
 template <int ND>
 struct __align__(16) PlanEntry {
   int idx[1 << ND];
-  uint32_t w[1 << ND];  // fp16: half2 pair (w, w); bf16: fp32 bits
+  uint32_t w[1 << ND];  // the weight x mask twice, in the storage dtype: half2 (w, w) / bfloat162 (w, w)
 };
 
 template <int ND>
@@ -68,7 +75,10 @@ __device__ __forceinline__ uint32_t pack_w(float w, __half) {
   __half2 h = __float2half2_rn(w);
   return *reinterpret_cast<uint32_t*>(&h);
 }
-__device__ __forceinline__ uint32_t pack_w(float w, __nv_bfloat16) { return __float_as_uint(w); }
+__device__ __forceinline__ uint32_t pack_w(float w, __nv_bfloat16) {
+  __nv_bfloat162 h = __float2bfloat162_rn(w);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
 
 // Sampling position of (row, tap): floor, fraction, range flag, mask value.
 template <int ND>
@@ -135,8 +145,9 @@ template <typename T, int ND>
 __device__ __forceinline__ PlanEntry<ND> plan_from_pos(const DevGeom& g, const RowCoord<ND>& rc,
                                                        const SamplePos<ND>& sp, int C8) {
   PlanEntry<ND> e;
+  const int zero_pos = g.B * g.IN * C8;   // the all-zero position behind the last sample (xt_bytes)
 #pragma unroll
-  for (int c = 0; c < (1 << ND); ++c) { e.idx[c] = 0; e.w[c] = 0u; }
+  for (int c = 0; c < (1 << ND); ++c) { e.idx[c] = zero_pos; e.w[c] = 0u; }
   if (!rc.valid || !sp.in_range) return e;
 #pragma unroll
   for (int c = 0; c < (1 << ND); ++c) {
@@ -185,39 +196,26 @@ __device__ __forceinline__ PlanEntry<ND> load_plan(uint32_t saddr) {
 }
 
 // ---- 8-channel interpolation ------------------------------------------------------------------------
-// fp16: packed HFMA2 with half2 weights; bf16: fp32 FMAs (8 mantissa bits cannot hold four products).
-__device__ __forceinline__ uint4 interp8(const uint4* v, const uint32_t* w, int nc, __half) {
-  uint4 acc = make_uint4(0u, 0u, 0u, 0u);
-  __half2* a = reinterpret_cast<__half2*>(&acc);
+// Packed HFMA2 in the storage dtype (HFMA2 for fp16, HFMA2.BF16 for bf16) with the weight x mask broadcast to both
+// halves: 4 instructions per corner for 8 channels.  The result feeds a 16-bit tensor-core operand anyway; the extra
+// roundings of the 4- / 8-term sum stay well inside the parity bars (profiles/r2_parity_margins.json).
+template <typename H2>
+__device__ __forceinline__ uint4 interp8_packed(const uint4* v, const uint32_t* w, int nc) {
+  uint4 acc = make_uint4(0u, 0u, 0u, 0u);   // +0.0 in both formats
+  H2* a = reinterpret_cast<H2*>(&acc);
   for (int c = 0; c < nc; ++c) {
-    const __half2 wh = *reinterpret_cast<const __half2*>(&w[c]);
-    const __half2* x = reinterpret_cast<const __half2*>(&v[c]);
+    const H2 wh = *reinterpret_cast<const H2*>(&w[c]);
+    const H2* x = reinterpret_cast<const H2*>(&v[c]);
 #pragma unroll
     for (int i = 0; i < 4; ++i) a[i] = __hfma2(wh, x[i], a[i]);
   }
   return acc;
 }
+__device__ __forceinline__ uint4 interp8(const uint4* v, const uint32_t* w, int nc, __half) {
+  return interp8_packed<__half2>(v, w, nc);
+}
 __device__ __forceinline__ uint4 interp8(const uint4* v, const uint32_t* w, int nc, __nv_bfloat16) {
-  float acc[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  for (int c = 0; c < nc; ++c) {
-    const float wf = __uint_as_float(w[c]);
-    const uint32_t* x = reinterpret_cast<const uint32_t*>(&v[c]);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      acc[2 * i] = fmaf(wf, __uint_as_float(x[i] << 16), acc[2 * i]);
-      acc[2 * i + 1] = fmaf(wf, __uint_as_float(x[i] & 0xFFFF0000u), acc[2 * i + 1]);
-    }
-  }
-  uint4 r;
-  uint32_t* o = reinterpret_cast<uint32_t*>(&r);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    __nv_bfloat162 p = __floats2bfloat162_rn(acc[2 * i], acc[2 * i + 1]);
-    o[i] = *reinterpret_cast<uint32_t*>(&p);
-  }
-  return r;
+  return interp8_packed<__nv_bfloat162>(v, w, nc);
 }
 
 // column value (8 channels) of one plan entry; xc already points at the channel chunk
@@ -230,7 +228,9 @@ __device__ __forceinline__ uint4 gather8(const uint4* __restrict__ xc, const Pla
 }
 
 // ---- pre-pass kernels (tensor_path.cu) ----------------------------------------------------------------
-template <typename T> void launch_to_channels_last(const T* x, T* xt, int B, int C, int IN, LaunchCtx& ctx);
+// zero_row: also clear the extra all-zero position behind the last sample (xt_bytes)
+template <typename T> void launch_to_channels_last(const T* x, T* xt, int B, int C, int IN, LaunchCtx& ctx,
+                                                   bool zero_row = false);
 // W [Co][Cg][K] -> Wr [Co][(cc*K + tap)*64 + ci]   (c = cc*64 + ci)
 template <typename T> void launch_reorder_weight(const T* w, T* wr, int Co, int Cg, int K, LaunchCtx& ctx);
 
@@ -238,7 +238,25 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 PFN_encodeTiled get_encode_fn();
-int sm_count();
+int sm_count();   // of the CURRENT device (cached per device ordinal)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute of a kernel: opt in once per
+// (kernel instantiation, device ordinal).  `seen` is a function-local static bitmask of the ordinals already done;
+// two threads racing on the first call both set the attribute, which is harmless.
+template <typename Kernel>
+inline void opt_in_dynamic_smem(Kernel* kernel, size_t smem, std::atomic<unsigned long long>& seen, LaunchCtx& ctx) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  const bool tracked = dev >= 0 && dev < 64;
+  const unsigned long long bit = tracked ? (1ull << dev) : 0ull;
+  if (tracked && (seen.load(std::memory_order_acquire) & bit)) return;
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    if (ctx.err == cudaSuccess) ctx.err = e;
+    return;
+  }
+  if (tracked) seen.fetch_or(bit, std::memory_order_release);
+}
 
 template <typename T>
 inline CUtensorMapDataType tmap_dtype() {
@@ -270,7 +288,7 @@ bool tensor_backward_supported(const DevGeom& g, int dtype);
 bool grad_sample_supported(const DevGeom& g);
 template <typename T>
 void tensor_grad_sample(const DevGeom& g, const T* xt, const T* wr, const void* off, const void* mask, const void* go,
-                        void* goff, void* gmask, LaunchCtx& ctx);
+                        int go_ld, void* goff, void* gmask, LaunchCtx& ctx);
 // grad_input (tensor_bwd_input.cu)
 bool grad_input_supported(const DevGeom& g);
 size_t grad_input_workspace(const DevGeom& g);

@@ -86,12 +86,12 @@ k_tc_grad_weight(const __grid_constant__ CUtensorMap tmap_go, const TcGwParams p
     ptx::prefetch_tensormap(&tmap_go);
     for (int s = 0; s < GW_STAGES; ++s) {
       ptx::mbar_init(&full_go[s], 1);
-      ptx::mbar_init(&full_col[s], GW_GATHER_THREADS);
+      ptx::mbar_init(&full_col[s], ptx::arrivals(GW_GATHER_THREADS));
       ptx::mbar_init(&empty[s], 1);
     }
     for (int s = 0; s < GW_PLAN_SLOTS; ++s) {
-      ptx::mbar_init(&plan_full[s], 128);
-      ptx::mbar_init(&plan_empty[s], GW_GATHER_THREADS);
+      ptx::mbar_init(&plan_full[s], ptx::arrivals(128));
+      ptx::mbar_init(&plan_empty[s], ptx::arrivals(GW_GATHER_THREADS));
     }
     ptx::mbar_init(done, 1);
     ptx::fence_barrier_init();
@@ -191,7 +191,7 @@ k_tc_grad_weight(const __grid_constant__ CUtensorMap tmap_go, const TcGwParams p
         const PlanEntry<ND> e = plan_from_pos<T, ND>(g, rc, sp, C8);
         ptx::mbar_wait_relaxed(&plan_empty[ps], pph ^ 1, 128);
         store_plan<ND>(ptx::smem_u32(sPlan + ps * 128 + pt), e);
-        ptx::mbar_arrive(&plan_full[ps]);
+        ptx::mbar_arrive_warp(&plan_full[ps]);
       }
     }
     if (warp < 8) {
@@ -276,8 +276,8 @@ k_tc_grad_weight(const __grid_constant__ CUtensorMap tmap_go, const TcGwParams p
         sts128(col_addr + sw128(r0 + 4, chunk), interp8(v1, w1, NC, T()));
       }
       ptx::fence_proxy_async_smem();
-      ptx::mbar_arrive(&full_col[s]);
-      ptx::mbar_arrive(&plan_empty[cps]);
+      ptx::mbar_arrive_warp(&full_col[s]);
+      ptx::mbar_arrive_warp(&plan_empty[cps]);
       if (++s == GW_STAGES) { s = 0; ph ^= 1; }
       if (++cps == GW_PLAN_SLOTS) cps = 0;
     };
@@ -324,6 +324,19 @@ __global__ void k_reduce_grad_weight(const float* __restrict__ part, T* __restri
   }
 }
 
+// grad_output rows [B*Co][P] -> [B*Co][ld] with a zero tail (ld = P rounded up to 8 elements): TMA needs every
+// global stride to be a multiple of 16 bytes, which NCHW rows of 14x14 / 7x7 / odd maps are not.
+template <typename T>
+__global__ void __launch_bounds__(256) k_pad_rows(const T* __restrict__ src, T* __restrict__ dst, size_t rows, int P,
+                                                  int ld) {
+  const size_t n = rows * (size_t)ld;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / ld;
+    const int p = (int)(i - r * ld);
+    dst[i] = p < P ? src[r * P + p] : cvt_to<T, float>(0.f);
+  }
+}
+
 int gw_splits(const DevGeom& g) {
   const int nblocks = (g.Cg / BK) * g.K;
   const int n_tiles = (nblocks + GW_NB - 1) / GW_NB;
@@ -347,13 +360,8 @@ size_t gw_smem_bytes() {
 template <typename T, int ND, bool MOD>
 void launch_grad_weight(const CUtensorMap& tmap, const TcGwParams& prm, int grid, LaunchCtx& ctx) {
   const size_t smem = gw_smem_bytes<ND>();
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e =
-        cudaFuncSetAttribute(k_tc_grad_weight<T, ND, MOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess && ctx.err == cudaSuccess) ctx.err = e;
-    configured = true;
-  }
+  static std::atomic<unsigned long long> configured{0};
+  opt_in_dynamic_smem(k_tc_grad_weight<T, ND, MOD>, smem, configured, ctx);
   ProfScope prof(ctx, "tc_grad_weight");
   k_tc_grad_weight<T, ND, MOD><<<grid, GW_THREADS, smem, ctx.stream>>>(tmap, prm);
   MDCONV_CHECK_LAUNCH(ctx);
@@ -362,19 +370,24 @@ void launch_grad_weight(const CUtensorMap& tmap, const TcGwParams& prm, int grid
 }  // namespace
 
 bool tensor_backward_supported(const DevGeom& g, int dtype) {
-  (void)dtype;
-  if (g.P % 8 != 0) return false;  // TMA global strides of grad_output must be multiples of 16 bytes
-  return true;
+  (void)g; (void)dtype;
+  return true;   // maps with P % 8 != 0 go through a row-padded copy of grad_output (go_ld)
+}
+
+// leading dimension (elements) of the grad_output rows the TMA maps see, and the bytes of the padded copy
+int go_ld(const DevGeom& g) { return (g.P + 7) & ~7; }
+static size_t go_pad_bytes(const DevGeom& g) {
+  return g.P % 8 == 0 ? 0 : align256((size_t)g.B * g.Co * go_ld(g) * 2);
 }
 
 static bool data_on_tensor_cores(const DevGeom& g) { return grad_sample_supported(g) && grad_input_supported(g); }
 
 size_t tensor_backward_workspace(const DevGeom& g) {
-  const size_t xt = align256((size_t)g.B * g.C * g.IN * 2);
+  const size_t xt = xt_bytes(g);
   const size_t wr = align256((size_t)g.Co * g.Kg * 2);
   const size_t part = align256((size_t)gw_splits(g) * g.Co * g.Kg * sizeof(float));
   const size_t data = data_on_tensor_cores(g) ? grad_input_workspace(g) : generic_workspace_bytes(g, MDCONV_F16, 1);
-  return xt + wr + part + data;
+  return xt + wr + part + go_pad_bytes(g) + data;
 }
 
 template <typename T>
@@ -383,17 +396,30 @@ void tensor_backward_t(const DevGeom& g, const void* x, const void* w, const voi
                        LaunchCtx& ctx) {
   char* base = reinterpret_cast<char*>(ws);
   const T* xt = reinterpret_cast<const T*>(base);
-  base += align256((size_t)g.B * g.C * g.IN * sizeof(T));
+  base += xt_bytes(g);
   const T* wr = reinterpret_cast<const T*>(base);
   base += align256((size_t)g.Co * g.Kg * sizeof(T));
   if (saved != nullptr) {
     // the forward of this very call pair left both layouts in its workspace (same offsets: tensor_forward_t)
     xt = reinterpret_cast<const T*>(saved);
-    wr = reinterpret_cast<const T*>(reinterpret_cast<const char*>(saved) + align256((size_t)g.B * g.C * g.IN * sizeof(T)));
+    wr = reinterpret_cast<const T*>(reinterpret_cast<const char*>(saved) + xt_bytes(g));
   }
   const int S = gw_splits(g);
   float* part = reinterpret_cast<float*>(base);
   base += align256((size_t)S * g.Co * g.Kg * sizeof(float));
+  // grad_output as the TMA maps read it: the caller's tensor, or a copy with rows padded to 16 bytes
+  const int ld = go_ld(g);
+  const void* go_tma = go;
+  if (g.P % 8 != 0) {
+    T* gp = reinterpret_cast<T*>(base);
+    base += go_pad_bytes(g);
+    ProfScope prof(ctx, "pad_grad_output");
+    const size_t rows = (size_t)g.B * g.Co, n = rows * ld;
+    const int blocks = (int)((n + 255) / 256 > 148 * 8 ? 148 * 8 : (n + 255) / 256);
+    k_pad_rows<T><<<blocks, 256, 0, ctx.stream>>>((const T*)go, gp, rows, g.P, ld);
+    MDCONV_CHECK_LAUNCH(ctx);
+    go_tma = gp;
+  }
   void* data_ws = base;
   const int dtype = std::is_same<T, __half>::value ? MDCONV_F16 : MDCONV_BF16;
   const bool data_tc = data_on_tensor_cores(g);
@@ -402,7 +428,7 @@ void tensor_backward_t(const DevGeom& g, const void* x, const void* w, const voi
   // layout passes and ahead of the big kernels
   if (data_tc) tensor_grad_input_prepare<T>(g, off, mask, data_ws, ctx);
   if (saved == nullptr) {
-    launch_to_channels_last<T>((const T*)x, const_cast<T*>(xt), g.B, g.C, g.IN, ctx);
+    launch_to_channels_last<T>((const T*)x, const_cast<T*>(xt), g.B, g.C, g.IN, ctx, /*zero_row=*/true);
     if (data_tc) launch_reorder_weight<T>((const T*)w, const_cast<T*>(wr), g.Co, g.Cg, g.K, ctx);
   }
 
@@ -425,10 +451,10 @@ void tensor_backward_t(const DevGeom& g, const void* x, const void* w, const voi
   }
   CUtensorMap tmap;
   const cuuint64_t dims[3] = {(cuuint64_t)g.P, (cuuint64_t)g.Co, (cuuint64_t)g.B};
-  const cuuint64_t strides[2] = {(cuuint64_t)g.P * sizeof(T), (cuuint64_t)g.Co * g.P * sizeof(T)};
+  const cuuint64_t strides[2] = {(cuuint64_t)ld * sizeof(T), (cuuint64_t)g.Co * ld * sizeof(T)};
   const cuuint32_t box[3] = {64, 128, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
-  const CUresult r = enc(&tmap, tmap_dtype<T>(), 3, const_cast<void*>(go), dims, strides, box, estr,
+  const CUresult r = enc(&tmap, tmap_dtype<T>(), 3, const_cast<void*>(go_tma), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -456,7 +482,7 @@ void tensor_backward_t(const DevGeom& g, const void* x, const void* w, const voi
 
   // ---- grad_offset / grad_mask / grad_input ----
   if (data_tc) {
-    tensor_grad_sample<T>(g, xt, wr, off, mask, go, goff, gmask, ctx);
+    tensor_grad_sample<T>(g, xt, wr, off, mask, go_tma, ld, goff, gmask, ctx);
     tensor_grad_input<T>(g, w, go, gx, data_ws, ctx);
   } else {
     generic_backward(g, dtype, x, w, off, mask, go, gx, gw, gb, goff, gmask, data_ws, ctx, GENERIC_BWD_DATA);

@@ -115,8 +115,12 @@ __device__ __forceinline__ void cswap(unsigned long long& a, unsigned long long&
   const unsigned long long lo = a < b ? a : b, hi = a < b ? b : a;
   a = lo; b = hi;
 }
+// Bins longer than GI_SORT_LOCAL entries (strongly clustered offsets) are not sorted here: their ids go to a work
+// list (`big`: [0] = count, [1..] = bin ids; it reuses the count array, which is all zero again after the fill
+// pass) and k_bin_sort_big sorts each with a whole block.
+constexpr int GI_SORT_LOCAL = 64;
 __global__ void __launch_bounds__(256) k_bin_sort(const int* __restrict__ start, BinEntry* __restrict__ entries,
-                                                  size_t nbins) {
+                                                  size_t nbins, int* __restrict__ big) {
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(entries);  // {row (low word), w} -> swap on use
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nbins; i += (size_t)gridDim.x * blockDim.x) {
     const int s = start[i], e = start[i + 1];
@@ -172,7 +176,7 @@ __global__ void __launch_bounds__(256) k_bin_sort(const int* __restrict__ start,
 #pragma unroll
       for (int a = 0; a < 16; ++a)
         if (a < n) keys[s + a] = (k[a] << 32) | (k[a] >> 32);
-    } else {
+    } else if (n <= GI_SORT_LOCAL) {
       for (int a = s + 1; a < e; ++a) {
         const BinEntry v = entries[a];
         int q = a - 1;
@@ -181,6 +185,35 @@ __global__ void __launch_bounds__(256) k_bin_sort(const int* __restrict__ start,
           --q;
         }
         entries[q + 1] = v;
+      }
+    } else {
+      big[1 + atomicAdd(big, 1)] = (int)i;   // at most nbins - 1 ids fit behind the counter; a bin id is < nbins
+    }
+  }
+}
+
+// One block per long bin: bitonic sorting network with every comparator ascending (partner i ^ (k-1) in the first
+// step of a merge, i ^ j afterwards), so the virtual padding up to a power of two is +infinity at the END and
+// comparators that touch it are no-ops.  O(n log^2 n / 256) steps per bin, straight on global memory.
+__global__ void __launch_bounds__(256) k_bin_sort_big(const int* __restrict__ start, BinEntry* __restrict__ entries,
+                                                      int* __restrict__ big) {
+  const int nbig = big[0];
+  for (int wi = blockIdx.x; wi < nbig; wi += gridDim.x) {
+    const int bin = big[1 + wi];
+    const int s = start[bin], n = start[bin + 1] - s;
+    BinEntry* e = entries + s;
+    unsigned np2 = 1;
+    while (np2 < (unsigned)n) np2 <<= 1;
+    for (unsigned k = 2; k <= np2; k <<= 1) {
+      for (unsigned j = k >> 1; j > 0; j >>= 1) {
+        for (unsigned i = threadIdx.x; i < np2; i += blockDim.x) {
+          const unsigned l = (j == (k >> 1)) ? (i ^ (k - 1)) : (i ^ j);
+          if (l > i && l < (unsigned)n) {
+            const BinEntry a = e[i], b = e[l];
+            if (a.row > b.row) { e[i] = b; e[l] = a; }
+          }
+        }
+        __syncthreads();
       }
     }
   }
@@ -198,8 +231,8 @@ struct TcGiParams {
   int kblocks;               // K * cobs
 };
 
-// 8-channel accumulator of the gather: packed half2 for fp16 (one HFMA2 per channel pair, as in the
-// forward gather), fp32 for bf16 (8 mantissa bits cannot carry a multi-term sum).
+// 8-channel accumulator of the gather: packed pairs in the storage dtype (one HFMA2 / HFMA2.BF16 per channel pair,
+// as in the forward gather).
 template <typename T> struct Acc8;
 template <> struct Acc8<__half> {
   __half2 a[4];
@@ -223,28 +256,23 @@ template <> struct Acc8<__half> {
   }
 };
 template <> struct Acc8<__nv_bfloat16> {
-  float a[8];
+  __nv_bfloat162 a[4];
   __device__ __forceinline__ void clear() {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = 0.f;
+    for (int i = 0; i < 4; ++i) a[i] = __float2bfloat162_rn(0.f);
   }
   __device__ __forceinline__ void fma(const uint4& v, __half w) { fma(v, __half2float(w)); }
   __device__ __forceinline__ void fma(const uint4& v, float w) {
-    const uint32_t* u = reinterpret_cast<const uint32_t*>(&v);
+    const __nv_bfloat162 wh = __float2bfloat162_rn(w);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      a[2 * i] = fmaf(w, __uint_as_float(u[i] << 16), a[2 * i]);
-      a[2 * i + 1] = fmaf(w, __uint_as_float(u[i] & 0xFFFF0000u), a[2 * i + 1]);
-    }
+    for (int i = 0; i < 4; ++i) a[i] = __hfma2(wh, h[i], a[i]);
   }
   __device__ __forceinline__ uint4 pack() const {
     uint4 r;
     uint32_t* o = reinterpret_cast<uint32_t*>(&r);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const __nv_bfloat162 h = __floats2bfloat162_rn(a[2 * i], a[2 * i + 1]);
-      o[i] = *reinterpret_cast<const uint32_t*>(&h);
-    }
+    for (int i = 0; i < 4; ++i) o[i] = *reinterpret_cast<const uint32_t*>(&a[i]);
     return r;
   }
 };
@@ -274,17 +302,17 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const TcGiParams pr
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_wt);
     for (int s = 0; s < GI_STAGES; ++s) {
-      ptx::mbar_init(&full_a[s], GI_GATHER_THREADS);
+      ptx::mbar_init(&full_a[s], ptx::arrivals(GI_GATHER_THREADS));
       ptx::mbar_init(&full_b[s], 1);
       ptx::mbar_init(&empty[s], 1);
     }
     for (int s = 0; s < GI_PLAN_SLOTS; ++s) {
-      ptx::mbar_init(&plan_full[s], GI_BM);
-      ptx::mbar_init(&plan_empty[s], GI_GATHER_THREADS);
+      ptx::mbar_init(&plan_full[s], ptx::arrivals(GI_BM));
+      ptx::mbar_init(&plan_empty[s], ptx::arrivals(GI_GATHER_THREADS));
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tmem_full[s], 1);
-      ptx::mbar_init(&tmem_empty[s], 128);
+      ptx::mbar_init(&tmem_empty[s], ptx::arrivals(128));
     }
     ptx::fence_barrier_init();
   }
@@ -375,7 +403,7 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const TcGiParams pr
         }
       }
       ptx::tc_fence_before_sync();
-      ptx::mbar_arrive(&tmem_empty[as]);
+      ptx::mbar_arrive_warp(&tmem_empty[as]);
       if (++as == 2) { as = 0; aph ^= 1; }
     }
   } else if (warp < GI_GATHER_WARP0) {
@@ -423,7 +451,7 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const TcGiParams pr
         const uint4* q = reinterpret_cast<const uint4*>(&r);
 #pragma unroll
         for (int i = 0; i < 4; ++i) sts128(pa + 16 * i, q[i]);
-        ptx::mbar_arrive(&plan_full[ps]);
+        ptx::mbar_arrive_warp(&plan_full[ps]);
         if (++ps == GI_PLAN_SLOTS) { ps = 0; pph ^= 1; }
       }
     }
@@ -489,11 +517,11 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const TcGiParams pr
           if (cob + 1 < prm.cobs) issue(va, 0, gcb + 128);
           finish(vb, 1, gcb, a_addr);
           ptx::fence_proxy_async_smem();
-          ptx::mbar_arrive(&full_a[s]);
+          ptx::mbar_arrive_warp(&full_a[s]);
           if (++s == GI_STAGES) { s = 0; ph ^= 1; }
           gcb += 128;
         }
-        ptx::mbar_arrive(&plan_empty[ps]);
+        ptx::mbar_arrive_warp(&plan_empty[ps]);
         if (++ps == GI_PLAN_SLOTS) { ps = 0; pph ^= 1; }
       }
     }
@@ -581,7 +609,10 @@ void build_bins(const DevGeom& g, const void* off, const void* mask, char* ws, c
   {
     ProfScope prof(ctx, "bin_sort");
     const int sb = (int)((nb + 255) / 256 > 148 * 16 ? 148 * 16 : (nb + 255) / 256);
-    k_bin_sort<<<sb, 256, 0, ctx.stream>>>(start, entries, nb);
+    // `count` is all zero again here (the fill pass took every slot): it doubles as the long-bin work list
+    k_bin_sort<<<sb, 256, 0, ctx.stream>>>(start, entries, nb, count);
+    MDCONV_CHECK_LAUNCH(ctx);
+    k_bin_sort_big<<<148, 256, 0, ctx.stream>>>(start, entries, count);
     MDCONV_CHECK_LAUNCH(ctx);
   }
 }
@@ -686,12 +717,8 @@ void tensor_grad_input(const DevGeom& g, const void* w, const void* go, void* gx
     return;
   }
   const size_t smem = smem_bytes_gi();
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_tc_grad_input<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess && ctx.err == cudaSuccess) ctx.err = e;
-    configured = true;
-  }
+  static std::atomic<unsigned long long> configured{0};
+  opt_in_dynamic_smem(k_tc_grad_input<T>, smem, configured, ctx);
   const int sms = sm_count() - ctx.spare_sms > 0 ? sm_count() - ctx.spare_sms : 1;
   const int grid = prm.total_tiles < sms ? prm.total_tiles : sms;
   ProfScope prof(ctx, "tc_grad_input");

@@ -80,15 +80,14 @@ __device__ __forceinline__ float dot8(const uint4& a, const uint4& b, __half) {
   return f.x + f.y;
 }
 __device__ __forceinline__ float dot8(const uint4& a, const uint4& b, __nv_bfloat16) {
-  const uint32_t* x = reinterpret_cast<const uint32_t*>(&a);
-  const uint32_t* y = reinterpret_cast<const uint32_t*>(&b);
-  float acc = 0.f;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    acc = fmaf(__uint_as_float(x[i] << 16), __uint_as_float(y[i] << 16), acc);
-    acc = fmaf(__uint_as_float(x[i] & 0xFFFF0000u), __uint_as_float(y[i] & 0xFFFF0000u), acc);
-  }
-  return acc;
+  const __nv_bfloat162* x = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* y = reinterpret_cast<const __nv_bfloat162*>(&b);
+  __nv_bfloat162 p = __hmul2(x[0], y[0]);
+  p = __hfma2(x[1], y[1], p);
+  p = __hfma2(x[2], y[2], p);
+  p = __hfma2(x[3], y[3], p);
+  const float2 f = __bfloat1622float2(p);
+  return f.x + f.y;
 }
 __device__ __forceinline__ uint32_t pack2(float a, float b, __half) {
   const __half2 h = __floats2half2_rn(a, b);
@@ -134,11 +133,11 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tmem_full[s], 1);
-      ptx::mbar_init(&tmem_empty[s], 128);
-      ptx::mbar_init(&t_full[s], 128);
-      ptx::mbar_init(&t_empty[s], GS_DOT_THREADS);
-      ptx::mbar_init(&plan_full[s], 128);
-      ptx::mbar_init(&plan_empty[s], GS_DOT_THREADS);
+      ptx::mbar_init(&tmem_empty[s], ptx::arrivals(128));
+      ptx::mbar_init(&t_full[s], ptx::arrivals(128));
+      ptx::mbar_init(&t_empty[s], ptx::arrivals(GS_DOT_THREADS));
+      ptx::mbar_init(&plan_full[s], ptx::arrivals(128));
+      ptx::mbar_init(&plan_empty[s], ptx::arrivals(GS_DOT_THREADS));
     }
     ptx::fence_barrier_init();
   }
@@ -297,7 +296,7 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
           const uint4* q = reinterpret_cast<const uint4*>(&e);
 #pragma unroll
           for (int i = 0; i < (int)(sizeof(SampleEntry<ND>) / 16); ++i) sts128(pa + 16 * i, q[i]);
-          ptx::mbar_arrive(&plan_full[ps]);
+          ptx::mbar_arrive_warp(&plan_full[ps]);
           if (++ps == 2) { ps = 0; pph ^= 1; }
         }
         for (int sub = 0; sub < nsub; ++sub) {
@@ -322,11 +321,11 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
                 sts128(tb + sw128(row, hlf * 4 + q), o);
               }
             }
-            ptx::mbar_arrive(&t_full[ts]);
+            ptx::mbar_arrive_warp(&t_full[ts]);
             if (++ts == 2) { ts = 0; tph ^= 1; }
           }
           ptx::tc_fence_before_sync();
-          ptx::mbar_arrive(&tmem_empty[as]);
+          ptx::mbar_arrive_warp(&tmem_empty[as]);
           if (++as == 2) { as = 0; aph ^= 1; }
         }
       }
@@ -385,7 +384,7 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
 #pragma unroll
               for (int c = 0; c < NC; ++c) S[i][c] += dot8(gc, xv[i][c], T());
             }
-            ptx::mbar_arrive(&t_empty[ts]);
+            ptx::mbar_arrive_warp(&t_empty[ts]);
             if (++ts == 2) { ts = 0; tph ^= 1; }
           }
         }
@@ -453,7 +452,7 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
             if (MOD) gmask[ch * g.P + p] = cvt_to<T, float>(gm);
           }
         }
-        ptx::mbar_arrive(&plan_empty[ps]);
+        ptx::mbar_arrive_warp(&plan_empty[ps]);
         if (++ps == 2) { ps = 0; pph ^= 1; }
       }
       if (++phs == phases) { phs = 0; ++t; }
@@ -474,13 +473,8 @@ size_t gs_smem_bytes() {
 template <typename T, int ND, bool MOD>
 void launch_grad_sample(const CUtensorMap& tmap_go, const CUtensorMap& tmap_w, const TcGsParams& prm, LaunchCtx& ctx) {
   const size_t smem = gs_smem_bytes<ND>();
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e =
-        cudaFuncSetAttribute(k_tc_grad_sample<T, ND, MOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess && ctx.err == cudaSuccess) ctx.err = e;
-    configured = true;
-  }
+  static std::atomic<unsigned long long> configured{0};
+  opt_in_dynamic_smem(k_tc_grad_sample<T, ND, MOD>, smem, configured, ctx);
   const int sms = sm_count() - ctx.spare_sms > 0 ? sm_count() - ctx.spare_sms : 1;
   const int grid = prm.items < sms ? (int)prm.items : sms;
   ProfScope prof(ctx, "tc_grad_sample");
@@ -491,13 +485,14 @@ void launch_grad_sample(const CUtensorMap& tmap_go, const CUtensorMap& tmap_w, c
 }  // namespace
 
 bool grad_sample_supported(const DevGeom& g) {
-  return g.Cog % GS_KCO == 0 && g.P % 8 == 0 && g.Cg % 64 == 0 && g.Cdg % 64 == 0;
+  return g.Cog % GS_KCO == 0 && g.Cg % 64 == 0 && g.Cdg % 64 == 0;
 }
 
-// xt: channels-last input; wr: weight re-ordered to [Co][(channel-block, tap, 64 channels)].
+// xt: channels-last input; wr: weight re-ordered to [Co][(channel-block, tap, 64 channels)]; go: grad_output rows
+// [B][Co][go_ld] (go_ld = P, or P rounded up to 8 elements for the padded copy).
 template <typename T>
 void tensor_grad_sample(const DevGeom& g, const T* xt, const T* wr, const void* off, const void* mask, const void* go,
-                        void* goff, void* gmask, LaunchCtx& ctx) {
+                        int go_ld, void* goff, void* gmask, LaunchCtx& ctx) {
   TcGsParams prm;
   prm.g = g;
   prm.xt = xt; prm.off = off; prm.mask = mask; prm.goff = goff; prm.gmask = gmask;
@@ -520,7 +515,7 @@ void tensor_grad_sample(const DevGeom& g, const T* xt, const T* wr, const void* 
   CUtensorMap tmap_go, tmap_w;
   {
     const cuuint64_t dims[3] = {(cuuint64_t)g.P, (cuuint64_t)g.Co, (cuuint64_t)g.B};
-    const cuuint64_t strides[2] = {(cuuint64_t)g.P * sizeof(T), (cuuint64_t)g.Co * g.P * sizeof(T)};
+    const cuuint64_t strides[2] = {(cuuint64_t)go_ld * sizeof(T), (cuuint64_t)g.Co * go_ld * sizeof(T)};
     const cuuint32_t box[3] = {64, GS_KCO, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = enc(&tmap_go, tmap_dtype<T>(), 3, const_cast<void*>(go), dims, strides, box, estr,
@@ -554,9 +549,9 @@ void tensor_grad_sample(const DevGeom& g, const T* xt, const T* wr, const void* 
 }
 
 template void tensor_grad_sample<__half>(const DevGeom&, const __half*, const __half*, const void*, const void*,
-                                         const void*, void*, void*, LaunchCtx&);
+                                         const void*, int, void*, void*, LaunchCtx&);
 template void tensor_grad_sample<__nv_bfloat16>(const DevGeom&, const __nv_bfloat16*, const __nv_bfloat16*,
-                                                const void*, const void*, const void*, void*, void*, LaunchCtx&);
+                                                const void*, const void*, const void*, int, void*, void*, LaunchCtx&);
 
 }  // namespace tc
 }  // namespace mdconv

@@ -147,17 +147,17 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const TcFwdParams prm) 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_w);
     for (int s = 0; s < TC_STAGES; ++s) {
-      ptx::mbar_init(&full_a[s], TC_GATHER_THREADS);
+      ptx::mbar_init(&full_a[s], ptx::arrivals(TC_GATHER_THREADS));
       ptx::mbar_init(&full_b[s], 1);
       ptx::mbar_init(&empty[s], 1);
     }
     for (int s = 0; s < TC_PLAN_SLOTS; ++s) {
-      ptx::mbar_init(&plan_full[s], TC_BM);
-      ptx::mbar_init(&plan_empty[s], TC_GATHER_THREADS);
+      ptx::mbar_init(&plan_full[s], ptx::arrivals(TC_BM));
+      ptx::mbar_init(&plan_empty[s], ptx::arrivals(TC_GATHER_THREADS));
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tmem_full[s], 1);
-      ptx::mbar_init(&tmem_empty[s], 128);
+      ptx::mbar_init(&tmem_empty[s], ptx::arrivals(128));
     }
     ptx::fence_barrier_init();
   }
@@ -257,7 +257,7 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const TcFwdParams prm) 
         }
       }
       ptx::tc_fence_before_sync();
-      ptx::mbar_arrive(&tmem_empty[as]);
+      ptx::mbar_arrive_warp(&tmem_empty[as]);
       if (++as == 2) { as = 0; aph ^= 1; }
     }
   } else if (warp < TC_GATHER_WARP0) {
@@ -284,7 +284,7 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const TcFwdParams prm) 
         const PlanEntry<ND> e = tc::make_plan_entry<T, ND, MOD>(g, off, mask, rc, grp * g.Cg + cc * TC_BK, tap, C8);
         ptx::mbar_wait_relaxed(&plan_empty[ps], pph ^ 1);
         tc::store_plan<ND>(ptx::smem_u32(sPlan + ps * TC_BM + row), e);
-        ptx::mbar_arrive(&plan_full[ps]);
+        ptx::mbar_arrive_warp(&plan_full[ps]);
         if (++ps == TC_PLAN_SLOTS) { ps = 0; pph ^= 1; }
       });
     }
@@ -342,10 +342,10 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const TcFwdParams prm) 
       tc::sts128(a_addr + tc::sw128(row0, chunk), tc::interp8(v0, w0, NC, T()));
       tc::sts128(a_addr + tc::sw128(row0 + 4, chunk), tc::interp8(v1, w1, NC, T()));
       ptx::fence_proxy_async_smem();
-      ptx::mbar_arrive(&full_a[s]);
+      ptx::mbar_arrive_warp(&full_a[s]);
       if (++s == TC_STAGES) { s = 0; ph ^= 1; }
       if (it.last()) {
-        ptx::mbar_arrive(&plan_empty[cps]);
+        ptx::mbar_arrive_warp(&plan_empty[cps]);
         if (++cps == TC_PLAN_SLOTS) cps = 0;
       }
     };
@@ -388,12 +388,15 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const TcFwdParams prm) 
 // elements = 33 words keeps both phases at most 2-way bank conflicted).  VEC == false is the scalar
 // form for sizes / pointers that are not 16-byte friendly.
 template <typename T, bool VEC>
-__global__ void __launch_bounds__(256) k_to_channels_last(const T* __restrict__ x, T* __restrict__ xt, int C, int IN) {
+__global__ void __launch_bounds__(256) k_to_channels_last(const T* __restrict__ x, T* __restrict__ xt, int C, int IN,
+                                                          int zero_row) {
   __shared__ __align__(16) T tile[64][66];  // [position][channel]
   const int b = blockIdx.z;
   const int c0 = blockIdx.y * 64, i0 = blockIdx.x * 64;
   const T* xb = x + (size_t)b * C * IN;
   T* xtb = xt + (size_t)b * C * IN;
+  if (zero_row && blockIdx.x == 0 && b == 0 && threadIdx.x < 64 && c0 + (int)threadIdx.x < C)
+    xt[(size_t)gridDim.z * C * IN + c0 + threadIdx.x] = cvt_to<T, float>(0.f);   // the all-zero position (xt_bytes)
   if (VEC) {
     // load: thread -> (channel, 8-position chunk); 512 (channel, chunk) pairs, two per thread
 #pragma unroll
@@ -472,12 +475,8 @@ size_t fwd_smem_bytes() {
 template <typename T, int ND, bool MOD>
 void launch_tc_forward(const CUtensorMap& tmap, const TcFwdParams& prm, LaunchCtx& ctx) {
   const size_t smem = fwd_smem_bytes<ND>();
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_tc_forward<T, ND, MOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess && ctx.err == cudaSuccess) ctx.err = e;
-    configured = true;
-  }
+  static std::atomic<unsigned long long> configured{0};
+  tc::opt_in_dynamic_smem(k_tc_forward<T, ND, MOD>, smem, configured, ctx);
   const int grid = prm.total_tiles < tc::sm_count() ? prm.total_tiles : tc::sm_count();
   ProfScope prof(ctx, "tc_forward");
   k_tc_forward<T, ND, MOD><<<grid, TC_THREADS, smem, ctx.stream>>>(tmap, prm);
@@ -488,8 +487,8 @@ template <typename T>
 void tensor_forward_t(const DevGeom& g, const void* x, const void* w, const void* bias, const void* off,
                       const void* mask, void* y, void* ws, LaunchCtx& ctx) {
   T* xt = reinterpret_cast<T*>(ws);
-  T* wr = reinterpret_cast<T*>(reinterpret_cast<char*>(ws) + align256((size_t)g.B * g.C * g.IN * sizeof(T)));
-  tc::launch_to_channels_last<T>((const T*)x, xt, g.B, g.C, g.IN, ctx);
+  T* wr = reinterpret_cast<T*>(reinterpret_cast<char*>(ws) + tc::xt_bytes(g));
+  tc::launch_to_channels_last<T>((const T*)x, xt, g.B, g.C, g.IN, ctx, /*zero_row=*/true);
   tc::launch_reorder_weight<T>((const T*)w, wr, g.Co, g.Cg, g.K, ctx);
   TcFwdParams prm;
   prm.g = g;
@@ -579,23 +578,25 @@ SideStream* side_stream() {
 }
 
 int sm_count() {
-  static int n = 0;
+  static std::atomic<int> per_dev[64];   // zero-initialised; 0 = not queried yet
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  const bool tracked = dev >= 0 && dev < 64;
+  int n = tracked ? per_dev[dev].load(std::memory_order_relaxed) : 0;
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    if (tracked) per_dev[dev].store(n, std::memory_order_relaxed);
   }
   return n;
 }
 
 template <typename T>
-void launch_to_channels_last(const T* x, T* xt, int B, int C, int IN, LaunchCtx& ctx) {
+void launch_to_channels_last(const T* x, T* xt, int B, int C, int IN, LaunchCtx& ctx, bool zero_row) {
   ProfScope prof(ctx, "to_channels_last");
   dim3 grid((unsigned)((IN + 63) / 64), (unsigned)((C + 63) / 64), (unsigned)B);
   const bool vec = IN % 8 == 0 && C % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)xt & 15) == 0;
-  if (vec) k_to_channels_last<T, true><<<grid, 256, 0, ctx.stream>>>(x, xt, C, IN);
-  else k_to_channels_last<T, false><<<grid, 256, 0, ctx.stream>>>(x, xt, C, IN);
+  if (vec) k_to_channels_last<T, true><<<grid, 256, 0, ctx.stream>>>(x, xt, C, IN, zero_row ? 1 : 0);
+  else k_to_channels_last<T, false><<<grid, 256, 0, ctx.stream>>>(x, xt, C, IN, zero_row ? 1 : 0);
   MDCONV_CHECK_LAUNCH(ctx);
 }
 template <typename T>
@@ -606,8 +607,9 @@ void launch_reorder_weight(const T* w, T* wr, int Co, int Cg, int K, LaunchCtx& 
   k_reorder_weight<T><<<blocks, 256, 0, ctx.stream>>>(w, wr, Co, Cg, K);
   MDCONV_CHECK_LAUNCH(ctx);
 }
-template void launch_to_channels_last<__half>(const __half*, __half*, int, int, int, LaunchCtx&);
-template void launch_to_channels_last<__nv_bfloat16>(const __nv_bfloat16*, __nv_bfloat16*, int, int, int, LaunchCtx&);
+template void launch_to_channels_last<__half>(const __half*, __half*, int, int, int, LaunchCtx&, bool);
+template void launch_to_channels_last<__nv_bfloat16>(const __nv_bfloat16*, __nv_bfloat16*, int, int, int, LaunchCtx&,
+                                                     bool);
 template void launch_reorder_weight<__half>(const __half*, __half*, int, int, int, LaunchCtx&);
 template void launch_reorder_weight<__nv_bfloat16>(const __nv_bfloat16*, __nv_bfloat16*, int, int, int, LaunchCtx&);
 
@@ -625,7 +627,7 @@ int comm_spare_sms() {
 bool tensor_path_supported(const DevGeom& g, int dtype, int backward) {
   if (dtype != MDCONV_F16 && dtype != MDCONV_BF16) return false;
   if (g.Cg % TC_BK != 0 || g.Cdg % TC_BK != 0) return false;
-  if ((long long)g.B * g.IN * (g.C / 8) > 2147483647LL) return false;
+  if (((long long)g.B * g.IN + 1) * (g.C / 8) > 2147483647LL) return false;
   if (backward) return tc::tensor_backward_supported(g, dtype);
   if (g.Cog % 32 != 0) return false;
   if (g.Cog > TC_MAX_BN && g.Cog % TC_MAX_BN != 0) return false;
@@ -635,7 +637,7 @@ bool tensor_path_supported(const DevGeom& g, int dtype, int backward) {
 size_t tensor_workspace_bytes(const DevGeom& g, int dtype, int backward) {
   (void)dtype;
   if (backward) return tc::tensor_backward_workspace(g);
-  return align256((size_t)g.B * g.C * g.IN * 2) + align256((size_t)g.Co * g.Kg * 2);
+  return tc::xt_bytes(g) + align256((size_t)g.Co * g.Kg * 2);
 }
 
 void tensor_forward(const DevGeom& g, int dtype, const void* x, const void* w, const void* bias, const void* off,
@@ -654,7 +656,7 @@ void tensor_backward(const DevGeom& g, int dtype, const void* x, const void* w, 
 // forward workspace prefix the backward can reuse: [channels-last input | re-ordered weight]
 size_t tensor_saved_bytes(const DevGeom& g, int dtype) {
   (void)dtype;
-  return align256((size_t)g.B * g.C * g.IN * 2) + align256((size_t)g.Co * g.Kg * 2);
+  return tc::xt_bytes(g) + align256((size_t)g.Co * g.Kg * 2);
 }
 
 }  // namespace mdconv

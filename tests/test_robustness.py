@@ -1,0 +1,121 @@
+"""GPU robustness tests (-m gpu): absent corners never read the input, strongly clustered offsets (long inverse-index
+bins), a second device in the same process, non-finite inputs."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from cases import Case, make_inputs, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(case, t, dev="cuda", path=0):
+    import MDCONV_CUDA
+    import modulated_deform_conv as mdc
+    fn = {(2, False): mdc.deform_conv2d, (2, True): mdc.modulated_deform_conv2d,
+          (3, False): mdc.deform_conv3d, (3, True): mdc.modulated_deform_conv3d}[(case.nd, case.modulated)]
+    lv = {k: (v.to(dev).requires_grad_() if v is not None and k != "grad_output" else v) for k, v in t.items()}
+    args = [lv["x"], lv["offset"]] + ([lv["mask"]] if case.modulated else []) + \
+           [lv["weight"], lv["bias"], case.s, case.p, case.d, case.g, case.dg, 64]
+    MDCONV_CUDA.set_path(path)
+    try:
+        y = fn(*args)
+        y.backward(t["grad_output"].to(dev))
+        torch.cuda.synchronize(dev)
+    finally:
+        MDCONV_CUDA.set_path(0)
+    out = {"y": y.detach(), "grad_input": lv["x"].grad, "grad_offset": lv["offset"].grad,
+           "grad_weight": lv["weight"].grad}
+    if case.modulated:
+        out["grad_mask"] = lv["mask"].grad
+    return {k: v.double().cpu().numpy() for k, v in out.items()}
+
+
+def _oracle(case, t):
+    a = (case.s, case.p, case.d, case.g, case.dg)
+    ref = oracle.backward(t["x"], t["weight"], t["offset"], t["mask"], t["grad_output"], *a, variant=case.rule,
+                          with_bias=case.bias)
+    ref["y"] = oracle.forward(t["x"], t["weight"], t["bias"], t["offset"], t["mask"], *a)
+    return {k: v for k, v in ref.items() if v is not None and k != "grad_bias"}
+
+
+@pytest.mark.parametrize("dtype,path", [(torch.float32, 1), (torch.float16, 2)], ids=["generic_f32", "tensor_f16"])
+def test_absent_corners_never_read_the_input(dtype, path):
+    """The reference returns an exact 0 for out-of-range samples and for corners outside the input WITHOUT reading
+    the input (src/mdeformable_conv.cu:19-29,80).  An Inf at x[0, :, 0, 0] (the pixel a zero-weight placeholder
+    index would hit) must therefore only reach outputs whose sampling footprint really contains that pixel: here
+    every sample of batch element 1 is clean, and with all offsets pushed out of range everything is exactly 0."""
+    case = Case("inf_pixel", 2, True, B=2, C=64, Co=64, size=(8, 8), bias=False, seed=301)
+    t = make_inputs(case, dtype)
+    t["x"][0, :, 0, 0] = float("inf")
+    out = _run(case, t, path=path)
+    assert np.isfinite(out["y"][1]).all(), "Inf of sample 0 leaked into sample 1 through an absent corner"
+    assert np.isfinite(out["grad_offset"][1]).all() and np.isfinite(out["grad_mask"][1]).all()
+    t2 = make_inputs(case, dtype)
+    t2["x"][0, :, 0, 0] = float("inf")
+    t2["offset"] += 1.0e4          # every sample out of range
+    out2 = _run(case, t2, path=path)
+    assert np.count_nonzero(out2["y"]) == 0 and np.isfinite(out2["y"]).all()
+    assert np.count_nonzero(out2["grad_weight"]) == 0 and np.isfinite(out2["grad_weight"]).all()
+
+
+def test_clustered_offsets_long_bins():
+    """Every tap of every output position samples (almost) the same input pixel: the inverse index of the
+    atomics-free grad_input then holds a handful of bins with thousands of entries (the block-wide sort path).
+    Results must match the oracle and be run-to-run identical."""
+    case = Case("clustered", 2, True, B=1, C=64, Co=64, size=(24, 24), bias=False, seed=302)
+    t = make_inputs(case, torch.float16)
+    H, W = case.size
+    ii, jj = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    off = torch.zeros_like(t["offset"], dtype=torch.float32)
+    for tap in range(9):
+        ki, kj = tap // 3, tap % 3
+        # sampling coordinate = out - pad + tap + offset  ->  force it to (5.25, 7.5) for every position and tap
+        off[0, 2 * tap] = 5.25 - (ii - 1 + ki)
+        off[0, 2 * tap + 1] = 7.5 - (jj - 1 + kj)
+    t["offset"] = off.to(torch.float16)
+    a = _run(case, t, path=0)
+    b = _run(case, t, path=0)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), f"{k} differs between two runs"
+    ref = _oracle(case, t)
+    for k, r in ref.items():
+        assert rel_err(a[k], r) < 1e-2, (k, rel_err(a[k], r))
+
+
+def test_second_device_in_the_same_process():
+    """cudaFuncAttributeMaxDynamicSharedMemorySize and the SM count are per device: the tcgen05 path on cuda:1
+    after cuda:0 in one process (nn.DataParallel, pipeline placement) must work and give the same bits."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs in one process")
+    case = Case("two_dev", 2, True, B=2, C=64, Co=64, size=(16, 16), seed=303)
+    t = make_inputs(case, torch.float16)
+    a = _run(case, t, dev="cuda:0", path=2)
+    b = _run(case, t, dev="cuda:1", path=2)
+    c = _run(case, t, dev="cuda:0", path=2)
+    for k in a:
+        assert np.array_equal(a[k], b[k]) and np.array_equal(a[k], c[k]), k
+
+
+@pytest.mark.parametrize("hw", [(14, 14), (7, 7), (9, 5)], ids=["14x14", "7x7", "9x5"])
+def test_tensor_backward_takes_maps_with_any_position_count(hw):
+    """Output maps whose position count is not a multiple of 8 (14x14 -> 196, 7x7 -> 49, 9x5 -> 45) stay on the
+    tcgen05 backward (grad_weight / grad_sample / grad_input), and match the oracle."""
+    import ctypes
+    import MDCONV_CUDA as M
+    case = Case(f"p_{hw[0]}x{hw[1]}", 2, True, B=3, C=64, Co=64, size=hw, seed=304)
+    t = make_inputs(case, torch.float16)
+    g = M._geom(t["x"], t["weight"], case.k, case.s, case.p, case.d, case.g, case.dg, True, case.bias)
+    g.path = 0
+    assert M._lib.mdconv_selected_path(ctypes.byref(g), 1) == 2, "tensor path refused the backward"
+    M.profile_enable(True)
+    try:
+        out = _run(case, t, path=0)
+        names = {n for n, _ in M.profile_read()}
+    finally:
+        M.profile_enable(False)
+    assert {"tc_forward", "tc_grad_weight", "tc_grad_sample", "tc_grad_input"} <= names, names
+    ref = _oracle(case, t)
+    for k, r in ref.items():
+        assert rel_err(out[k], r) < 1e-2, (k, rel_err(out[k], r))
