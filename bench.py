@@ -150,9 +150,22 @@ def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         p = json.load(open(path))
-        return {"hbm_gbs": p["hbm_gbs"], "tflops": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+        return {"hbm_gbs": p["hbm_gbs"], "tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
                 "tflops_burst": p["bf16_tflops"], "source": "measured (MEASURED_PEAKS.json)"}
-    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "tflops_burst": 1590.0, "source": "fallback (B200_PROFILING.md)"}
+    return {"hbm_gbs": 6650.0, "tflops_sustained": 1400.0, "tflops_burst": 1590.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+def pick_tensor_peak(peaks, timed_region_s, clocks):
+    """Burst cuBLAS figure unless the timed region is a seconds-long run whose SM clock settled well below max
+    (the conditions MEASURED_PEAKS.json's sustained figure was taken under)."""
+    mhz, mx = clocks.get("sm_mhz"), clocks.get("sm_max_mhz")
+    sustained = timed_region_s >= 2.0 and mhz is not None and mx and mhz < 0.9 * mx
+    if sustained:
+        return peaks["tflops_sustained"], "sustained bf16 cuBLAS (timed region %.1f s, SM clock %s of %s MHz)" % (
+            timed_region_s, mhz, mx)
+    return peaks["tflops_burst"], "burst bf16 cuBLAS (timed region %.3f s, SM clock %s of %s MHz)" % (
+        timed_region_s, mhz, mx)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -310,6 +323,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--path", type=int, default=0, help="0 auto, 1 generic SIMT, 2 tcgen05")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: the workload's per-GPU batch on every rank (default); strong: a FIXED global batch of "
+                         "--global-batch samples split over the ranks (SURVEY 8(e): cfg5, N=256)")
+    ap.add_argument("--global-batch", type=int, default=256)
+    ap.add_argument("--comm-ctas", type=int, default=4,
+                    help="N>1: CTAs of the dedicated NCCL communicator for the gradient all-reduce = SMs the "
+                         "data-gradient kernels leave free (0: default communicator, library default of 8 SMs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
     args = ap.parse_args()
@@ -340,6 +360,10 @@ def main():
     dtype = DTYPES[w["dtype"]]
     es = torch.tensor([], dtype=dtype).element_size()
     B = w["B"]
+    if args.scaling == "strong":
+        if args.global_batch % world:
+            raise SystemExit("--global-batch must be a multiple of the number of ranks")
+        B = args.global_batch // world
 
     cls = {(2, True): mdc.ModulatedDeformConv2d, (2, False): mdc.DeformConv2d,
            (3, True): mdc.ModulatedDeformConv3d, (3, False): mdc.DeformConv3d}[(w["nd"], w["modulated"])]
@@ -348,8 +372,9 @@ def main():
               deformable_groups=w["dg"], bias=False).to(dev).to(dtype)
     # data-parallel: the module all-reduces [grad_weight, grad_bias] inside its own backward, on a communication
     # stream that waits only for the weight-gradient kernels (overlaps grad_offset / grad_mask / grad_input)
+    grad_sync = None
     if world > 1:
-        mdconv_dist.attach(mod, None)
+        grad_sync = mdconv_dist.attach(mod, None, max_ctas=args.comm_ctas if args.comm_ctas > 0 else None)
 
     host = make_host_inputs(w, B, 100 + rank, dtype, pin=True)
     d = {k: (None if v is None else v.to(dev)) for k, v in host.items()}
@@ -470,22 +495,66 @@ def main():
     e2e_value = (B * world) / (ms_e2e / ke * 1e-3) / 1e6
     clocks.stop()
 
+    # copy-only probe: the same per-step H2D and D2H transfers with no kernels in between, both directions at once
+    # (what the link of THIS box gives; a slow lease shows up here, not as a regression of the code)
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    probe_n = 5
+    sync_all()
+    pe0.record()
+    for i in range(probe_n):
+        b_ = i % NBUF
+        with torch.cuda.stream(s_h2d):
+            for k in keys:
+                dbuf[b_][k].copy_(host[k], non_blocking=True)
+        with torch.cuda.stream(s_d2h):
+            for hbuf, r in zip(out_host[b_], keep[b_]):
+                hbuf.copy_(r, non_blocking=True)
+    main.wait_stream(s_h2d)
+    main.wait_stream(s_d2h)
+    pe1.record()
+    sync_all()
+    ms_probe = pe0.elapsed_time(pe1) / probe_n
+    copy_probe = {"ms_per_step": ms_probe, "h2d_gbs": h2d / (ms_probe * 1e-3) / 1e9,
+                  "d2h_gbs": d2h / (ms_probe * 1e-3) / 1e9,
+                  "note": "same pinned buffers, H2D and D2H streams running concurrently, no kernels"}
+
     # ---- N > 1: the in-backward all-reduce must equal an explicit all-reduce of the local gradients ----
     allreduce_check = None
+    comm_trace = None
     if world > 1:
         sync_obj = getattr(mod, "_grad_sync", None)
         mod._grad_sync = None                       # local gradients only
         step_resident()
-        expect = mod.weight.grad.detach().float().clone()
+        expect = mod.weight.grad.detach().double().clone()
         dist.all_reduce(expect, op=dist.ReduceOp.SUM)
         mod._grad_sync = sync_obj
         step_resident()
-        got = mod.weight.grad.detach().float()
+        got = mod.weight.grad.detach().double()
         torch.cuda.synchronize()
         err = float((got - expect).abs().max() / expect.abs().max())
-        allreduce_check = {"rel_err_vs_explicit_allreduce": err, "ok": bool(err < 5e-3)}
+        allreduce_check = {"rel_err_vs_explicit_allreduce": err, "ok": bool(err < 5e-3),
+                           "reduced_in": "fp32 (un-rounded parameter gradients), rounded once after the exchange"}
         if not allreduce_check["ok"]:
             raise SystemExit(f"in-backward all-reduce differs from the explicit one: {err}")
+        # where the collective sits inside a step: time from the weight-ready event to the end of the collective,
+        # next to the whole backward (events on the communication stream; outside the timed regions)
+        sync_obj.trace = []
+        tb0, tb1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ntr = 5
+        sync_all()
+        tb0.record()
+        for _ in range(ntr):
+            step_resident()
+        tb1.record()
+        sync_all()
+        coll = [a.elapsed_time(b) for a, b in sync_obj.trace]
+        sync_obj.trace = None
+        nb = mod.weight.numel() * 4
+        comm_trace = {"collective_ms_mean": sum(coll) / max(1, len(coll)), "collective_ms_max": max(coll) if coll else None,
+                      "step_ms": tb0.elapsed_time(tb1) / ntr, "allreduce_bytes_per_rank": nb,
+                      "nvlink_bytes_per_step_per_rank": 2 * nb * (world - 1) / world,
+                      "comm_ctas": args.comm_ctas, "note": "collective = fp32 all-reduce + the rounding copy, on the "
+                      "communication stream, measured from the moment the weight-ready event has fired"}
 
     # ---- per-kernel durations (CUDA events on the launching stream, inside the library) ----
     MDCONV_CUDA.profile_enable(True)
@@ -500,6 +569,8 @@ def main():
     calls = {k: len(v) // nprof for k, v in kt.items()}
 
     peaks = load_peaks()
+    clk = clocks.summary()
+    tpeak, tpeak_kind = pick_tensor_peak(peaks, ms_total * 1e-3, clk)
     bytes_fwd, bytes_bwd, flops_fwd, flops_bwd = algorithmic(w, B, es)
     # dominant kernel and the algorithmic work of ONE launch of it.  Each of the four GEMM kernels of the
     # tensor path (forward, grad_weight, grad_sample = grad_offset+grad_mask, grad_input) performs one
@@ -522,13 +593,13 @@ def main():
     for k, v in cand.items():
         dur = v / max(1, calls[k]) * 1e-3
         roofline_kernels[k] = {"launch_ms": dur * 1e3, "tflops": gemm_kernels[k] / dur / 1e12,
-                               "frac_of_tensor_peak": gemm_kernels[k] / dur / 1e12 / peaks["tflops"]}
+                               "frac_of_tensor_peak": gemm_kernels[k] / dur / 1e12 / tpeak}
     if dom is not None and tensor_path:
         dur = kernels[dom] / max(1, calls[dom]) * 1e-3
         ach = gemm_kernels.get(dom, flops_fwd) / dur / 1e12
-        roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                    "frac": ach / peaks["tflops"], "traffic": traffic.get(dom), "launch_ms": dur * 1e3,
-                    "peak_source": peaks["source"] + ", sustained bf16 cuBLAS (kernel timed inside a long step)",
+        roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s",
+                    "frac": ach / tpeak, "traffic": traffic.get(dom), "launch_ms": dur * 1e3,
+                    "peak_source": peaks["source"] + ", " + tpeak_kind,
                     "share_of_step": kernels[dom] / max(1e-9, sum(kernels.values()))}
     elif dom is not None:
         # SIMT path (fp32 / fp64): no tensor cores; report the dominant kernel against the HBM roof with the
@@ -559,22 +630,26 @@ def main():
         if world == 1 and not args.no_ref_cuda:
             ref_cuda = time_reference_cuda(w, d, mod, B)
         line = {"metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": K_steps, "warmup": W,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": w["dtype"], "data": "synthetic",
-                "config": {"workload": w["desc"], "global_batch": B * world, "parallelism": f"batch-shard x{world}",
+                "config": {"workload": w["desc"], "global_batch": B * world, "per_gpu_batch": B,
+                           "parallelism": f"batch-shard x{world}",
                            "l2": "working set (277 MB at cfg2) exceeds the 126 MB L2; no explicit flush",
                            "path": {0: "auto", 1: "generic", 2: "tensor"}[args.path],
                            "collective": "1 NCCL all-reduce(sum) of [grad_weight||grad_bias] per step, issued inside the backward on a "
                                          "side stream once the weight-gradient kernels finish" if world > 1 else "none"},
                 "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / ke, "steps": ke,
+                        "achieved_h2d_gbs": h2d / (ms_e2e / ke * 1e-3) / 1e9,
+                        "achieved_d2h_gbs": d2h / (ms_e2e / ke * 1e-3) / 1e9,
+                        "copy_only_probe": copy_probe,
                         "how": "public Module API; per step: H2D of x/offset/mask/grad_output from pinned host memory, "
                                "fwd+bwd, D2H of output and all gradients; copies of adjacent steps overlap the kernels "
                                "(3 streams, double-buffered); fill and drain included"},
-                "gpu_launches": n_launch, "clocks": clocks.summary(), "roofline": roofline, "roofline_kernels": roofline_kernels,
+                "gpu_launches": n_launch, "clocks": clk, "roofline": roofline, "roofline_kernels": roofline_kernels,
                 "roofline_hbm": roofline_hbm,
                 "kernels_ms_per_step": kernels, "cpu_baseline": cpu_base, "reference_cuda": ref_cuda,
-                "allreduce_check": allreduce_check}
+                "allreduce_check": allreduce_check, "comm_trace": comm_trace}
         _emit(line)
     if world > 1:
         dist.barrier()

@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define MDCONV_B200_ABI_VERSION 2
+#define MDCONV_B200_ABI_VERSION 3
 
 enum mdconv_dtype { MDCONV_F32 = 0, MDCONV_F16 = 1, MDCONV_BF16 = 2, MDCONV_F64 = 3 };
 
@@ -75,6 +75,11 @@ enum mdconv_path {
   MDCONV_PATH_TENSOR = 2    /* tcgen05/TMEM path; MDCONV_ERR_BAD_GEOMETRY if it does not qualify */
 };
 
+/* Memory layout of the ACTIVATION tensors of a call (input, output, grad_output, grad_input).  Weight, bias, offset
+ * and mask always keep the reference's layouts.  CHANNELS_LAST = [B, spatial..., C] (torch.channels_last /
+ * channels_last_3d): the layout the kernels gather from, so no internal re-layout pass runs (ABI version 3). */
+enum mdconv_layout { MDCONV_LAYOUT_NCHW = 0, MDCONV_LAYOUT_CHANNELS_LAST = 1 };
+
 typedef struct mdconv_geom {
   int32_t nd;                 /* 2 or 3 */
   int32_t batch, c_in, c_out;
@@ -90,6 +95,7 @@ typedef struct mdconv_geom {
   int32_t grad_rule;          /* enum mdconv_grad_rule */
   int32_t with_bias;
   int32_t path;               /* enum mdconv_path */
+  int32_t io_layout;          /* enum mdconv_layout (ABI version 3) */
 } mdconv_geom_t;
 
 int mdconv_abi_version(void);
@@ -150,6 +156,31 @@ int mdconv_backward_saved(const mdconv_geom_t* g, const void* input, const void*
                           void* grad_bias, void* grad_offset, void* grad_mask, void* workspace,
                           size_t workspace_bytes, const void* saved, size_t saved_bytes, void* weight_ready_event,
                           void* stream);
+
+/* Optional extras of a backward call (ABI version 3); every field may be 0 / NULL.
+ *   saved, saved_bytes, weight_ready_event: as in mdconv_backward_saved.
+ *   grad_weight_f32 / grad_bias_f32: device buffers of c_out*(c_in/groups)*K resp. c_out floats that receive the
+ *     parameter gradients BEFORE they are rounded to the storage dtype (fp16 / bf16 calls; fp32 calls get a copy).
+ *     The parameter gradients are the only quantities of this path that sum over samples (reference:
+ *     src/mdeformable_conv.cu:436-444), i.e. the only ones a batch-sharded caller exchanges: all-reducing the fp32
+ *     values and rounding once afterwards gives the single-GPU result instead of a sum of rounded partial sums. */
+typedef struct mdconv_bwd_extra {
+  const void* saved;
+  size_t saved_bytes;
+  void* weight_ready_event;
+  float* grad_weight_f32;
+  float* grad_bias_f32;
+} mdconv_bwd_extra_t;
+
+int mdconv_backward_ex(const mdconv_geom_t* g, const void* input, const void* weight, const void* offset,
+                       const void* mask, const void* grad_output, void* grad_input, void* grad_weight,
+                       void* grad_bias, void* grad_offset, void* grad_mask, void* workspace, size_t workspace_bytes,
+                       const mdconv_bwd_extra_t* extra, void* stream);
+
+/* Streaming multiprocessors the persistent data-gradient kernels leave free once weight_ready_event has been
+ * recorded, so the caller's collective kernel has somewhere to run (default 8, or MDCONV_B200_COMM_SMS; 0..64).
+ * Match it to the CTA count of the communicator (e.g. NCCL max_ctas).  Returns the previous value. */
+int mdconv_set_comm_sms(int sms);
 
 /* ---- The reference's eight entry points, C ABI form --------------------------------------
  * Argument order follows the reference signatures; tensor handles become device pointers and the

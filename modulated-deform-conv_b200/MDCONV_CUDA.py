@@ -38,7 +38,13 @@ class _Geom(ctypes.Structure):
                 ("stride", ctypes.c_int32 * 3), ("pad", ctypes.c_int32 * 3), ("dilation", ctypes.c_int32 * 3),
                 ("groups", ctypes.c_int32), ("deformable_groups", ctypes.c_int32), ("dtype", ctypes.c_int32),
                 ("modulated", ctypes.c_int32), ("grad_rule", ctypes.c_int32), ("with_bias", ctypes.c_int32),
-                ("path", ctypes.c_int32)]
+                ("path", ctypes.c_int32), ("io_layout", ctypes.c_int32)]
+
+
+class _BwdExtra(ctypes.Structure):
+    """struct mdconv_bwd_extra (include/mdconv_b200.h)."""
+    _fields_ = [("saved", ctypes.c_void_p), ("saved_bytes", ctypes.c_size_t), ("weight_ready_event", ctypes.c_void_p),
+                ("grad_weight_f32", ctypes.c_void_p), ("grad_bias_f32", ctypes.c_void_p)]
 
 
 _lib.mdconv_abi_version.restype = _i
@@ -60,6 +66,10 @@ _lib.mdconv_saved_bytes.restype = _sz
 _lib.mdconv_saved_bytes.argtypes = [ctypes.POINTER(_Geom)]
 _lib.mdconv_backward_saved.restype = _i
 _lib.mdconv_backward_saved.argtypes = [ctypes.POINTER(_Geom)] + [_vp] * 11 + [_sz, _vp, _sz, _vp, _vp]
+_lib.mdconv_backward_ex.restype = _i
+_lib.mdconv_backward_ex.argtypes = [ctypes.POINTER(_Geom)] + [_vp] * 11 + [_sz, ctypes.POINTER(_BwdExtra), _vp]
+_lib.mdconv_set_comm_sms.restype = _i
+_lib.mdconv_set_comm_sms.argtypes = [_i]
 
 _TAIL = [_i, _vp, _sz, _vp]  # dtype, workspace, workspace_bytes, stream
 _G2 = [_i] * 17              # batch, channels, H, W, Cout, kh,kw, sh,sw, ph,pw, dh,dw, g, dg, in_step, with_bias
@@ -76,7 +86,7 @@ for _name, _nptr, _geo in (("deform_conv2d_forward_cuda", 5, _G2), ("deform_conv
 _lib.mdconv_legacy_workspace_bytes.restype = _sz
 _lib.mdconv_legacy_workspace_bytes.argtypes = [_i] * 25
 
-if _lib.mdconv_abi_version() != 2:
+if _lib.mdconv_abi_version() != 3:
     raise ImportError("MDCONV_CUDA: libmdconv_b200.so ABI version mismatch")
 
 _DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2, torch.float64: 3}
@@ -106,6 +116,12 @@ def total_launch_count() -> int:
 
 def library_path() -> str:
     return _LIB_PATH
+
+
+def set_comm_sms(sms: int) -> int:
+    """SMs the persistent data-gradient kernels leave free for a concurrent collective once the parameter
+    gradients are final (see mdconv_set_comm_sms).  Returns the previous value."""
+    return int(_lib.mdconv_set_comm_sms(int(sms)))
 
 
 _lib.mdconv_profile_enable.restype = _i
@@ -256,11 +272,13 @@ def _forward(input, weight, bias, offset, mask, output, kernel, stride, pad, dil
 
 
 def _backward(input, weight, bias, offset, mask, grad_output, grads, kernel, stride, pad, dil, group, dgroup,
-              with_bias, saved=None, weight_ready=None):
+              with_bias, saved=None, weight_ready=None, want_f32=False):
     """grads: None (allocate and return) or dict of caller-owned tensors (out-param style).
     saved: what ``_forward(..., keep=True)`` returned for the same input / weight / geometry, or None.
     weight_ready: a ``torch.cuda.Event`` recorded on the current stream once grad_weight / grad_bias are final
-    (before the data gradients are computed on the tensor path), or None."""
+    (before the data gradients are computed on the tensor path), or None.
+    want_f32: also return ``flat_f32`` = fp32 [grad_weight || grad_bias] before rounding to the storage dtype (what a
+    batch-sharded caller all-reduces)."""
     nd = len(kernel)
     modulated = mask is not None
     named = [("input", input), ("weight", weight), ("bias", bias), ("offset", offset)]
@@ -290,13 +308,21 @@ def _backward(input, weight, bias, offset, mask, grad_output, grads, kernel, str
         if saved is not None and saved[2] == g.path and saved[0].device == input.device and \
                 int(_lib.mdconv_saved_bytes(ctypes.byref(g))) == saved[1]:
             sv_ptr, sv_n = _ptr(saved[0]), saved[1]
-        rc = _lib.mdconv_backward_saved(ctypes.byref(g), _ptr(input), _ptr(weight), _ptr(offset), _ptr(mask),
-                                        _ptr(grad_output), _ptr(grads["grad_input"]), _ptr(grads["grad_weight"]),
-                                        _ptr(grads["grad_bias"]) if with_bias else None, _ptr(grads["grad_offset"]),
-                                        _ptr(grads.get("grad_mask")) if modulated else None, _ptr(ws), n,
-                                        sv_ptr, sv_n,
-                                        ctypes.c_void_p(weight_ready.cuda_event) if weight_ready is not None else None,
-                                        ctypes.c_void_p(stream))
+        ex = _BwdExtra()
+        ex.saved = sv_ptr.value if sv_ptr is not None else None
+        ex.saved_bytes = sv_n
+        ex.weight_ready_event = weight_ready.cuda_event if weight_ready is not None else None
+        if want_f32 and input.dtype != torch.float64:
+            nw = weight.numel()
+            flat = torch.empty(nw + (bias.numel() if with_bias else 0), dtype=torch.float32, device=input.device)
+            ex.grad_weight_f32 = flat.data_ptr()
+            ex.grad_bias_f32 = flat.data_ptr() + 4 * nw if with_bias else None
+            grads["flat_f32"] = flat
+        rc = _lib.mdconv_backward_ex(ctypes.byref(g), _ptr(input), _ptr(weight), _ptr(offset), _ptr(mask),
+                                     _ptr(grad_output), _ptr(grads["grad_input"]), _ptr(grads["grad_weight"]),
+                                     _ptr(grads["grad_bias"]) if with_bias else None, _ptr(grads["grad_offset"]),
+                                     _ptr(grads.get("grad_mask")) if modulated else None, _ptr(ws), n,
+                                     ctypes.byref(ex), ctypes.c_void_p(stream))
     _check(rc, "mdconv_backward")
     return grads
 
@@ -310,10 +336,12 @@ def forward_ex(input, weight, bias, offset, mask, output, kernel, stride, pad, d
 
 
 def backward_ex(input, weight, bias, offset, mask, grad_output, kernel, stride, pad, dil, group, deformable_group,
-                with_bias, saved=None, weight_ready=None):
-    """Generic form of the four backwards -> dict grad_input / grad_offset / grad_mask / grad_weight / grad_bias."""
+                with_bias, saved=None, weight_ready=None, want_f32=False):
+    """Generic form of the four backwards -> dict grad_input / grad_offset / grad_mask / grad_weight / grad_bias
+    (+ flat_f32 with ``want_f32``)."""
     return _backward(input, weight, bias, offset, mask, grad_output, None, tuple(kernel), tuple(stride), tuple(pad),
-                     tuple(dil), group, deformable_group, with_bias, saved=saved, weight_ready=weight_ready)
+                     tuple(dil), group, deformable_group, with_bias, saved=saved, weight_ready=weight_ready,
+                     want_f32=want_f32)
 
 
 # ---- the eight reference entry points ------------------------------------------------------------

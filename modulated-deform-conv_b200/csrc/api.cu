@@ -65,6 +65,7 @@ int resolve(const mdconv_geom_t* in, DevGeom& g) {
   g.modulated = in->modulated ? 1 : 0;
   g.rule = in->grad_rule ? 1 : 0;
   g.with_bias = in->with_bias ? 1 : 0;
+  if (in->io_layout != MDCONV_LAYOUT_NCHW) return MDCONV_ERR_BAD_GEOMETRY;   // (channels-last: see below)
   for (int a = 0; a < 3; ++a) {
     g.fd_out[a] = make_fastdiv(g.out[a]);
     g.fd_k[a] = make_fastdiv(g.k[a]);
@@ -233,6 +234,17 @@ int mdconv_backward_saved(const mdconv_geom_t* gi, const void* input, const void
                           const void* mask, const void* grad_output, void* grad_input, void* grad_weight,
                           void* grad_bias, void* grad_offset, void* grad_mask, void* workspace, size_t workspace_bytes,
                           const void* saved, size_t saved_bytes, void* weight_ready_event, void* stream) {
+  mdconv_bwd_extra_t ex;
+  memset(&ex, 0, sizeof(ex));
+  ex.saved = saved; ex.saved_bytes = saved_bytes; ex.weight_ready_event = weight_ready_event;
+  return mdconv_backward_ex(gi, input, weight, offset, mask, grad_output, grad_input, grad_weight, grad_bias,
+                            grad_offset, grad_mask, workspace, workspace_bytes, &ex, stream);
+}
+
+int mdconv_backward_ex(const mdconv_geom_t* gi, const void* input, const void* weight, const void* offset,
+                       const void* mask, const void* grad_output, void* grad_input, void* grad_weight,
+                       void* grad_bias, void* grad_offset, void* grad_mask, void* workspace, size_t workspace_bytes,
+                       const mdconv_bwd_extra_t* extra, void* stream) {
   DevGeom g;
   int rc = resolve(gi, g);
   if (rc != MDCONV_OK) return rc;
@@ -247,13 +259,21 @@ int mdconv_backward_saved(const mdconv_geom_t* gi, const void* input, const void
   if (need > 0 && (workspace == nullptr || workspace_bytes < need || ((uintptr_t)workspace & 255)))
     return MDCONV_ERR_WORKSPACE;
   LaunchCtx ctx{(cudaStream_t)stream, 0, cudaSuccess};
-  ctx.weight_ready = (cudaEvent_t)weight_ready_event;
-  (void)cudaGetLastError();
-  if (saved != nullptr) {
-    // only meaningful when both directions run on the tensor path; anything else is a caller error
-    const size_t want = mdconv_saved_bytes(gi);
-    if (want == 0 || saved_bytes < want || ((uintptr_t)saved & 255)) return MDCONV_ERR_WORKSPACE;
+  const void* saved = nullptr;
+  if (extra != nullptr) {
+    ctx.weight_ready = (cudaEvent_t)extra->weight_ready_event;
+    if (gi->dtype != MDCONV_F64) {   // fp64 gradients are already wider than the fp32 copy
+      ctx.gw32 = extra->grad_weight_f32;
+      ctx.gb32 = g.with_bias ? extra->grad_bias_f32 : nullptr;
+    }
+    saved = extra->saved;
+    if (saved != nullptr) {
+      // only meaningful when both directions run on the tensor path; anything else is a caller error
+      const size_t want = mdconv_saved_bytes(gi);
+      if (want == 0 || extra->saved_bytes < want || ((uintptr_t)saved & 255)) return MDCONV_ERR_WORKSPACE;
+    }
   }
+  (void)cudaGetLastError();
   if (path == MDCONV_PATH_TENSOR)
     tensor_backward(g, gi->dtype, input, weight, offset, mask, grad_output, grad_input, grad_weight, grad_bias,
                     grad_offset, grad_mask, workspace, saved, ctx);
@@ -263,6 +283,8 @@ int mdconv_backward_saved(const mdconv_geom_t* gi, const void* input, const void
   signal_weight_ready(ctx);   // paths that did not signal earlier: everything is enqueued by now
   return finish(ctx);
 }
+
+int mdconv_set_comm_sms(int sms) { return mdconv::set_comm_spare_sms(sms); }
 
 // ---- legacy-named entry points -----------------------------------------------------------------
 static mdconv_geom_t legacy_geom(int nd, int modulated, int batch, int channels, int height, int width, int length,

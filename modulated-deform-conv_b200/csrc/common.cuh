@@ -215,9 +215,13 @@ struct LaunchCtx {
   // SMs the persistent kernels launched from now on leave free (set once the weight-ready event has been
   // recorded: the caller's all-reduce kernel needs somewhere to run while the data gradients are computed)
   int spare_sms = 0;
+  // backward only: optional fp32 copies of the parameter gradients before rounding (mdconv_bwd_extra_t)
+  float* gw32 = nullptr;
+  float* gb32 = nullptr;
 };
 // SMs left to a concurrent collective after the weight-ready event (MDCONV_B200_COMM_SMS, default 8; api.cu)
 int comm_spare_sms();
+int set_comm_spare_sms(int sms);   // returns the previous value
 inline void signal_weight_ready(LaunchCtx& ctx) {
   if (ctx.weight_ready != nullptr) {
     cudaError_t e = cudaEventRecord(ctx.weight_ready, ctx.stream);

@@ -416,7 +416,8 @@ __global__ void __launch_bounds__(NT) k_generic_bwd_weight(const DevGeom g, cons
 // grad_bias[co] = sum over samples and positions of grad_output; one block per channel,
 // fixed reduction order (deterministic).
 template <typename T, typename F>
-__global__ void __launch_bounds__(NT) k_grad_bias(const DevGeom g, const T* __restrict__ go, T* __restrict__ gb) {
+__global__ void __launch_bounds__(NT) k_grad_bias(const DevGeom g, const T* __restrict__ go, T* __restrict__ gb,
+                                                  float* __restrict__ gb32) {
   __shared__ F red[NT];
   const int co = blockIdx.x;
   F acc = (F)0;
@@ -430,7 +431,10 @@ __global__ void __launch_bounds__(NT) k_grad_bias(const DevGeom g, const T* __re
     if ((int)threadIdx.x < sft) red[threadIdx.x] += red[threadIdx.x + sft];
     __syncthreads();
   }
-  if (threadIdx.x == 0) gb[co] = cvt_to<T, F>(red[0]);
+  if (threadIdx.x == 0) {
+    gb[co] = cvt_to<T, F>(red[0]);
+    if (gb32 != nullptr) gb32[co] = (float)red[0];
+  }
 }
 
 template <typename T>
@@ -533,7 +537,7 @@ void launch_backward(const DevGeom& g, const void* x, const void* w, const void*
   }
   if (do_bias && g.with_bias && gb != nullptr) {
     ProfScope prof(ctx, "grad_bias");
-    k_grad_bias<T, F><<<g.Co, NT, 0, ctx.stream>>>(g, (const T*)go, (T*)gb);
+    k_grad_bias<T, F><<<g.Co, NT, 0, ctx.stream>>>(g, (const T*)go, (T*)gb, ctx.gb32);
     MDCONV_CHECK_LAUNCH(ctx);
   }
   if (!direct) {
@@ -545,6 +549,10 @@ void launch_backward(const DevGeom& g, const void* x, const void* w, const void*
       }
       if (do_weight) convert_from_f32<T>((const float*)a_gw, gw, sz.n_gw, ctx);
     }
+  }
+  if (do_weight && ctx.gw32 != nullptr && sizeof(F) == 4) {   // fp32 accumulator (fp16 / bf16 / fp32 calls): plain copy
+    cudaError_t e = cudaMemcpyAsync(ctx.gw32, a_gw, sz.n_gw * sizeof(float), cudaMemcpyDeviceToDevice, ctx.stream);
+    if (e != cudaSuccess && ctx.err == cudaSuccess) ctx.err = e;
   }
 }
 

@@ -310,7 +310,8 @@ k_tc_grad_weight(const __grid_constant__ CUtensorMap tmap_go, const TcGwParams p
 
 // gW[co][c][tap] = sum_s part[s][co][((c/64)*K + tap)*64 + c%64]   (fixed order => deterministic)
 template <typename T>
-__global__ void k_reduce_grad_weight(const float* __restrict__ part, T* __restrict__ gw, int S, int Co, int Cg, int K) {
+__global__ void k_reduce_grad_weight(const float* __restrict__ part, T* __restrict__ gw, float* __restrict__ gw32, int S,
+                                     int Co, int Cg, int K) {
   const size_t n = (size_t)Co * Cg * K;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int Kg = Cg * K;
@@ -321,6 +322,7 @@ __global__ void k_reduce_grad_weight(const float* __restrict__ part, T* __restri
     float acc = 0.f;
     for (int s = 0; s < S; ++s) acc += part[(size_t)s * n + src];
     gw[i] = cvt_to<T, float>(acc);
+    if (gw32 != nullptr) gw32[i] = acc;   // un-rounded copy for a data-parallel caller's fp32 all-reduce
   }
 }
 
@@ -472,7 +474,7 @@ void tensor_backward_t(const DevGeom& g, const void* x, const void* w, const voi
     ProfScope prof(ctx, "reduce_grad_weight");
     const size_t n = (size_t)g.Co * g.Kg;
     const int blocks = (int)((n + 255) / 256 > 1184 ? 1184 : (n + 255) / 256);
-    k_reduce_grad_weight<T><<<blocks, 256, 0, ctx.stream>>>(part, (T*)gw, S, g.Co, g.Cg, g.K);
+    k_reduce_grad_weight<T><<<blocks, 256, 0, ctx.stream>>>(part, (T*)gw, ctx.gw32, S, g.Co, g.Cg, g.K);
     MDCONV_CHECK_LAUNCH(ctx);
   }
 

@@ -5,7 +5,7 @@
 // materialised grad_columns buffer (G2, :417-419).
 //
 // Here the scatter is turned into a gather.  A small inverse index (CSR) is built per call:
-//     bin (sample, deformable group, input position, tap)  ->  list of (output position, weight)
+//     bin (sample, deformable group, tap, input position)  ->  list of (output position, weight)
 // with weight = interpolation weight x mask of the corner that touches that input position.  Then
 //     G[pos, (tap, co)] = sum over the bin's entries of weight * go[entry position, co]
 //     grad_input[pos, c] = sum over (tap, co) of G[pos, (tap, co)] * W[co, c, tap]
@@ -44,7 +44,7 @@ constexpr int GI_NE = 8;  // bin entries staged per (position, tap); longer bins
 // One (input position, tap) of the tile: the first GI_NE entries of its bin, ready for the gather.
 struct __align__(16) GiPlanRow {
   uint32_t idx[GI_NE]; // byte offset of the entry's row in the channels-last grad_output
-  __half w[GI_NE];     // interpolation weight x mask (values in [0, max|mask|]; fp16 keeps 11 bits)
+  uint16_t w[GI_NE];   // interpolation weight x mask in the storage dtype (fp16 / bf16 bits)
   int n;               // entries in the bin
   int e0;              // index of the bin's first entry (for bins longer than GI_NE)
 };
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256) k_bin_entries(const DevGeom g, const T* _
         pix = pix * g.in[a] + ia;
       }
       if (!ok) continue;
-      const size_t bin = (((size_t)b * g.dg + dgi) * g.IN + pix) * g.K + tap;
+      const size_t bin = (((size_t)b * g.dg + dgi) * g.K + tap) * g.IN + pix;   // tap-major: neighbours in p hit neighbouring bins
       if (!FILL) {
         atomicAdd(count + bin, 1);
       } else {
@@ -261,9 +261,9 @@ template <> struct Acc8<__nv_bfloat16> {
 #pragma unroll
     for (int i = 0; i < 4; ++i) a[i] = __float2bfloat162_rn(0.f);
   }
-  __device__ __forceinline__ void fma(const uint4& v, __half w) { fma(v, __half2float(w)); }
-  __device__ __forceinline__ void fma(const uint4& v, float w) {
-    const __nv_bfloat162 wh = __float2bfloat162_rn(w);
+  __device__ __forceinline__ void fma(const uint4& v, float w) { fma(v, __float2bfloat16_rn(w)); }
+  __device__ __forceinline__ void fma(const uint4& v, __nv_bfloat16 w) {
+    const __nv_bfloat162 wh = __bfloat162bfloat162(w);
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
 #pragma unroll
     for (int i = 0; i < 4; ++i) a[i] = __hfma2(wh, h[i], a[i]);
@@ -422,20 +422,25 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const TcGiParams pr
       const int nt = t / prm.m_tiles;
       const int dgi = (nt * BN) / g.Cdg;
       const long long gp = (long long)mt * GI_BM + row;
+      // bins are tap-major: bin(tap) = bin0 + tap * IN; the bounds of the next tap's bin are fetched one tap ahead
       long long bin0 = -1;
       if (gp < total_pos) {
         const long long b = gp / g.IN, pix = gp - b * g.IN;
-        bin0 = ((b * g.dg + dgi) * g.IN + pix) * g.K;
+        bin0 = (b * g.dg + dgi) * (long long)g.K * g.IN + pix;
       }
-      int e_lo = 0, e_hi = 0;
+      int e_lo = 0, e_hi = 0, n_lo = 0, n_hi = 0;
       if (bin0 >= 0) { e_lo = __ldg(bin_start + bin0); e_hi = __ldg(bin_start + bin0 + 1); }
+      if (bin0 >= 0 && g.K > 1) { n_lo = __ldg(bin_start + bin0 + g.IN); n_hi = __ldg(bin_start + bin0 + g.IN + 1); }
       for (int tap = 0; tap < g.K; ++tap) {
         const int e0 = e_lo, n = e_hi - e_lo;
-        e_lo = e_hi;
-        if (bin0 >= 0 && tap + 1 < g.K) e_hi = __ldg(bin_start + bin0 + tap + 2);
+        e_lo = n_lo; e_hi = n_hi;
+        if (bin0 >= 0 && tap + 2 < g.K) {
+          const long long nb = bin0 + (long long)(tap + 2) * g.IN;
+          n_lo = __ldg(bin_start + nb); n_hi = __ldg(bin_start + nb + 1);
+        }
         GiPlanRow r;
 #pragma unroll
-        for (int i = 0; i < GI_NE; ++i) { r.idx[i] = 0u; r.w[i] = __float2half_rn(0.f); }
+        for (int i = 0; i < GI_NE; ++i) { r.idx[i] = 0u; r.w[i] = 0; }
         r.n = n;
         r.e0 = e0;
 #pragma unroll
@@ -443,7 +448,8 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const TcGiParams pr
           if (i < n) {
             const int2 ev = __ldg(entries2 + e0 + i);
             r.idx[i] = (uint32_t)ev.x * (uint32_t)(g.Co * 2);
-            r.w[i] = __float2half_rn(__int_as_float(ev.y));
+            const T wt = cvt_to<T, float>(__int_as_float(ev.y));
+            r.w[i] = *reinterpret_cast<const uint16_t*>(&wt);
           }
         }
         ptx::mbar_wait_relaxed(&plan_empty[ps], pph ^ 1, 128);
@@ -494,7 +500,7 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const TcGiParams pr
         auto finish = [&](const uint4 (&v)[GI_NE], int pass, const char* base, uint32_t a_addr) {
           const uint32_t pa = plan_addr + pass * 4 * (uint32_t)sizeof(GiPlanRow);
           const uint4 wv = lds128(pa + 32), meta = lds128(pa + 48);
-          const __half* wh = reinterpret_cast<const __half*>(&wv);
+          const T* wh = reinterpret_cast<const T*>(&wv);
           const int n = (int)meta.x;
           Acc8<T> acc;
           acc.clear();

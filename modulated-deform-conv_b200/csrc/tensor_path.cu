@@ -615,13 +615,21 @@ template void launch_reorder_weight<__nv_bfloat16>(const __nv_bfloat16*, __nv_bf
 
 }  // namespace tc
 
+static std::atomic<int> g_comm_sms{-1};   // -1: not set yet -> MDCONV_B200_COMM_SMS or 8
 int comm_spare_sms() {
-  static const int n = [] {
+  int v = g_comm_sms.load(std::memory_order_relaxed);
+  if (v < 0) {
     const char* e = getenv("MDCONV_B200_COMM_SMS");
-    const int v = e ? atoi(e) : 8;
-    return v < 0 ? 0 : (v > 64 ? 64 : v);
-  }();
-  return n;
+    v = e ? atoi(e) : 8;
+    v = v < 0 ? 0 : (v > 64 ? 64 : v);
+    g_comm_sms.store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+int set_comm_spare_sms(int sms) {
+  const int prev = comm_spare_sms();
+  g_comm_sms.store(sms < 0 ? 0 : (sms > 64 ? 64 : sms), std::memory_order_relaxed);
+  return prev;
 }
 
 bool tensor_path_supported(const DevGeom& g, int dtype, int backward) {

@@ -88,18 +88,26 @@ class GradSync:
     """Overlapped all-reduce of one module's parameter gradients, driven from inside the op's backward.
 
     The tcgen05 backward computes grad_weight / grad_bias FIRST and records a CUDA event when they are final
-    (``mdconv_backward_saved(..., weight_ready_event)``).  ``reduce`` then runs ONE all-reduce(sum) of the two
-    tensors on a communication stream that waits for that event only, so the collective overlaps the
-    grad_offset / grad_mask / grad_input kernels; the compute stream re-joins before the backward returns, which
-    keeps autograd's accumulation into ``.grad`` ordered after the reduction.  Attach with ``attach(module, group)``;
-    the reduction is in the gradients' own dtype and in place (as DDP does), sum not mean.
-    On CPU tensors / a non-initialised process group it degrades to a plain (or no) all-reduce.
+    (``mdconv_backward_ex(..., weight_ready_event)``).  ``reduce`` then runs ONE all-reduce(sum) on a communication
+    stream that waits for that event only, so the collective overlaps the grad_offset / grad_mask / grad_input kernels;
+    the compute stream re-joins before the backward returns, which keeps autograd's accumulation into ``.grad``
+    ordered after the reduction.
+
+    What is reduced: for fp16 / bf16 parameters the library also hands out the two gradients in fp32 BEFORE rounding
+    (one flat buffer [grad_weight || grad_bias], ``mdconv_bwd_extra_t.grad_weight_f32``); the ranks exchange that and
+    round once afterwards, so G GPUs give what one GPU gives on the concatenated batch instead of a sum of G rounded
+    partial sums.  fp32 / fp64 parameters are reduced in place in their own dtype.
+    ``average=True`` divides by the world size (DistributedDataParallel's convention); the default is the op's own
+    single-GPU semantics, a sum.  On CPU tensors / a non-initialised process group it degrades to a plain (or no)
+    all-reduce.
     """
 
-    def __init__(self, group=None, device: Optional[torch.device] = None):
+    def __init__(self, group=None, device: Optional[torch.device] = None, average: bool = False):
         self.group = group
+        self.average = average
         self._stream = None
         self.event = None
+        self.trace = None            # optional list of (start, stop) CUDA events around each collective (bench.py)
         if device is not None and device.type == "cuda":
             self._stream = torch.cuda.Stream(device=device)
             self.event = torch.cuda.Event()
@@ -108,35 +116,147 @@ class GradSync:
     def active(self) -> bool:
         return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
 
-    def reduce(self, tensors: Sequence[Optional[torch.Tensor]]) -> None:
-        ts = [t for t in tensors if t is not None and t.numel() > 0]
-        if not ts or not self.active():
+    def wants_f32(self, weight: torch.Tensor) -> bool:
+        return weight.is_cuda and weight.dtype in (torch.float16, torch.bfloat16)
+
+    def _scale(self, t: torch.Tensor) -> None:
+        if self.average:
+            t.div_(dist.get_world_size(self.group))
+
+    def reduce(self, grads, with_bias: bool = True) -> None:
+        """``grads``: the dict MDCONV_CUDA.backward_ex returned (grad_weight, grad_bias, optionally flat_f32), or a
+        plain sequence of tensors to reduce in place."""
+        if not self.active():
+            return
+        if not isinstance(grads, dict):
+            ts = [t for t in grads if t is not None and t.numel() > 0]
+            grads = {"_list": ts}
+            flat32, outs = None, ts
+        else:
+            flat32 = grads.get("flat_f32")
+            outs = [grads["grad_weight"]] + ([grads["grad_bias"]] if with_bias and grads.get("grad_bias") is not None
+                                              and grads["grad_bias"].numel() else [])
+        if not outs:
             return
         if self._stream is None:
-            for t in ts:
+            for t in outs:
                 dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+                self._scale(t)
             return
-        main = torch.cuda.current_stream(ts[0].device)
+        main = torch.cuda.current_stream(outs[0].device)
         self._stream.wait_event(self.event)          # only grad_weight / grad_bias, not the whole backward
         with torch.cuda.stream(self._stream):
-            flat = ts[0] if len(ts) == 1 else torch.cat([t.reshape(-1) for t in ts])
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
-            if len(ts) > 1:
+            if self.trace is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(self._stream)
+            if flat32 is not None:
+                dist.all_reduce(flat32, op=dist.ReduceOp.SUM, group=self.group)
+                self._scale(flat32)
                 off = 0
-                for t in ts:
-                    t.copy_(flat[off:off + t.numel()].reshape(t.shape))
+                for t in outs:                       # the single rounding to the storage dtype
+                    t.copy_(flat32[off:off + t.numel()].view(t.shape))
                     off += t.numel()
-            for t in ts:
+                flat32.record_stream(self._stream)
+            else:
+                flat = outs[0] if len(outs) == 1 else torch.cat([t.reshape(-1) for t in outs])
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+                self._scale(flat)
+                if len(outs) > 1:
+                    off = 0
+                    for t in outs:
+                        t.copy_(flat[off:off + t.numel()].reshape(t.shape))
+                        off += t.numel()
+            if self.trace is not None:
+                e1.record(self._stream)
+                self.trace.append((e0, e1))
+            for t in outs:
                 t.record_stream(self._stream)
         main.wait_stream(self._stream)
 
 
-def attach(module, group=None) -> "GradSync":
-    """Make ``module`` (a DeformConv*/ModulatedDeformConv* module of this package) all-reduce its weight / bias
-    gradients inside its own backward, overlapped with the data gradients.  Returns the GradSync."""
+_comm_groups = {}
+
+
+def comm_group(max_ctas: int = 4):
+    """A dedicated NCCL communicator for the parameter-gradient all-reduce, limited to ``max_ctas`` CTAs: the
+    collective runs BESIDE the persistent data-gradient kernels, which own every SM they are given, so it can only
+    use the SMs those kernels leave free (mdconv_set_comm_sms) -- a communicator that wants 16+ CTAs would leave
+    most of its channels waiting for an SM.  2.4 MB per step needs no more than a few.  Collective call (every rank,
+    same order); cached per ``max_ctas``.  Returns None when the default backend is not NCCL."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_backend() != "nccl":
+        return None
+    if max_ctas not in _comm_groups:
+        opts = dist.ProcessGroupNCCL.Options()
+        try:
+            opts.config.max_ctas = int(max_ctas)
+            opts.config.min_ctas = 1
+        except Exception:
+            pass
+        _comm_groups[max_ctas] = dist.new_group(backend="nccl", pg_options=opts)
+    return _comm_groups[max_ctas]
+
+
+def _is_deform_module(m) -> bool:
+    return hasattr(m, "deformable_groups") and hasattr(m, "_conv_args")
+
+
+def attach(module, group=None, average: bool = False, max_ctas: Optional[int] = None) -> "GradSync":
+    """Make ``module`` (a DeformConv*/ModulatedDeformConv*[Pack] module of this package) all-reduce its weight / bias
+    gradients inside its own backward, overlapped with the data gradients.  Every OTHER parameter of the module --
+    the conv_offset / conv_mask producers of a Pack -- gets a post-accumulate-grad hook that all-reduces its
+    gradient the same way (sum, or mean with ``average``), so a data-parallel user of Pack modules has no silently
+    diverging replicas.  ``max_ctas``: run the collectives on a dedicated small NCCL communicator (``comm_group``)
+    and leave exactly that many SMs free beside the data-gradient kernels.  Returns the GradSync."""
     p = next(module.parameters())
-    module._grad_sync = GradSync(group, p.device)
-    return module._grad_sync
+    if max_ctas is not None and group is None and p.is_cuda:
+        group = comm_group(max_ctas)
+        import MDCONV_CUDA
+        MDCONV_CUDA.set_comm_sms(max_ctas)
+    sync = GradSync(group, p.device, average=average)
+    module._grad_sync = sync
+    own = {id(module.weight)} | ({id(module.bias)} if getattr(module, "bias", None) is not None else set())
+
+    def _reduce_other(param):
+        if sync.active() and param.grad is not None:
+            dist.all_reduce(param.grad, op=dist.ReduceOp.SUM, group=sync.group)
+            sync._scale(param.grad)
+
+    handles = []
+    for q in module.parameters():
+        if id(q) not in own and q.requires_grad:
+            handles.append(q.register_post_accumulate_grad_hook(_reduce_other))
+    module._grad_sync_handles = handles
+    return sync
+
+
+def detach(module) -> None:
+    """Undo ``attach``: the module returns LOCAL gradients again (what DistributedDataParallel expects to reduce)."""
+    for h in getattr(module, "_grad_sync_handles", []):
+        h.remove()
+    module._grad_sync_handles = []
+    module._grad_sync = None
+
+
+def prepare_ddp(model, group=None, max_ctas: Optional[int] = None):
+    """Use the in-backward overlapped reduction together with ``torch.nn.parallel.DistributedDataParallel``.
+
+    Two modes exist for the parameter gradients of the deformable convolutions under DDP:
+      * local-grad mode (default, nothing to call): the op returns local gradients and DDP's bucketed all-reduce
+        averages them like every other parameter's;
+      * this function: every deformable-conv module in ``model`` is attached with ``average=True`` (DDP's
+        convention) and its parameters are put on DDP's ignore list, so DDP neither re-reduces the already reduced
+        gradients nor waits for them -- the only cross-sample reduction of the op (reference
+        src/mdeformable_conv.cu:436-444) then overlaps the op's own data-gradient kernels.
+    Call it BEFORE wrapping ``model`` in DistributedDataParallel.  Returns the list of ignored parameter names."""
+    ignored = []
+    for name, m in model.named_modules():
+        if _is_deform_module(m):
+            attach(m, group, average=True, max_ctas=max_ctas)
+            ignored += [f"{name}.{n}" if name else n for n, _ in m.named_parameters()]
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    prev = list(getattr(model, "_ddp_params_and_buffers_to_ignore", []))
+    DDP._set_params_and_buffers_to_ignore_for_model(model, prev + ignored)
+    return ignored
 
 
 def all_reduce_param_grads(params: Sequence[torch.Tensor], group=None) -> None:

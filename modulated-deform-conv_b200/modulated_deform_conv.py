@@ -55,124 +55,114 @@ def _needs_grad(*tensors):
 # The Functions below go through MDCONV_CUDA.forward_ex / backward_ex -- the same C entry points the eight
 # reference-named functions bind (MDCONV_CUDA.*_forward_cuda / *_backward_cuda stay available and equivalent) --
 # because that form can hand the forward's internal layouts (channels-last input, re-ordered weight) to the
-# backward through ctx, which the reference's positional signatures (:28-34, :57-64) have no slot for.
-def _forward_op(ctx, input, weight, bias, offset, mask, keep):
+# backward, which the reference's positional signatures (:28-34, :57-64) have no slot for.  The hand-off buffer
+# travels through ctx.save_for_backward like every other saved activation, so saved-tensor hooks (CPU offload,
+# checkpointing) see it; MDCONV_CUDA.set_keep_layouts(False) / MDCONV_B200_KEEP_LAYOUTS=0 drops it (the backward then
+# rebuilds the layouts: two more kernels, ~4 % of a cfg2 step, for one input-sized buffer less between the calls).
+def _forward_common(ctx, ntuple, modulated, input, offset, mask, weight, bias, stride, padding, dilation, groups,
+                    deformable_groups, in_step, grad_sync):
+    ctx.grad_sync = grad_sync
+    ctx.modulated = modulated
+    with_bias_tensor = bias
+    bias = _setup(ctx, ntuple, input, bias, stride, padding, dilation, groups, deformable_groups, in_step)
+    keep = _needs_grad(input, offset, mask, weight, with_bias_tensor)
     out = MDCONV_CUDA.forward_ex(input, weight, bias, offset, mask, None, weight.shape[2:], ctx.stride, ctx.padding,
                                  ctx.dilation, ctx.groups, ctx.deformable_groups, ctx.with_bias, keep=keep)
-    if keep:
-        out, ctx.layouts = out
+    if not keep:
+        return out
+    out, layouts = out
+    ctx.layout_meta = None if layouts is None else layouts[1:]
+    saved = [input, offset, weight, bias] + ([mask] if modulated else [])
+    if layouts is not None:
+        saved.append(layouts[0])
+    ctx.save_for_backward(*saved)
     return out
 
 
-def _backward_op(ctx, input, weight, bias, offset, mask, grad_output):
+def _backward_common(ctx, grad_output):
+    """-> (dict of gradients, with_bias)"""
+    grad_output = grad_output.contiguous()
+    if not grad_output.is_cuda:
+        raise NotImplementedError
+    saved = list(ctx.saved_tensors)
+    layouts = None
+    if ctx.layout_meta is not None:
+        layouts = (saved.pop(),) + tuple(ctx.layout_meta)
+    input, offset, weight, bias = saved[:4]
+    mask = saved[4] if ctx.modulated else None
     sync = getattr(ctx, "grad_sync", None)
     if sync is not None and not sync.active():
         sync = None
     g = MDCONV_CUDA.backward_ex(input, weight, bias, offset, mask, grad_output, weight.shape[2:], ctx.stride,
                                 ctx.padding, ctx.dilation, ctx.groups, ctx.deformable_groups, ctx.with_bias,
-                                saved=getattr(ctx, "layouts", None),
-                                weight_ready=sync.event if sync is not None else None)
-    ctx.layouts = None
+                                saved=layouts, weight_ready=sync.event if sync is not None else None,
+                                want_f32=sync is not None and sync.wants_f32(weight))
     if sync is not None:
         # data-parallel: ONE all-reduce of [grad_weight, grad_bias], overlapped with the data-gradient kernels
-        sync.reduce([g["grad_weight"], g["grad_bias"] if ctx.with_bias else None])
+        sync.reduce(g, ctx.with_bias)
     return g
+
+
+def _plain_grads(ctx, g):
+    return (g["grad_input"], g["grad_offset"], g["grad_weight"], g["grad_bias"] if ctx.with_bias else None,
+            None, None, None, None, None, None, None)
+
+
+def _modulated_grads(ctx, g):
+    return (g["grad_input"], g["grad_offset"], g["grad_mask"], g["grad_weight"],
+            g["grad_bias"] if ctx.with_bias else None, None, None, None, None, None, None, None)
 
 
 class DeformConv2dFunction(Function):
     @staticmethod
     def forward(ctx, input, offset, weight, bias=None, stride=1, padding=0, dilation=1,
                 groups=1, deformable_groups=1, in_step=64, grad_sync=None):
-        ctx.grad_sync = grad_sync
-        with_bias_tensor = bias
-        bias = _setup(ctx, _pair, input, bias, stride, padding, dilation, groups, deformable_groups, in_step)
-        keep = _needs_grad(input, offset, weight, with_bias_tensor)
-        if keep:
-            ctx.save_for_backward(input, offset, weight, bias)
-        return _forward_op(ctx, input, weight, bias, offset, None, keep)
+        return _forward_common(ctx, _pair, False, input, offset, None, weight, bias, stride, padding, dilation,
+                               groups, deformable_groups, in_step, grad_sync)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_output):
-        grad_output = grad_output.contiguous()
-        if not grad_output.is_cuda:
-            raise NotImplementedError
-        input, offset, weight, bias = ctx.saved_tensors
-        g = _backward_op(ctx, input, weight, bias, offset, None, grad_output)
-        return (g["grad_input"], g["grad_offset"], g["grad_weight"], g["grad_bias"] if ctx.with_bias else None,
-                None, None, None, None, None, None, None)
+        return _plain_grads(ctx, _backward_common(ctx, grad_output))
 
 
 class ModulatedDeformConv2dFunction(Function):
     @staticmethod
     def forward(ctx, input, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1,
                 groups=1, deformable_groups=1, in_step=64, grad_sync=None):
-        ctx.grad_sync = grad_sync
-        with_bias_tensor = bias
-        bias = _setup(ctx, _pair, input, bias, stride, padding, dilation, groups, deformable_groups, in_step)
-        keep = _needs_grad(input, offset, mask, weight, with_bias_tensor)
-        if keep:
-            ctx.save_for_backward(input, offset, mask, weight, bias)
-        return _forward_op(ctx, input, weight, bias, offset, mask, keep)
+        return _forward_common(ctx, _pair, True, input, offset, mask, weight, bias, stride, padding, dilation,
+                               groups, deformable_groups, in_step, grad_sync)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_output):
-        grad_output = grad_output.contiguous()
-        if not grad_output.is_cuda:
-            raise NotImplementedError
-        input, offset, mask, weight, bias = ctx.saved_tensors
-        g = _backward_op(ctx, input, weight, bias, offset, mask, grad_output)
-        return (g["grad_input"], g["grad_offset"], g["grad_mask"], g["grad_weight"],
-                g["grad_bias"] if ctx.with_bias else None, None, None, None, None, None, None, None)
+        return _modulated_grads(ctx, _backward_common(ctx, grad_output))
 
 
 class DeformConv3dFunction(Function):
     @staticmethod
     def forward(ctx, input, offset, weight, bias=None, stride=1, padding=0, dilation=1,
                 groups=1, deformable_groups=1, in_step=64, grad_sync=None):
-        ctx.grad_sync = grad_sync
-        with_bias_tensor = bias
-        bias = _setup(ctx, _triple, input, bias, stride, padding, dilation, groups, deformable_groups, in_step)
-        keep = _needs_grad(input, offset, weight, with_bias_tensor)
-        if keep:
-            ctx.save_for_backward(input, offset, weight, bias)
-        return _forward_op(ctx, input, weight, bias, offset, None, keep)
+        return _forward_common(ctx, _triple, False, input, offset, None, weight, bias, stride, padding, dilation,
+                               groups, deformable_groups, in_step, grad_sync)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_output):
-        grad_output = grad_output.contiguous()
-        if not grad_output.is_cuda:
-            raise NotImplementedError
-        input, offset, weight, bias = ctx.saved_tensors
-        g = _backward_op(ctx, input, weight, bias, offset, None, grad_output)
-        return (g["grad_input"], g["grad_offset"], g["grad_weight"], g["grad_bias"] if ctx.with_bias else None,
-                None, None, None, None, None, None, None)
+        return _plain_grads(ctx, _backward_common(ctx, grad_output))
 
 
 class ModulatedDeformConv3dFunction(Function):
     @staticmethod
     def forward(ctx, input, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1,
                 groups=1, deformable_groups=1, in_step=64, grad_sync=None):
-        ctx.grad_sync = grad_sync
-        with_bias_tensor = bias
-        bias = _setup(ctx, _triple, input, bias, stride, padding, dilation, groups, deformable_groups, in_step)
-        keep = _needs_grad(input, offset, mask, weight, with_bias_tensor)
-        if keep:
-            ctx.save_for_backward(input, offset, mask, weight, bias)
-        return _forward_op(ctx, input, weight, bias, offset, mask, keep)
+        return _forward_common(ctx, _triple, True, input, offset, mask, weight, bias, stride, padding, dilation,
+                               groups, deformable_groups, in_step, grad_sync)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_output):
-        grad_output = grad_output.contiguous()
-        if not grad_output.is_cuda:
-            raise NotImplementedError
-        input, offset, mask, weight, bias = ctx.saved_tensors
-        g = _backward_op(ctx, input, weight, bias, offset, mask, grad_output)
-        return (g["grad_input"], g["grad_offset"], g["grad_mask"], g["grad_weight"],
-                g["grad_bias"] if ctx.with_bias else None, None, None, None, None, None, None, None)
+        return _modulated_grads(ctx, _backward_common(ctx, grad_output))
 
 
 def _amp(*tensors):
@@ -308,10 +298,35 @@ def _make_producer(mod, channels_per_tap):
     return conv
 
 
+def _plain_producer(conv):
+    """True when ``conv`` is an unmodified producer as ``_make_producer`` builds it: a stock nn.Conv2d / nn.Conv3d with
+    default dilation / groups / zero padding mode and no hooks.  Only then may its forward() be bypassed."""
+    if type(conv) not in (nn.Conv2d, nn.Conv3d):
+        return False
+    if any(d != 1 for d in conv.dilation) or conv.groups != 1 or conv.padding_mode != "zeros" or conv.bias is None:
+        return False
+    if isinstance(conv.padding, str):
+        return False
+    hooks = (conv._forward_hooks, conv._forward_pre_hooks, conv._backward_hooks, conv._backward_pre_hooks,
+             getattr(conv, "_forward_hooks_with_kwargs", {}), getattr(conv, "_forward_pre_hooks_with_kwargs", {}))
+    if any(len(h) for h in hooks):
+        return False
+    # torch.nn.utils.prune / parametrizations re-compute .weight in a forward pre-hook or a property: both show up
+    # as a missing plain Parameter
+    return isinstance(conv._parameters.get("weight"), nn.Parameter) and isinstance(conv._parameters.get("bias"), nn.Parameter)
+
+
 def _offset_and_mask(mod, x):
-    """conv_offset(x), conv_mask(x) of a modulated Pack as ONE convolution launch over the concatenated filters
-    (x is read once; parameters and state-dict keys stay the reference's two separate convs)."""
+    """conv_offset(x), conv_mask(x) of a modulated Pack (reference: modulated_deform_conv.py:781-785, :835-839).
+    When both producers are plain convolutions with identical geometry they run as ONE convolution launch over the
+    concatenated filters (x is read once); anything else -- hooks, pruning, a replaced / wrapped producer, different
+    stride or padding -- goes through the submodules' own forward() exactly as the reference does."""
     co, cm = mod.conv_offset, mod.conv_mask
+    fused = (_plain_producer(co) and _plain_producer(cm) and type(co) is type(cm) and co.stride == cm.stride
+             and co.padding == cm.padding and co.kernel_size == cm.kernel_size and co.in_channels == cm.in_channels
+             and not torch.jit.is_scripting() and getattr(mod, "fuse_producers", True))
+    if not fused:
+        return co(x), cm(x)
     f = torch.nn.functional.conv2d if x.dim() == 4 else torch.nn.functional.conv3d
     both = f(x, torch.cat([co.weight, cm.weight], 0), torch.cat([co.bias, cm.bias], 0), co.stride, co.padding)
     n = co.out_channels

@@ -74,3 +74,59 @@ def test_two_rank_gloo_allreduce_matches_full_batch():
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     assert dict(ret) == {0: True, 1: True}
+
+
+def _worker_attach(rank, world, port, ret):
+    for p in (os.path.join(ROOT, "modulated-deform-conv_b200"), ROOT, HERE):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import mdconv_dist
+        import modulated_deform_conv as mdc
+        torch.manual_seed(0)
+        pack = mdc.ModulatedDeformConv2dPack(4, 4, 3, padding=1, bias=True)
+        sync = mdconv_dist.attach(pack)
+        ok = sync.active() and len(pack._grad_sync_handles) == 4     # conv_offset.{weight,bias}, conv_mask.{weight,bias}
+        # the producers' gradients are all-reduced when autograd accumulates them (sum over ranks)
+        x = torch.full((1, 4, 5, 5), float(rank + 1))
+        (pack.conv_offset(x).sum() + pack.conv_mask(x).sum()).backward()
+        ref = mdc.ModulatedDeformConv2dPack(4, 4, 3, padding=1, bias=True)
+        ref.load_state_dict(pack.state_dict())
+        xs = torch.cat([torch.full((1, 4, 5, 5), float(r + 1)) for r in range(world)])
+        (ref.conv_offset(xs).sum() + ref.conv_mask(xs).sum()).backward()
+        for a, b in ((pack.conv_offset.weight, ref.conv_offset.weight), (pack.conv_mask.bias, ref.conv_mask.bias)):
+            ok = ok and torch.allclose(a.grad, b.grad, rtol=1e-5, atol=1e-6)
+        # average=True is DDP's convention
+        mdconv_dist.detach(pack)
+        ok = ok and pack._grad_sync is None
+        # prepare_ddp: deformable-conv parameters go on DDP's ignore list, everything else stays with DDP
+        model = torch.nn.Sequential(torch.nn.Conv2d(4, 4, 3, padding=1), mdc.ModulatedDeformConv2dPack(4, 4, 3, padding=1))
+        ignored = mdconv_dist.prepare_ddp(model)
+        ok = ok and set(ignored) == {"1.weight", "1.conv_offset.weight", "1.conv_offset.bias", "1.conv_mask.weight",
+                                     "1.conv_mask.bias"}
+        ok = ok and model[1]._grad_sync.average
+        ddp = torch.nn.parallel.DistributedDataParallel(model)
+        ok = ok and set(ddp.parameters_to_ignore) == set(ignored)
+        # GradSync on a backward_ex-style dict with the fp32 flat buffer: exchange fp32, round once
+        gw = torch.full((4, 4, 3, 3), float(rank + 1), dtype=torch.float16)
+        gb = torch.full((4,), 0.5 * (rank + 1), dtype=torch.float16)
+        flat = torch.cat([gw.float().reshape(-1) + 1e-4, gb.float()])
+        s2 = mdconv_dist.GradSync(None, torch.device("cpu"))
+        g = {"grad_weight": gw, "grad_bias": gb, "flat_f32": flat}
+        s2.reduce(g, True)          # CPU tensors: in-place all-reduce in the gradients' own dtype
+        ok = ok and float(gw[0, 0, 0, 0]) == 3.0 and float(gb[0]) == 1.5
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_attach_reduces_pack_producers_and_prepare_ddp_ignores_them():
+    world = 2
+    port = 31500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_attach, args=(world, port, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}
