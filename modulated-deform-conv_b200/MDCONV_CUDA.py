@@ -132,21 +132,24 @@ _lib.mdconv_profile_read.restype = _i
 _lib.mdconv_profile_read.argtypes = [ctypes.c_char_p, _sz]
 
 
-def profile_enable(on: bool) -> None:
+def profile_enable(on: bool, keep_side_stream: bool = False) -> None:
     """Bracket every kernel this library launches with CUDA events (benchmark use).  While profiling,
-    the backward's side stream is switched off so each kernel's time is its own."""
+    the backward's side stream is switched off so each kernel's time is its own (``keep_side_stream`` leaves it
+    on: for timelines, where the overlap is the point)."""
     _lib.mdconv_profile_enable(1 if on else 0)
-    _lib.mdconv_side_stream_enable(0 if on else 1)
+    _lib.mdconv_side_stream_enable(1 if (not on or keep_side_stream) else 0)
 
 
-def profile_read():
-    """-> list of (kernel_name, milliseconds) in launch order since the last read (synchronises)."""
-    buf = ctypes.create_string_buffer(1 << 16)
+def profile_read(with_start: bool = False):
+    """-> list of (kernel_name, milliseconds) in launch order since the last read (synchronises); with
+    ``with_start`` each entry is (name, milliseconds, start_ms relative to the first launch of the batch)."""
+    buf = ctypes.create_string_buffer(1 << 18)
     _lib.mdconv_profile_read(buf, len(buf))
     out = []
     for line in buf.value.decode().splitlines():
-        name, _, ms = line.partition("=")
-        out.append((name, float(ms)))
+        name, _, rest = line.partition("=")
+        ms, _, at = rest.partition("@")
+        out.append((name, float(ms), float(at or 0.0)) if with_start else (name, float(ms)))
     return out
 
 

@@ -127,15 +127,19 @@ int mdconv_profile_read(char* buf, size_t cap) {
   std::string out;
   std::lock_guard<std::mutex> lk(g_prof_mu);
   if (g_prof) {
+    cudaEvent_t first = g_prof->empty() ? nullptr : g_prof->front().a;
     for (ProfEntry& e : *g_prof) {
-      float ms = -1.f;
+      float ms = -1.f, at = 0.f;
       if (cudaEventSynchronize(e.b) == cudaSuccess) cudaEventElapsedTime(&ms, e.a, e.b);
+      if (first != nullptr && e.a != first) cudaEventElapsedTime(&at, first, e.a);   // start, relative to the first launch
       char line[160];
-      snprintf(line, sizeof(line), "%s=%.6f\n", e.name, ms);
+      snprintf(line, sizeof(line), "%s=%.6f@%.6f\n", e.name, ms, at);
       out += line;
+      ++n;
+    }
+    for (ProfEntry& e : *g_prof) {   // only now: `first` is the first entry's start event
       cudaEventDestroy(e.a);
       cudaEventDestroy(e.b);
-      ++n;
     }
     g_prof->clear();
   }

@@ -108,6 +108,8 @@ class GradSync:
         self._stream = None
         self.event = None
         self.trace = None            # optional list of (start, stop) CUDA events around each collective (bench.py)
+        self.keep_last = False       # keep a reference to the last reduced fp32 buffer in .last_flat32 (checks)
+        self.last_flat32 = None
         if device is not None and device.type == "cuda":
             self._stream = torch.cuda.Stream(device=device)
             self.event = torch.cuda.Event()
@@ -157,6 +159,8 @@ class GradSync:
                     t.copy_(flat32[off:off + t.numel()].view(t.shape))
                     off += t.numel()
                 flat32.record_stream(self._stream)
+                if self.keep_last:
+                    self.last_flat32 = flat32
             else:
                 flat = outs[0] if len(outs) == 1 else torch.cat([t.reshape(-1) for t in outs])
                 dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
@@ -177,30 +181,36 @@ class GradSync:
 _comm_groups = {}
 
 
-def comm_group(max_ctas: int = 4):
-    """A dedicated NCCL communicator for the parameter-gradient all-reduce, limited to ``max_ctas`` CTAs: the
-    collective runs BESIDE the persistent data-gradient kernels, which own every SM they are given, so it can only
-    use the SMs those kernels leave free (mdconv_set_comm_sms) -- a communicator that wants 16+ CTAs would leave
-    most of its channels waiting for an SM.  2.4 MB per step needs no more than a few.  Collective call (every rank,
-    same order); cached per ``max_ctas``.  Returns None when the default backend is not NCCL."""
+def comm_group(max_ctas: int = 4, cga_cluster_size: int = 1):
+    """A dedicated NCCL communicator for the parameter-gradient all-reduce, limited to ``max_ctas`` CTAs that are
+    launched WITHOUT thread-block clusters (``cga_cluster_size`` 1; NCCL's default on sm_90+ is clusters of 4).
+    The collective runs BESIDE the persistent data-gradient kernels, which own every SM they are given, so it can
+    only use the SMs those kernels leave free (mdconv_set_comm_sms): a communicator that wants 16+ CTAs leaves most
+    of its channels waiting, and a cluster of 4 CTAs needs 4 free SMs of ONE GPC at the same moment, which the
+    scattered spare SMs never offer before the neighbouring kernel retires.  Collective call (every rank, same
+    order); cached per setting.  Returns None when the default backend is not NCCL."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_backend() != "nccl":
         return None
-    if max_ctas not in _comm_groups:
+    key = (int(max_ctas), int(cga_cluster_size))
+    if key not in _comm_groups:
         opts = dist.ProcessGroupNCCL.Options()
         try:
-            opts.config.max_ctas = int(max_ctas)
+            opts.config.max_ctas = key[0]
             opts.config.min_ctas = 1
+            if key[1] >= 0:
+                opts.config.cga_cluster_size = key[1]
         except Exception:
             pass
-        _comm_groups[max_ctas] = dist.new_group(backend="nccl", pg_options=opts)
-    return _comm_groups[max_ctas]
+        _comm_groups[key] = dist.new_group(backend="nccl", pg_options=opts)
+    return _comm_groups[key]
 
 
 def _is_deform_module(m) -> bool:
     return hasattr(m, "deformable_groups") and hasattr(m, "_conv_args")
 
 
-def attach(module, group=None, average: bool = False, max_ctas: Optional[int] = None) -> "GradSync":
+def attach(module, group=None, average: bool = False, max_ctas: Optional[int] = None,
+           cga_cluster_size: int = 1) -> "GradSync":
     """Make ``module`` (a DeformConv*/ModulatedDeformConv*[Pack] module of this package) all-reduce its weight / bias
     gradients inside its own backward, overlapped with the data gradients.  Every OTHER parameter of the module --
     the conv_offset / conv_mask producers of a Pack -- gets a post-accumulate-grad hook that all-reduces its
@@ -209,7 +219,7 @@ def attach(module, group=None, average: bool = False, max_ctas: Optional[int] = 
     and leave exactly that many SMs free beside the data-gradient kernels.  Returns the GradSync."""
     p = next(module.parameters())
     if max_ctas is not None and group is None and p.is_cuda:
-        group = comm_group(max_ctas)
+        group = comm_group(max_ctas, cga_cluster_size)
         import MDCONV_CUDA
         MDCONV_CUDA.set_comm_sms(max_ctas)
     sync = GradSync(group, p.device, average=average)
