@@ -165,11 +165,29 @@ def _ptr(t):
     return None if t is None or t.numel() == 0 else ctypes.c_void_p(t.data_ptr())
 
 
-def _validate(named, weight, kernel, group, nd):
-    """The reference's entry checks (src/mdeformable_conv.cu:127-148 and twins)."""
+_ACTIVATIONS = ("input", "output", "grad_output", "grad_input")
+
+
+def _cl_format(nd):
+    return torch.channels_last if nd == 2 else torch.channels_last_3d
+
+
+def _is_channels_last(t) -> bool:
+    """Dense channels-last (NHWC / NDHWC strides) and NOT also NCHW-contiguous (size-1 dims make both true)."""
+    if t is None or t.dim() not in (4, 5) or t.is_contiguous():
+        return False
+    return t.is_contiguous(memory_format=_cl_format(t.dim() - 2))
+
+
+def _validate(named, weight, kernel, group, nd, cl=False):
+    """The reference's entry checks (src/mdeformable_conv.cu:127-148 and twins).  With ``cl`` the activation
+    tensors (input / output / grad_output / grad_input) must be dense channels-last instead of NCHW-contiguous."""
     first = named[0][1]
     for name, t in named:
-        if not t.is_contiguous():
+        if cl and name in _ACTIVATIONS:
+            if not t.is_contiguous(memory_format=_cl_format(nd)):
+                raise RuntimeError(f"{name} tensor has to be channels-last like the input")
+        elif not t.is_contiguous():
             raise RuntimeError(f"{name} tensor has to be contiguous")
         if not t.is_cuda:
             raise RuntimeError(f"{name} tensor has to be a CUDA tensor (no CPU path)")
@@ -187,7 +205,7 @@ def _validate(named, weight, kernel, group, nd):
             first.shape[1], weight.shape[1] * group))
 
 
-def _geom(input, weight, kernel, stride, pad, dil, group, dgroup, modulated, with_bias):
+def _geom(input, weight, kernel, stride, pad, dil, group, dgroup, modulated, with_bias, cl=False):
     nd = input.dim() - 2
     g = _Geom()
     g.nd, g.batch, g.c_in, g.c_out = nd, input.shape[0], input.shape[1], weight.shape[0]
@@ -203,7 +221,17 @@ def _geom(input, weight, kernel, stride, pad, dil, group, dgroup, modulated, wit
     g.grad_rule = 0 if (nd == 2 and modulated) else 1
     g.with_bias = 1 if with_bias else 0
     g.path = _path_override
+    g.io_layout = 1 if cl else 0
     return g
+
+
+def _channels_last_ok(input, weight, kernel, stride, pad, dil, group, dgroup, modulated, with_bias, backward):
+    """Does the library take this call with channels-last activations?  (tcgen05 kernels only: fp16 / bf16,
+    channels per group multiples of 64, ...)"""
+    if input.dtype not in (torch.float16, torch.bfloat16):
+        return False
+    g = _geom(input, weight, kernel, stride, pad, dil, group, dgroup, modulated, with_bias, cl=True)
+    return int(_lib.mdconv_selected_path(ctypes.byref(g), 1 if backward else 0)) == 2
 
 
 def _out_shape(g, input, weight):
@@ -242,13 +270,22 @@ def _forward(input, weight, bias, offset, mask, output, kernel, stride, pad, dil
     layouts the matching backward can reuse (None when the tensor path does not run both directions)."""
     nd = len(kernel)
     modulated = mask is not None
+    # channels-last activations (torch.channels_last / channels_last_3d) are taken as they are -- the kernels gather
+    # from that layout anyway -- and the output comes back channels-last; shapes / dtypes the tcgen05 kernels do
+    # not take fall back to an NCHW copy
+    cl = _is_channels_last(input) and (output is None or _is_channels_last(output))
+    if cl and not _channels_last_ok(input, weight, kernel, stride, pad, dil, group, dgroup, modulated, with_bias,
+                                    False):
+        cl = False
+    if not cl and _is_channels_last(input) and output is None:
+        input = input.contiguous()
     named = [("input", input), ("weight", weight), ("bias", bias), ("offset", offset)]
     if modulated:
         named.append(("mask", mask))
     if output is not None:
         named.append(("output", output))
-    _validate(named, weight, kernel, group, nd)
-    g = _geom(input, weight, kernel, stride, pad, dil, group, dgroup, modulated, with_bias)
+    _validate(named, weight, kernel, group, nd, cl)
+    g = _geom(input, weight, kernel, stride, pad, dil, group, dgroup, modulated, with_bias, cl)
     shape = _out_shape(g, input, weight)
     K = 1
     for k in kernel:
@@ -260,7 +297,8 @@ def _forward(input, weight, bias, offset, mask, output, kernel, stride, pad, dil
         _expect(bias, (weight.shape[0],), "bias")
     with torch.cuda.device(input.device):
         if output is None:
-            output = torch.empty(shape, dtype=input.dtype, device=input.device)
+            output = torch.empty(shape, dtype=input.dtype, device=input.device,
+                                 memory_format=_cl_format(nd) if cl else torch.contiguous_format)
         else:
             _expect(output, shape, "output")
         ws, n = _workspace(g, False, input.device)
@@ -270,7 +308,7 @@ def _forward(input, weight, bias, offset, mask, output, kernel, stride, pad, dil
     _check(rc, "mdconv_forward")
     if keep:
         nsave = int(_lib.mdconv_saved_bytes(ctypes.byref(g))) if (_keep_layouts and ws is not None) else 0
-        return output, ((ws, nsave, g.path) if nsave > 0 else None)
+        return output, ((ws, nsave, g.path, cl) if nsave > 0 else None)
     return output
 
 
@@ -284,18 +322,30 @@ def _backward(input, weight, bias, offset, mask, grad_output, grads, kernel, str
     batch-sharded caller all-reduces)."""
     nd = len(kernel)
     modulated = mask is not None
+    # channels-last input -> channels-last grad_output in, channels-last grad_input out (when the tcgen05 backward
+    # takes the shape; otherwise NCHW copies)
+    cl = _is_channels_last(input) and grads is None and \
+        _channels_last_ok(input, weight, kernel, stride, pad, dil, group, dgroup, modulated, with_bias, True)
+    if cl:
+        grad_output = grad_output.contiguous(memory_format=_cl_format(nd))
+    else:
+        if _is_channels_last(input) and grads is None:
+            input = input.contiguous()
+        if grads is None:
+            grad_output = grad_output.contiguous()
     named = [("input", input), ("weight", weight), ("bias", bias), ("offset", offset)]
     if modulated:
         named.append(("mask", mask))
     named.append(("grad_output", grad_output))
     if grads is not None:
         named += [(k, v) for k, v in grads.items() if v is not None]
-    _validate(named, weight, kernel, group, nd)
-    g = _geom(input, weight, kernel, stride, pad, dil, group, dgroup, modulated, with_bias)
+    _validate(named, weight, kernel, group, nd, cl)
+    g = _geom(input, weight, kernel, stride, pad, dil, group, dgroup, modulated, with_bias, cl)
     _expect(grad_output, _out_shape(g, input, weight), "grad_output")
     with torch.cuda.device(input.device):
         if grads is None:
-            grads = {"grad_input": torch.empty_like(input), "grad_offset": torch.empty_like(offset),
+            grads = {"grad_input": torch.empty_like(input, memory_format=torch.preserve_format),
+                     "grad_offset": torch.empty_like(offset),
                      "grad_mask": torch.empty_like(mask) if modulated else None,
                      "grad_weight": torch.empty_like(weight),
                      "grad_bias": torch.empty_like(bias) if with_bias else torch.zeros_like(bias)}
@@ -309,7 +359,7 @@ def _backward(input, weight, bias, offset, mask, grad_output, grads, kernel, str
         stream = torch.cuda.current_stream().cuda_stream
         sv_ptr, sv_n = None, 0
         if saved is not None and saved[2] == g.path and saved[0].device == input.device and \
-                int(_lib.mdconv_saved_bytes(ctypes.byref(g))) == saved[1]:
+                (len(saved) < 4 or saved[3] == cl) and int(_lib.mdconv_saved_bytes(ctypes.byref(g))) == saved[1]:
             sv_ptr, sv_n = _ptr(saved[0]), saved[1]
         ex = _BwdExtra()
         ex.saved = sv_ptr.value if sv_ptr is not None else None

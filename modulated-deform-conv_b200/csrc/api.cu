@@ -65,7 +65,9 @@ int resolve(const mdconv_geom_t* in, DevGeom& g) {
   g.modulated = in->modulated ? 1 : 0;
   g.rule = in->grad_rule ? 1 : 0;
   g.with_bias = in->with_bias ? 1 : 0;
-  if (in->io_layout != MDCONV_LAYOUT_NCHW) return MDCONV_ERR_BAD_GEOMETRY;   // (channels-last: see below)
+  if (in->io_layout != MDCONV_LAYOUT_NCHW && in->io_layout != MDCONV_LAYOUT_CHANNELS_LAST)
+    return MDCONV_ERR_BAD_GEOMETRY;
+  g.cl = in->io_layout == MDCONV_LAYOUT_CHANNELS_LAST ? 1 : 0;
   for (int a = 0; a < 3; ++a) {
     g.fd_out[a] = make_fastdiv(g.out[a]);
     g.fd_k[a] = make_fastdiv(g.k[a]);
@@ -77,6 +79,7 @@ int resolve(const mdconv_geom_t* in, DevGeom& g) {
 
 int pick_path(const mdconv_geom_t* in, const DevGeom& g, int backward) {
   const bool can = tensor_path_supported(g, in->dtype, backward);
+  if (g.cl) return (can && in->path != MDCONV_PATH_GENERIC) ? MDCONV_PATH_TENSOR : -1;   // tensor kernels only
   if (in->path == MDCONV_PATH_GENERIC) return MDCONV_PATH_GENERIC;
   if (in->path == MDCONV_PATH_TENSOR) return can ? MDCONV_PATH_TENSOR : -1;
   return can ? MDCONV_PATH_TENSOR : MDCONV_PATH_GENERIC;

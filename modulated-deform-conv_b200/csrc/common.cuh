@@ -49,6 +49,7 @@ struct DevGeom {
   int Cg, Cog, Cdg;
   int Kg;   // Cg * K, reduction length of the per-group contraction
   int modulated, rule, with_bias;
+  int cl;   // 1: activations (input, output, grad_output, grad_input) are channels-last [B, spatial..., C]
   FastDiv fd_out[3], fd_k[3];  // divisors out[a], k[a]
   FastDiv fd_K, fd_Cdg;        // divisors K (taps), Cdg (channels per deformable group)
 };
@@ -218,6 +219,8 @@ struct LaunchCtx {
   // backward only: optional fp32 copies of the parameter gradients before rounding (mdconv_bwd_extra_t)
   float* gw32 = nullptr;
   float* gb32 = nullptr;
+  // backward only: row stride (elements) of the grad_output rows handed to the bias-gradient kernel (0: P)
+  int go_ld = 0;
 };
 // SMs left to a concurrent collective after the weight-ready event (MDCONV_B200_COMM_SMS, default 8; api.cu)
 int comm_spare_sms();

@@ -417,12 +417,12 @@ __global__ void __launch_bounds__(NT) k_generic_bwd_weight(const DevGeom g, cons
 // fixed reduction order (deterministic).
 template <typename T, typename F>
 __global__ void __launch_bounds__(NT) k_grad_bias(const DevGeom g, const T* __restrict__ go, T* __restrict__ gb,
-                                                  float* __restrict__ gb32) {
+                                                  float* __restrict__ gb32, int ld) {
   __shared__ F red[NT];
   const int co = blockIdx.x;
   F acc = (F)0;
   for (int b = 0; b < g.B; ++b) {
-    const T* row = go + ((size_t)b * g.Co + co) * g.P;
+    const T* row = go + ((size_t)b * g.Co + co) * ld;
     for (int p = threadIdx.x; p < g.P; p += NT) acc += ld_as<F>(row + p);
   }
   red[threadIdx.x] = acc;
@@ -537,7 +537,7 @@ void launch_backward(const DevGeom& g, const void* x, const void* w, const void*
   }
   if (do_bias && g.with_bias && gb != nullptr) {
     ProfScope prof(ctx, "grad_bias");
-    k_grad_bias<T, F><<<g.Co, NT, 0, ctx.stream>>>(g, (const T*)go, (T*)gb, ctx.gb32);
+    k_grad_bias<T, F><<<g.Co, NT, 0, ctx.stream>>>(g, (const T*)go, (T*)gb, ctx.gb32, ctx.go_ld > 0 ? ctx.go_ld : g.P);
     MDCONV_CHECK_LAUNCH(ctx);
   }
   if (!direct) {

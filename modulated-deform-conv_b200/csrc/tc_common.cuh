@@ -18,7 +18,13 @@ inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 // plans point every absent corner (sample out of range, corner outside the input) at that position: the reference
 // returns an exact 0 there WITHOUT reading the input (src/mdeformable_conv.cu:19-29,80), so an Inf/NaN elsewhere in x
 // must not turn into 0 * Inf = NaN through a zero-weight load of some unrelated pixel.
-inline size_t xt_bytes(const DevGeom& g) { return align256(((size_t)g.B * g.IN + 1) * g.C * 2); }
+inline size_t xt_bytes(const DevGeom& g) { return g.cl ? 0 : align256(((size_t)g.B * g.IN + 1) * g.C * 2); }
+
+// Shared by the forward and grad_input epilogues when the caller's activations are channels-last: one 64-channel
+// chunk of a 128-row accumulator tile goes TMEM -> registers -> (+bias, convert) -> a 128B-swizzled staging tile in
+// shared memory -> ONE TMA store (cp.async.bulk.tensor) of [128 rows x 64 channels]; rows past the end of the
+// tensor are clipped by the tensor map.  Two staging tiles alternate so a store overlaps the next chunk.
+constexpr int CL_STAGE_BYTES = 128 * 128;
 
 // ---- explicit shared-state-space accesses (generic LD/ST through a computed pointer is slower) ----
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
@@ -145,7 +151,10 @@ template <typename T, int ND>
 __device__ __forceinline__ PlanEntry<ND> plan_from_pos(const DevGeom& g, const RowCoord<ND>& rc,
                                                        const SamplePos<ND>& sp, int C8) {
   PlanEntry<ND> e;
-  const int zero_pos = g.B * g.IN * C8;   // the all-zero position behind the last sample (xt_bytes)
+  // NCHW callers: the all-zero position behind the last sample of the workspace copy (xt_bytes).  Channels-last
+  // callers are gathered from in place (nothing can be appended to their tensor): a zero-weight load of the
+  // sample's own first pixel stands in, the one case where a non-finite input can differ from the reference.
+  const int zero_pos = (g.cl ? rc.b : g.B) * g.IN * C8;
 #pragma unroll
   for (int c = 0; c < (1 << ND); ++c) { e.idx[c] = zero_pos; e.w[c] = 0u; }
   if (!rc.valid || !sp.in_range) return e;
@@ -227,10 +236,64 @@ __device__ __forceinline__ uint4 gather8(const uint4* __restrict__ xc, const Pla
   return interp8(v, e.w, 1 << ND, T());
 }
 
+// ---- channels-last epilogue (forward output, grad_input) ---------------------------------------------------
+__device__ __forceinline__ uint32_t pack2_storage(float a, float b, __half) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack2_storage(float a, float b, __nv_bfloat16) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// Called by all 128 epilogue threads (4 warps; thread `row` owns TMEM lane `row` = tile row) once the accumulator
+// of a tile is complete.  taddr: TMEM address of this warp's 32 lanes at the tile's first column; ncols (multiple of
+// 64) columns go out as ncols/64 TMA stores at (column col0 + 64*i, row row0) of the [rows][channels] tensor behind
+// `tmap`.  bias: NULL or the bias of column col0 (added in fp32 before the conversion).  `buf` is the caller's
+// staging-buffer toggle (kept across tiles); `leader` = the one thread that issues / tracks the bulk stores.
+// bar_id: a named barrier reserved for these 128 threads.
+template <typename T>
+__device__ __forceinline__ void epilogue_store_channels_last(uint32_t taddr, int ncols, const T* __restrict__ bias,
+                                                             uint8_t* sStage, int& buf, const CUtensorMap* tmap,
+                                                             int col0, int row0, int row, bool leader, int bar_id) {
+  for (int ch = 0; ch < ncols; ch += 64) {
+    if (leader) ptx::bulk_wait_group_read<1>();   // the store that last read this staging tile has drained it
+    ptx::named_bar_sync(bar_id, 128);
+    const uint32_t sb = ptx::smem_u32(sStage + buf * CL_STAGE_BYTES);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t v[16];
+      ptx::tmem_ld_32x16(taddr + ch + q * 16, v);
+      ptx::tmem_ld_wait();
+      float f[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        f[j] = __uint_as_float(v[j]);
+        if (bias != nullptr) f[j] += ld_as<float>(bias + ch + q * 16 + j);
+      }
+      uint4 o0, o1;
+      o0.x = pack2_storage(f[0], f[1], T());   o0.y = pack2_storage(f[2], f[3], T());
+      o0.z = pack2_storage(f[4], f[5], T());   o0.w = pack2_storage(f[6], f[7], T());
+      o1.x = pack2_storage(f[8], f[9], T());   o1.y = pack2_storage(f[10], f[11], T());
+      o1.z = pack2_storage(f[12], f[13], T()); o1.w = pack2_storage(f[14], f[15], T());
+      sts128(sb + sw128(row, 2 * q), o0);
+      sts128(sb + sw128(row, 2 * q + 1), o1);
+    }
+    ptx::fence_proxy_async_smem();                // generic-proxy writes -> visible to the TMA (async proxy) read
+    ptx::named_bar_sync(bar_id, 128);
+    if (leader) {
+      ptx::tma_store_2d(tmap, sStage + buf * CL_STAGE_BYTES, col0 + ch, row0);
+      ptx::bulk_commit_group();
+    }
+    buf ^= 1;
+  }
+}
+
 // ---- pre-pass kernels (tensor_path.cu) ----------------------------------------------------------------
 // zero_row: also clear the extra all-zero position behind the last sample (xt_bytes)
+// out_ld > 0: row stride of the output (the inverse direction, see k_to_channels_last)
 template <typename T> void launch_to_channels_last(const T* x, T* xt, int B, int C, int IN, LaunchCtx& ctx,
-                                                   bool zero_row = false);
+                                                   bool zero_row = false, int out_ld = 0);
 // W [Co][Cg][K] -> Wr [Co][(cc*K + tap)*64 + ci]   (c = cc*64 + ci)
 template <typename T> void launch_reorder_weight(const T* w, T* wr, int Co, int Cg, int K, LaunchCtx& ctx);
 
@@ -256,6 +319,22 @@ inline void opt_in_dynamic_smem(Kernel* kernel, size_t smem, std::atomic<unsigne
     return;
   }
   if (tracked) seen.fetch_or(bit, std::memory_order_release);
+}
+
+template <typename T> inline CUtensorMapDataType tmap_dtype();
+// [rows][channels] row-major tensor (a channels-last activation), box = 64 channels x 128 rows, 128B swizzle:
+// the map the channels-last epilogues store through
+template <typename T>
+inline bool encode_rows_by_channels(CUtensorMap* m, void* base, size_t rows, int channels) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)channels, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)channels * sizeof(T)};
+  const cuuint32_t box[2] = {64, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(m, tmap_dtype<T>(), 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 template <typename T>

@@ -371,15 +371,18 @@ void launch_grad_weight(const CUtensorMap& tmap, const TcGwParams& prm, int grid
 
 }  // namespace
 
+static bool data_on_tensor_cores(const DevGeom& g);
 bool tensor_backward_supported(const DevGeom& g, int dtype) {
-  (void)g; (void)dtype;
-  return true;   // maps with P % 8 != 0 go through a row-padded copy of grad_output (go_ld)
+  (void)dtype;
+  // maps with P % 8 != 0 go through a row-padded copy of grad_output (go_ld); channels-last callers need every
+  // gradient on the tensor kernels (the SIMT fallback of the data gradients reads and writes NCHW)
+  return g.cl ? data_on_tensor_cores(g) : true;
 }
 
 // leading dimension (elements) of the grad_output rows the TMA maps see, and the bytes of the padded copy
 int go_ld(const DevGeom& g) { return (g.P + 7) & ~7; }
 static size_t go_pad_bytes(const DevGeom& g) {
-  return g.P % 8 == 0 ? 0 : align256((size_t)g.B * g.Co * go_ld(g) * 2);
+  return (g.P % 8 == 0 && !g.cl) ? 0 : align256((size_t)g.B * g.Co * go_ld(g) * 2);
 }
 
 static bool data_on_tensor_cores(const DevGeom& g) { return grad_sample_supported(g) && grad_input_supported(g); }
@@ -406,13 +409,21 @@ void tensor_backward_t(const DevGeom& g, const void* x, const void* w, const voi
     xt = reinterpret_cast<const T*>(saved);
     wr = reinterpret_cast<const T*>(reinterpret_cast<const char*>(saved) + xt_bytes(g));
   }
+  if (g.cl) xt = reinterpret_cast<const T*>(x);   // channels-last callers: the input itself is the gather source
   const int S = gw_splits(g);
   float* part = reinterpret_cast<float*>(base);
   base += align256((size_t)S * g.Co * g.Kg * sizeof(float));
   // grad_output as the TMA maps read it: the caller's tensor, or a copy with rows padded to 16 bytes
   const int ld = go_ld(g);
   const void* go_tma = go;
-  if (g.P % 8 != 0) {
+  if (g.cl) {
+    // channels-last grad_output [B][P][Co] -> rows [B][Co][ld] for the two kernels that read it by TMA as a
+    // [channels x positions] operand (grad_weight, grad_sample) and for the bias gradient
+    T* gp = reinterpret_cast<T*>(base);
+    base += go_pad_bytes(g);
+    launch_to_channels_last<T>((const T*)go, gp, g.B, g.P, g.Co, ctx, false, ld);
+    go_tma = gp;
+  } else if (g.P % 8 != 0) {
     T* gp = reinterpret_cast<T*>(base);
     base += go_pad_bytes(g);
     ProfScope prof(ctx, "pad_grad_output");
@@ -430,7 +441,7 @@ void tensor_backward_t(const DevGeom& g, const void* x, const void* w, const voi
   // layout passes and ahead of the big kernels
   if (data_tc) tensor_grad_input_prepare<T>(g, off, mask, data_ws, ctx);
   if (saved == nullptr) {
-    launch_to_channels_last<T>((const T*)x, const_cast<T*>(xt), g.B, g.C, g.IN, ctx, /*zero_row=*/true);
+    if (!g.cl) launch_to_channels_last<T>((const T*)x, const_cast<T*>(xt), g.B, g.C, g.IN, ctx, /*zero_row=*/true);
     if (data_tc) launch_reorder_weight<T>((const T*)w, const_cast<T*>(wr), g.Co, g.Cg, g.K, ctx);
   }
 
@@ -479,7 +490,9 @@ void tensor_backward_t(const DevGeom& g, const void* x, const void* w, const voi
   }
 
   // grad_bias next: with it both parameter gradients are final and the caller's all-reduce may start
-  generic_backward(g, dtype, x, w, off, mask, go, gx, gw, gb, goff, gmask, nullptr, ctx, GENERIC_BWD_BIAS);
+  ctx.go_ld = ld;
+  generic_backward(g, dtype, x, w, off, mask, go_tma, gx, gw, gb, goff, gmask, nullptr, ctx, GENERIC_BWD_BIAS);
+  ctx.go_ld = 0;
   signal_weight_ready(ctx);
 
   // ---- grad_offset / grad_mask / grad_input ----

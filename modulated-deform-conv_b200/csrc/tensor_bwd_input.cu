@@ -19,6 +19,8 @@
 //   warps 4-7   epilogue: tcgen05.ld -> convert -> NCHW stores
 //   warps 8-15  gather producers: 8 lanes per input position walk the bin, 16-byte channels-last
 //               loads of grad_output, weighted accumulate, 16-byte stores into the swizzled A tile
+#include <string.h>
+
 #include <cub/device/device_scan.cuh>
 
 #include "tc_common.cuh"
@@ -279,12 +281,14 @@ template <> struct Acc8<__nv_bfloat16> {
 
 template <typename T>
 __global__ void __launch_bounds__(GI_THREADS, 1)
-k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const TcGiParams prm) {
+k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const __grid_constant__ CUtensorMap tmap_gx,
+                const TcGiParams prm) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = sA + GI_STAGES * GI_A_BYTES;
-  GiPlanRow* sPlan = reinterpret_cast<GiPlanRow*>(sB + GI_STAGES * GI_B_BYTES);
+  uint8_t* sStage = sB + GI_STAGES * GI_B_BYTES;   // two output staging tiles, channels-last callers only
+  GiPlanRow* sPlan = reinterpret_cast<GiPlanRow*>(sStage + (prm.g.cl ? 2 * CL_STAGE_BYTES : 0));
   uint64_t* bars = reinterpret_cast<uint64_t*>(sPlan + GI_PLAN_SLOTS * GI_BM);
   uint64_t* full_a = bars;
   uint64_t* full_b = full_a + GI_STAGES;
@@ -301,6 +305,7 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const TcGiParams pr
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_wt);
+    if (prm.g.cl) ptx::prefetch_tensormap(&tmap_gx);
     for (int s = 0; s < GI_STAGES; ++s) {
       ptx::mbar_init(&full_a[s], ptx::arrivals(GI_GATHER_THREADS));
       ptx::mbar_init(&full_b[s], 1);
@@ -382,6 +387,7 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const TcGiParams pr
     T* __restrict__ gx = reinterpret_cast<T*>(prm.gx);
     int as = 0;
     uint32_t aph = 0;
+    int cl_buf = 0;
     for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x) {
       const int mt = t % prm.m_tiles;
       const int nt = t / prm.m_tiles;
@@ -393,19 +399,26 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const TcGiParams pr
       ptx::mbar_wait_relaxed(&tmem_full[as], aph);
       ptx::tc_fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * GI_MAX_BN);
-      for (int cc = 0; cc < BN; cc += 16) {
-        uint32_t v[16];
-        ptx::tmem_ld_32x16(taddr + cc, v);
-        ptx::tmem_ld_wait();
-        if (valid) {
+      if (g.cl) {
+        // channels-last grad_input [B*IN][C]: 64-channel chunks through shared memory and TMA stores
+        epilogue_store_channels_last<T>(taddr, BN, nullptr, sStage, cl_buf, &tmap_gx, nt * BN, mt * GI_BM,
+                                        ew * 32 + lane, ew == 0 && lane == 0, 1);
+      } else {
+        for (int cc = 0; cc < BN; cc += 16) {
+          uint32_t v[16];
+          ptx::tmem_ld_32x16(taddr + cc, v);
+          ptx::tmem_ld_wait();
+          if (valid) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) xrow[(size_t)(cc + j) * g.IN] = cvt_to<T, float>(__uint_as_float(v[j]));
+            for (int j = 0; j < 16; ++j) xrow[(size_t)(cc + j) * g.IN] = cvt_to<T, float>(__uint_as_float(v[j]));
+          }
         }
       }
       ptx::tc_fence_before_sync();
       ptx::mbar_arrive_warp(&tmem_empty[as]);
       if (++as == 2) { as = 0; aph ^= 1; }
     }
+    if (g.cl && ew == 0 && lane == 0) ptx::bulk_wait_group<0>();   // the staging tiles must outlive their stores
   } else if (warp < GI_GATHER_WARP0) {
     // ===================== plan producers =====================
     ptx::reg_dealloc<GI_REGS_PLAN>();
@@ -553,9 +566,9 @@ __global__ void k_transpose_weight(const T* __restrict__ w, T* __restrict__ wt, 
   }
 }
 
-size_t smem_bytes_gi() {
-  return 1024 + (size_t)GI_STAGES * (GI_A_BYTES + GI_B_BYTES) + (size_t)GI_PLAN_SLOTS * GI_BM * sizeof(GiPlanRow) +
-         (3 * GI_STAGES + 2 * GI_PLAN_SLOTS + 4) * sizeof(uint64_t) + 16;
+size_t smem_bytes_gi(bool cl) {
+  return 1024 + (size_t)GI_STAGES * (GI_A_BYTES + GI_B_BYTES) + (cl ? 2 * CL_STAGE_BYTES : 0) +
+         (size_t)GI_PLAN_SLOTS * GI_BM * sizeof(GiPlanRow) + (3 * GI_STAGES + 2 * GI_PLAN_SLOTS + 4) * sizeof(uint64_t) + 16;
 }
 
 int pick_bn_gi(const DevGeom& g) {
@@ -632,9 +645,12 @@ bool grad_input_supported(const DevGeom& g) {
   return true;
 }
 
+// channels-last copy of grad_output (NCHW callers only: channels-last callers' grad_output is gathered in place)
+static size_t got_bytes(const DevGeom& g) { return g.cl ? 0 : align256((size_t)g.B * g.Co * g.P * 2); }
+
 size_t grad_input_workspace(const DevGeom& g) {
   // channels-last grad_output + transposed weight + inverse index
-  return align256((size_t)g.B * g.Co * g.P * 2) + align256((size_t)g.Co * g.Kg * 2) + gi_layout(g).total;
+  return got_bytes(g) + align256((size_t)g.Co * g.Kg * 2) + gi_layout(g).total;
 }
 
 // Stage 1 (can be issued early): the inverse index, on the side stream when there is one.  Returns with
@@ -642,7 +658,7 @@ size_t grad_input_workspace(const DevGeom& g) {
 template <typename T>
 void tensor_grad_input_prepare(const DevGeom& g, const void* off, const void* mask, void* ws, LaunchCtx& ctx) {
   char* base = reinterpret_cast<char*>(ws);
-  base += align256((size_t)g.B * g.Co * g.P * sizeof(T));
+  base += got_bytes(g);
   base += align256((size_t)g.Co * g.Kg * sizeof(T));
   const GiLayout L = gi_layout(g);
   // no fork while the caller's stream is being captured into a CUDA graph: the whole call then stays on that stream
@@ -672,13 +688,13 @@ void tensor_grad_input_prepare(const DevGeom& g, const void* off, const void* ma
 template <typename T>
 void tensor_grad_input(const DevGeom& g, const void* w, const void* go, void* gx, void* ws, LaunchCtx& ctx) {
   char* base = reinterpret_cast<char*>(ws);
-  T* got = reinterpret_cast<T*>(base);
-  base += align256((size_t)g.B * g.Co * g.P * sizeof(T));
+  const T* got = g.cl ? reinterpret_cast<const T*>(go) : reinterpret_cast<const T*>(base);
+  base += got_bytes(g);
   T* wt = reinterpret_cast<T*>(base);
   base += align256((size_t)g.Co * g.Kg * sizeof(T));
   const GiLayout L = gi_layout(g);
 
-  launch_to_channels_last<T>((const T*)go, got, g.B, g.Co, g.P, ctx);
+  if (!g.cl) launch_to_channels_last<T>((const T*)go, const_cast<T*>(got), g.B, g.Co, g.P, ctx);
   {
     ProfScope prof(ctx, "transpose_weight");
     const size_t n = (size_t)g.Co * g.Kg;
@@ -722,13 +738,19 @@ void tensor_grad_input(const DevGeom& g, const void* w, const void* go, void* gx
     if (ctx.err == cudaSuccess) ctx.err = cudaErrorInvalidValue;
     return;
   }
-  const size_t smem = smem_bytes_gi();
+  CUtensorMap tmap_gx;
+  memset(&tmap_gx, 0, sizeof(tmap_gx));
+  if (g.cl && !encode_rows_by_channels<T>(&tmap_gx, gx, (size_t)g.B * g.IN, g.C)) {
+    if (ctx.err == cudaSuccess) ctx.err = cudaErrorInvalidValue;
+    return;
+  }
+  const size_t smem = smem_bytes_gi(g.cl != 0);
   static std::atomic<unsigned long long> configured{0};
-  opt_in_dynamic_smem(k_tc_grad_input<T>, smem, configured, ctx);
+  opt_in_dynamic_smem(k_tc_grad_input<T>, smem_bytes_gi(true), configured, ctx);   // the larger of the two
   const int sms = sm_count() - ctx.spare_sms > 0 ? sm_count() - ctx.spare_sms : 1;
   const int grid = prm.total_tiles < sms ? prm.total_tiles : sms;
   ProfScope prof(ctx, "tc_grad_input");
-  k_tc_grad_input<T><<<grid, GI_THREADS, smem, ctx.stream>>>(tmap, prm);
+  k_tc_grad_input<T><<<grid, GI_THREADS, smem, ctx.stream>>>(tmap, tmap_gx, prm);
   MDCONV_CHECK_LAUNCH(ctx);
 }
 

@@ -23,6 +23,7 @@
 //
 // Replaces reference K1-K4 + G1 (src/mdeformable_conv.cu:38-87,172-184 and twins).
 #include <stdlib.h>
+#include <string.h>
 
 #include <atomic>
 
@@ -122,13 +123,16 @@ static_assert(128 * (TC_REGS_CTL + TC_REGS_EPI + TC_REGS_PLAN) + TC_GATHER_THREA
 
 template <typename T, int ND, bool MOD>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const TcFwdParams prm) {
+k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_y,
+             const TcFwdParams prm) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve-up (all stage buffers 1024-byte aligned for the 128B swizzle)
+  // carve-up (all stage buffers 1024-byte aligned for the 128B swizzle); the two output staging tiles exist only
+  // for channels-last callers (the launch asks for the extra shared memory only then)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = sA + TC_STAGES * TC_A_BYTES;
-  PlanEntry<ND>* sPlan = reinterpret_cast<PlanEntry<ND>*>(sB + TC_STAGES * TC_B_BYTES);
+  uint8_t* sStage = sB + TC_STAGES * TC_B_BYTES;
+  PlanEntry<ND>* sPlan = reinterpret_cast<PlanEntry<ND>*>(sStage + (prm.g.cl ? 2 * tc::CL_STAGE_BYTES : 0));
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sPlan) +
                                                TC_PLAN_SLOTS * TC_BM * sizeof(PlanEntry<ND>));
   uint64_t* full_a = bars;
@@ -146,6 +150,7 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const TcFwdParams prm) 
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_w);
+    if (prm.g.cl) ptx::prefetch_tensormap(&tmap_y);
     for (int s = 0; s < TC_STAGES; ++s) {
       ptx::mbar_init(&full_a[s], ptx::arrivals(TC_GATHER_THREADS));
       ptx::mbar_init(&full_b[s], 1);
@@ -230,6 +235,7 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const TcFwdParams prm) 
     const T* __restrict__ bias = reinterpret_cast<const T*>(prm.bias);
     int as = 0;
     uint32_t aph = 0;
+    int cl_buf = 0;
     for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x) {
       const int mt = t % prm.m_tiles;
       const int rest = t / prm.m_tiles;
@@ -243,16 +249,22 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const TcFwdParams prm) 
       ptx::mbar_wait_relaxed(&tmem_full[as], aph);
       ptx::tc_fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * TC_MAX_BN);
-      for (int c0 = 0; c0 < BN; c0 += 16) {
-        uint32_t v[16];
-        ptx::tmem_ld_32x16(taddr + c0, v);
-        ptx::tmem_ld_wait();
-        if (valid) {
+      if (g.cl) {
+        // channels-last output [B*P][Co]: 64-channel chunks through shared memory and TMA stores
+        tc::epilogue_store_channels_last<T>(taddr, BN, g.with_bias ? bias + co0 : nullptr, sStage, cl_buf, &tmap_y, co0,
+                                            mt * TC_BM, ew * 32 + lane, ew == 0 && lane == 0, 1);
+      } else {
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          uint32_t v[16];
+          ptx::tmem_ld_32x16(taddr + c0, v);
+          ptx::tmem_ld_wait();
+          if (valid) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float f = __uint_as_float(v[j]);
-            if (g.with_bias) f += ld_as<float>(bias + co0 + c0 + j);
-            yrow[(size_t)(c0 + j) * g.P] = cvt_to<T, float>(f);
+            for (int j = 0; j < 16; ++j) {
+              float f = __uint_as_float(v[j]);
+              if (g.with_bias) f += ld_as<float>(bias + co0 + c0 + j);
+              yrow[(size_t)(c0 + j) * g.P] = cvt_to<T, float>(f);
+            }
           }
         }
       }
@@ -260,6 +272,7 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const TcFwdParams prm) 
       ptx::mbar_arrive_warp(&tmem_empty[as]);
       if (++as == 2) { as = 0; aph ^= 1; }
     }
+    if (g.cl && ew == 0 && lane == 0) ptx::bulk_wait_group<0>();   // the staging tiles must outlive their stores
   } else if (warp < TC_GATHER_WARP0) {
     // ===================== plan producers =====================
     ptx::reg_dealloc<TC_REGS_PLAN>();
@@ -389,12 +402,14 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const TcFwdParams prm) 
 // form for sizes / pointers that are not 16-byte friendly.
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(256) k_to_channels_last(const T* __restrict__ x, T* __restrict__ xt, int C, int IN,
-                                                          int zero_row) {
+                                                          int zero_row, int out_ld) {
+  // out_ld: row stride of the output in elements (C for the dense channels-last copy; the same kernel also turns a
+  // channels-last grad_output [P][Co] back into rows [Co][ld] padded to 16 bytes: C := P, IN := Co, out_ld := ld)
   __shared__ __align__(16) T tile[64][66];  // [position][channel]
   const int b = blockIdx.z;
   const int c0 = blockIdx.y * 64, i0 = blockIdx.x * 64;
   const T* xb = x + (size_t)b * C * IN;
-  T* xtb = xt + (size_t)b * C * IN;
+  T* xtb = xt + (size_t)b * IN * out_ld;
   if (zero_row && blockIdx.x == 0 && b == 0 && threadIdx.x < 64 && c0 + (int)threadIdx.x < C)
     xt[(size_t)gridDim.z * C * IN + c0 + threadIdx.x] = cvt_to<T, float>(0.f);   // the all-zero position (xt_bytes)
   if (VEC) {
@@ -421,7 +436,7 @@ __global__ void __launch_bounds__(256) k_to_channels_last(const T* __restrict__ 
         const uint32_t* src = reinterpret_cast<const uint32_t*>(&tile[i][ch * 8]);
 #pragma unroll
         for (int k = 0; k < 4; ++k) o[k] = src[k];
-        *reinterpret_cast<uint4*>(xtb + (size_t)(i0 + i) * C + c0 + ch * 8) = v;
+        *reinterpret_cast<uint4*>(xtb + (size_t)(i0 + i) * out_ld + c0 + ch * 8) = v;
       }
     }
   } else {
@@ -442,7 +457,7 @@ __global__ void __launch_bounds__(256) k_to_channels_last(const T* __restrict__ 
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int c = tx + 32 * h;
-        if (c0 + c < C && i0 + i < IN) xtb[(size_t)(i0 + i) * C + c0 + c] = tile[i][c];
+        if (c0 + c < C && i0 + i < IN) xtb[(size_t)(i0 + i) * out_ld + c0 + c] = tile[i][c];
       }
     }
   }
@@ -467,28 +482,30 @@ __global__ void k_reorder_weight(const T* __restrict__ w, T* __restrict__ wr, in
 int pick_bn(const DevGeom& g) { return g.Cog <= TC_MAX_BN ? g.Cog : TC_MAX_BN; }
 
 template <int ND>
-size_t fwd_smem_bytes() {
-  return 1024 + (size_t)TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + (size_t)TC_PLAN_SLOTS * TC_BM * sizeof(PlanEntry<ND>) +
-         (3 * TC_STAGES + 2 * TC_PLAN_SLOTS + 4) * sizeof(uint64_t) + 16;
+size_t fwd_smem_bytes(bool cl) {
+  return 1024 + (size_t)TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + (cl ? 2 * tc::CL_STAGE_BYTES : 0) +
+         (size_t)TC_PLAN_SLOTS * TC_BM * sizeof(PlanEntry<ND>) + (3 * TC_STAGES + 2 * TC_PLAN_SLOTS + 4) * sizeof(uint64_t) +
+         16;
 }
 
 template <typename T, int ND, bool MOD>
-void launch_tc_forward(const CUtensorMap& tmap, const TcFwdParams& prm, LaunchCtx& ctx) {
-  const size_t smem = fwd_smem_bytes<ND>();
+void launch_tc_forward(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const TcFwdParams& prm, LaunchCtx& ctx) {
+  const size_t smem = fwd_smem_bytes<ND>(prm.g.cl != 0);
   static std::atomic<unsigned long long> configured{0};
-  tc::opt_in_dynamic_smem(k_tc_forward<T, ND, MOD>, smem, configured, ctx);
+  tc::opt_in_dynamic_smem(k_tc_forward<T, ND, MOD>, fwd_smem_bytes<ND>(true), configured, ctx);   // the larger of the two
   const int grid = prm.total_tiles < tc::sm_count() ? prm.total_tiles : tc::sm_count();
   ProfScope prof(ctx, "tc_forward");
-  k_tc_forward<T, ND, MOD><<<grid, TC_THREADS, smem, ctx.stream>>>(tmap, prm);
+  k_tc_forward<T, ND, MOD><<<grid, TC_THREADS, smem, ctx.stream>>>(tmap, tmap_y, prm);
   MDCONV_CHECK_LAUNCH(ctx);
 }
 
 template <typename T>
 void tensor_forward_t(const DevGeom& g, const void* x, const void* w, const void* bias, const void* off,
                       const void* mask, void* y, void* ws, LaunchCtx& ctx) {
-  T* xt = reinterpret_cast<T*>(ws);
+  // channels-last callers are gathered from in place; NCHW callers get a channels-last copy in the workspace
+  const T* xt = g.cl ? reinterpret_cast<const T*>(x) : reinterpret_cast<const T*>(ws);
   T* wr = reinterpret_cast<T*>(reinterpret_cast<char*>(ws) + tc::xt_bytes(g));
-  tc::launch_to_channels_last<T>((const T*)x, xt, g.B, g.C, g.IN, ctx, /*zero_row=*/true);
+  if (!g.cl) tc::launch_to_channels_last<T>((const T*)x, reinterpret_cast<T*>(ws), g.B, g.C, g.IN, ctx, /*zero_row=*/true);
   tc::launch_reorder_weight<T>((const T*)w, wr, g.Co, g.Cg, g.K, ctx);
   TcFwdParams prm;
   prm.g = g;
@@ -520,12 +537,18 @@ void tensor_forward_t(const DevGeom& g, const void* x, const void* w, const void
     if (ctx.err == cudaSuccess) ctx.err = cudaErrorInvalidValue;
     return;
   }
+  CUtensorMap tmap_y;
+  memset(&tmap_y, 0, sizeof(tmap_y));
+  if (g.cl && !tc::encode_rows_by_channels<T>(&tmap_y, y, (size_t)g.B * g.P, g.Co)) {
+    if (ctx.err == cudaSuccess) ctx.err = cudaErrorInvalidValue;
+    return;
+  }
   if (g.nd == 2) {
-    if (g.modulated) launch_tc_forward<T, 2, true>(tmap, prm, ctx);
-    else launch_tc_forward<T, 2, false>(tmap, prm, ctx);
+    if (g.modulated) launch_tc_forward<T, 2, true>(tmap, tmap_y, prm, ctx);
+    else launch_tc_forward<T, 2, false>(tmap, tmap_y, prm, ctx);
   } else {
-    if (g.modulated) launch_tc_forward<T, 3, true>(tmap, prm, ctx);
-    else launch_tc_forward<T, 3, false>(tmap, prm, ctx);
+    if (g.modulated) launch_tc_forward<T, 3, true>(tmap, tmap_y, prm, ctx);
+    else launch_tc_forward<T, 3, false>(tmap, tmap_y, prm, ctx);
   }
 }
 
@@ -591,12 +614,13 @@ int sm_count() {
 }
 
 template <typename T>
-void launch_to_channels_last(const T* x, T* xt, int B, int C, int IN, LaunchCtx& ctx, bool zero_row) {
-  ProfScope prof(ctx, "to_channels_last");
+void launch_to_channels_last(const T* x, T* xt, int B, int C, int IN, LaunchCtx& ctx, bool zero_row, int out_ld) {
+  ProfScope prof(ctx, out_ld > 0 ? "from_channels_last" : "to_channels_last");
+  if (out_ld <= 0) out_ld = C;
   dim3 grid((unsigned)((IN + 63) / 64), (unsigned)((C + 63) / 64), (unsigned)B);
-  const bool vec = IN % 8 == 0 && C % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)xt & 15) == 0;
-  if (vec) k_to_channels_last<T, true><<<grid, 256, 0, ctx.stream>>>(x, xt, C, IN, zero_row ? 1 : 0);
-  else k_to_channels_last<T, false><<<grid, 256, 0, ctx.stream>>>(x, xt, C, IN, zero_row ? 1 : 0);
+  const bool vec = IN % 8 == 0 && C % 8 == 0 && out_ld % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)xt & 15) == 0;
+  if (vec) k_to_channels_last<T, true><<<grid, 256, 0, ctx.stream>>>(x, xt, C, IN, zero_row ? 1 : 0, out_ld);
+  else k_to_channels_last<T, false><<<grid, 256, 0, ctx.stream>>>(x, xt, C, IN, zero_row ? 1 : 0, out_ld);
   MDCONV_CHECK_LAUNCH(ctx);
 }
 template <typename T>
@@ -607,9 +631,9 @@ void launch_reorder_weight(const T* w, T* wr, int Co, int Cg, int K, LaunchCtx& 
   k_reorder_weight<T><<<blocks, 256, 0, ctx.stream>>>(w, wr, Co, Cg, K);
   MDCONV_CHECK_LAUNCH(ctx);
 }
-template void launch_to_channels_last<__half>(const __half*, __half*, int, int, int, LaunchCtx&, bool);
+template void launch_to_channels_last<__half>(const __half*, __half*, int, int, int, LaunchCtx&, bool, int);
 template void launch_to_channels_last<__nv_bfloat16>(const __nv_bfloat16*, __nv_bfloat16*, int, int, int, LaunchCtx&,
-                                                     bool);
+                                                     bool, int);
 template void launch_reorder_weight<__half>(const __half*, __half*, int, int, int, LaunchCtx&);
 template void launch_reorder_weight<__nv_bfloat16>(const __nv_bfloat16*, __nv_bfloat16*, int, int, int, LaunchCtx&);
 
@@ -636,6 +660,7 @@ bool tensor_path_supported(const DevGeom& g, int dtype, int backward) {
   if (dtype != MDCONV_F16 && dtype != MDCONV_BF16) return false;
   if (g.Cg % TC_BK != 0 || g.Cdg % TC_BK != 0) return false;
   if (((long long)g.B * g.IN + 1) * (g.C / 8) > 2147483647LL) return false;
+  if (g.cl && (g.Cog % 64 != 0 || g.Co % 8 != 0 || g.C % 8 != 0)) return false;   // 64-channel TMA store chunks
   if (backward) return tc::tensor_backward_supported(g, dtype);
   if (g.Cog % 32 != 0) return false;
   if (g.Cog > TC_MAX_BN && g.Cog % TC_MAX_BN != 0) return false;

@@ -80,8 +80,7 @@ def _forward_common(ctx, ntuple, modulated, input, offset, mask, weight, bias, s
 
 
 def _backward_common(ctx, grad_output):
-    """-> (dict of gradients, with_bias)"""
-    grad_output = grad_output.contiguous()
+    """-> dict of gradients"""
     if not grad_output.is_cuda:
         raise NotImplementedError
     saved = list(ctx.saved_tensors)

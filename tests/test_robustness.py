@@ -119,3 +119,68 @@ def test_tensor_backward_takes_maps_with_any_position_count(hw):
     ref = _oracle(case, t)
     for k, r in ref.items():
         assert rel_err(out[k], r) < 1e-2, (k, rel_err(out[k], r))
+
+
+@pytest.mark.parametrize("name", ["tc_m2d_c256_multi_tile", "tc_m2d_ragged", "tc_m2d_g2", "tc_d2d_c64", "tc_m3d_c64",
+                                  "tc_m2d_stride2_dg2"])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16], ids=["f16", "bf16"])
+def test_channels_last_io_matches_nchw_bitwise(name, dtype):
+    """activations in torch.channels_last / channels_last_3d go through the SAME kernels with no
+    re-layout pass of x (the gather reads the caller's tensor in place), the output and grad_input come back
+    channels-last through TMA stores, and every result has the bits of the NCHW call."""
+    import MDCONV_CUDA as M
+    import modulated_deform_conv as mdc
+    from cases import TENSOR_CASES
+    case = {c.name: c for c in TENSOR_CASES}[name]
+    t = make_inputs(case, dtype)
+    fmt = torch.channels_last if case.nd == 2 else torch.channels_last_3d
+    fn = {(2, False): mdc.deform_conv2d, (2, True): mdc.modulated_deform_conv2d,
+          (3, False): mdc.deform_conv3d, (3, True): mdc.modulated_deform_conv3d}[(case.nd, case.modulated)]
+
+    def run(cl):
+        lv = {k: (v.cuda().requires_grad_() if v is not None and k != "grad_output" else v) for k, v in t.items()}
+        x = lv["x"]
+        if cl:
+            x = lv["x"].detach().contiguous(memory_format=fmt).requires_grad_()
+        args = [x, lv["offset"]] + ([lv["mask"]] if case.modulated else []) + \
+               [lv["weight"], lv["bias"], case.s, case.p, case.d, case.g, case.dg, 64]
+        M.profile_enable(True)
+        try:
+            y = fn(*args)
+            go = t["grad_output"].cuda()
+            y.backward(go.contiguous(memory_format=fmt) if cl else go)
+            torch.cuda.synchronize()
+            names = [n for n, _ in M.profile_read()]
+        finally:
+            M.profile_enable(False)
+        out = {"y": y.detach(), "grad_input": x.grad, "grad_offset": lv["offset"].grad, "grad_weight": lv["weight"].grad}
+        if case.modulated:
+            out["grad_mask"] = lv["mask"].grad
+        if case.bias:
+            out["grad_bias"] = lv["bias"].grad
+        return out, names
+
+    ref, names_ref = run(False)
+    got, names = run(True)
+    assert got["y"].is_contiguous(memory_format=fmt) and got["grad_input"].is_contiguous(memory_format=fmt)
+    assert "to_channels_last" in names_ref and "to_channels_last" not in names, names
+    assert names.count("from_channels_last") == 1
+    for k in ref:
+        assert torch.equal(got[k].contiguous(), ref[k].contiguous()), k
+    orc = _oracle(case, t)
+    tol = 1e-2 if dtype == torch.float16 else 3e-2
+    for k, r in orc.items():
+        assert rel_err(got[k].contiguous().double().cpu().numpy(), r) < tol, k
+
+
+def test_channels_last_input_on_an_unsupported_shape_falls_back_to_a_copy():
+    """fp32 / small-channel calls have no channels-last kernels: the binding converts, results are the NCHW ones."""
+    import modulated_deform_conv as mdc
+    case = Case("cl_fallback", 2, True, B=2, C=8, Co=8, size=(9, 7), seed=305)
+    t = make_inputs(case, torch.float32)
+    d = {k: (v.cuda() if v is not None else None) for k, v in t.items()}
+    y0 = mdc.modulated_deform_conv2d(d["x"], d["offset"], d["mask"], d["weight"], d["bias"], case.s, case.p, case.d)
+    xcl = d["x"].contiguous(memory_format=torch.channels_last).requires_grad_()
+    y1 = mdc.modulated_deform_conv2d(xcl, d["offset"], d["mask"], d["weight"], d["bias"], case.s, case.p, case.d)
+    y1.sum().backward()
+    assert torch.equal(y0, y1) and xcl.grad is not None and xcl.grad.shape == xcl.shape
