@@ -134,6 +134,35 @@ int mdconv_forward(const mdconv_geom_t* g, const void* input, const void* weight
                    const void* offset, const void* mask, void* output, void* workspace,
                    size_t workspace_bytes, void* stream);
 
+/* Optional extras of a forward call (ABI version 3); every field may be 0 / NULL.
+ *   input_channels_last: a buffer mdconv_to_channels_last() filled from THIS input (mdconv_channels_last_bytes()
+ *     bytes).  The forward then skips its own re-layout pass, so several operators over one input -- a Pack module's
+ *     offset/mask producer convolution and its deformable convolution (reference modulated_deform_conv.py:781-785)
+ *     -- share one.  If it is the head of `workspace` itself, the saved-layout hand-off to the backward still works;
+ *     if it lives elsewhere the workspace only has to hold the re-ordered weight (c_out * (c_in/groups) * K * 2
+ *     bytes rounded up to 256).
+ *   regular_grid = 1: there is no offset tensor; every tap samples its integer grid position, i.e. a plain
+ *     convolution with this geometry's kernel / stride / pad / dilation (modulated must be 0, deformable_groups 1,
+ *     offset and mask NULL).  This is the producer of the Pack modules, run on the same kernel as the deformable
+ *     forward (fp16 / bf16, c_in a multiple of 64).  c_out must be a multiple of 32: pad the filter bank with zero
+ *     rows and say how many channels are real in c_out_valid; channels [split, c_out_valid) go to output2
+ *     [B, c_out_valid - split, P] and channels [0, split) to output [B, split, P] (output2 NULL: one tensor
+ *     [B, c_out_valid, P]). */
+typedef struct mdconv_fwd_extra {
+  const void* input_channels_last;
+  int32_t regular_grid;
+  int32_t c_out_valid;
+  void* output2;
+  int32_t split;
+} mdconv_fwd_extra_t;
+
+int mdconv_forward_ex(const mdconv_geom_t* g, const void* input, const void* weight, const void* bias,
+                      const void* offset, const void* mask, void* output, void* workspace,
+                      size_t workspace_bytes, const mdconv_fwd_extra_t* extra, void* stream);
+/* Bytes of the channels-last copy (0 when the tcgen05 path does not take this geometry), and the pass itself. */
+size_t mdconv_channels_last_bytes(const mdconv_geom_t* g);
+int mdconv_to_channels_last(const mdconv_geom_t* g, const void* input, void* channels_last, void* stream);
+
 /* Any of grad_bias / grad_mask may be NULL (with_bias == 0 / modulated == 0). */
 int mdconv_backward(const mdconv_geom_t* g, const void* input, const void* weight, const void* offset,
                     const void* mask, const void* grad_output, void* grad_input, void* grad_weight,

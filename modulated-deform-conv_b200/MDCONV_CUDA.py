@@ -41,6 +41,12 @@ class _Geom(ctypes.Structure):
                 ("path", ctypes.c_int32), ("io_layout", ctypes.c_int32)]
 
 
+class _FwdExtra(ctypes.Structure):
+    """struct mdconv_fwd_extra (include/mdconv_b200.h)."""
+    _fields_ = [("input_channels_last", ctypes.c_void_p), ("regular_grid", ctypes.c_int32),
+                ("c_out_valid", ctypes.c_int32), ("output2", ctypes.c_void_p), ("split", ctypes.c_int32)]
+
+
 class _BwdExtra(ctypes.Structure):
     """struct mdconv_bwd_extra (include/mdconv_b200.h)."""
     _fields_ = [("saved", ctypes.c_void_p), ("saved_bytes", ctypes.c_size_t), ("weight_ready_event", ctypes.c_void_p),
@@ -66,6 +72,12 @@ _lib.mdconv_saved_bytes.restype = _sz
 _lib.mdconv_saved_bytes.argtypes = [ctypes.POINTER(_Geom)]
 _lib.mdconv_backward_saved.restype = _i
 _lib.mdconv_backward_saved.argtypes = [ctypes.POINTER(_Geom)] + [_vp] * 11 + [_sz, _vp, _sz, _vp, _vp]
+_lib.mdconv_forward_ex.restype = _i
+_lib.mdconv_forward_ex.argtypes = [ctypes.POINTER(_Geom)] + [_vp] * 7 + [_sz, ctypes.POINTER(_FwdExtra), _vp]
+_lib.mdconv_channels_last_bytes.restype = _sz
+_lib.mdconv_channels_last_bytes.argtypes = [ctypes.POINTER(_Geom)]
+_lib.mdconv_to_channels_last.restype = _i
+_lib.mdconv_to_channels_last.argtypes = [ctypes.POINTER(_Geom), _vp, _vp, _vp]
 _lib.mdconv_backward_ex.restype = _i
 _lib.mdconv_backward_ex.argtypes = [ctypes.POINTER(_Geom)] + [_vp] * 11 + [_sz, ctypes.POINTER(_BwdExtra), _vp]
 _lib.mdconv_set_comm_sms.restype = _i
@@ -265,7 +277,7 @@ def set_keep_layouts(on: bool) -> None:
 
 
 def _forward(input, weight, bias, offset, mask, output, kernel, stride, pad, dil, group, dgroup, with_bias,
-             keep=False):
+             keep=False, prelaid=None):
     """-> output, or (output, saved) when ``keep``: ``saved`` is the workspace tensor whose head holds the
     layouts the matching backward can reuse (None when the tensor path does not run both directions)."""
     nd = len(kernel)
@@ -301,10 +313,21 @@ def _forward(input, weight, bias, offset, mask, output, kernel, stride, pad, dil
                                  memory_format=_cl_format(nd) if cl else torch.contiguous_format)
         else:
             _expect(output, shape, "output")
-        ws, n = _workspace(g, False, input.device)
         stream = torch.cuda.current_stream().cuda_stream
-        rc = _lib.mdconv_forward(ctypes.byref(g), _ptr(input), _ptr(weight), _ptr(bias) if with_bias else None,
-                                 _ptr(offset), _ptr(mask), _ptr(output), _ptr(ws), n, ctypes.c_void_p(stream))
+        ex = None
+        if prelaid is not None and not cl and prelaid.device == input.device and \
+                prelaid.numel() >= int(_lib.mdconv_workspace_bytes(ctypes.byref(g), 0)) > 0 and \
+                int(_lib.mdconv_channels_last_bytes(ctypes.byref(g))) > 0:
+            # `prelaid` is a forward workspace whose head already holds the channels-last copy of THIS input
+            # (to_channels_last): use it as the workspace, skip the re-layout pass
+            ws, n = prelaid, prelaid.numel()
+            ex = _FwdExtra()
+            ex.input_channels_last = ws.data_ptr()
+        else:
+            ws, n = _workspace(g, False, input.device)
+        rc = _lib.mdconv_forward_ex(ctypes.byref(g), _ptr(input), _ptr(weight), _ptr(bias) if with_bias else None,
+                                    _ptr(offset), _ptr(mask), _ptr(output), _ptr(ws), n,
+                                    ctypes.byref(ex) if ex is not None else None, ctypes.c_void_p(stream))
     _check(rc, "mdconv_forward")
     if keep:
         nsave = int(_lib.mdconv_saved_bytes(ctypes.byref(g))) if (_keep_layouts and ws is not None) else 0
@@ -381,11 +404,79 @@ def _backward(input, weight, bias, offset, mask, grad_output, grads, kernel, str
 
 
 def forward_ex(input, weight, bias, offset, mask, output, kernel, stride, pad, dil, group, deformable_group,
-               with_bias, keep=False):
+               with_bias, keep=False, prelaid=None):
     """Generic form of the four forwards (mask None = plain op; output None = allocate).  With ``keep`` it
-    returns (output, saved) for ``backward_ex``; used by the autograd Functions."""
+    returns (output, saved) for ``backward_ex``; used by the autograd Functions.  ``prelaid``: what
+    ``to_channels_last`` returned for this input and geometry (the re-layout pass is then skipped)."""
     return _forward(input, weight, bias, offset, mask, output, tuple(kernel), tuple(stride), tuple(pad), tuple(dil),
-                    group, deformable_group, with_bias, keep=keep)
+                    group, deformable_group, with_bias, keep=keep, prelaid=prelaid)
+
+
+def to_channels_last(input, weight, kernel, stride, pad, dil, group, deformable_group, modulated, with_bias):
+    """Run the forward's re-layout pass on its own: -> a forward WORKSPACE tensor for this geometry whose head holds
+    the channels-last copy of ``input`` (pass it as ``prelaid`` to forward_ex / producer_conv), or None when the
+    tcgen05 path does not take the call (then every op simply does its own thing)."""
+    if not input.is_cuda or input.dtype not in (torch.float16, torch.bfloat16) or not input.is_contiguous():
+        return None
+    g = _geom(input, weight, tuple(kernel), tuple(stride), tuple(pad), tuple(dil), group, deformable_group, modulated,
+              with_bias)
+    if int(_lib.mdconv_channels_last_bytes(ctypes.byref(g))) == 0:
+        return None
+    with torch.cuda.device(input.device):
+        ws, n = _workspace(g, False, input.device)
+        rc = _lib.mdconv_to_channels_last(ctypes.byref(g), _ptr(input), _ptr(ws),
+                                          ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _check(rc, "mdconv_to_channels_last")
+    return ws
+
+
+def producer_conv(input, weight, bias, n_first, kernel, stride, pad, prelaid=None):
+    """Plain convolution on the deformable forward kernel in regular-grid mode (mdconv_fwd_extra_t.regular_grid):
+    the offset / mask producer of the Pack modules.  weight [n, C, *kernel], bias [n]; the first ``n_first`` output
+    channels come back as one tensor and the rest as a second one (None when n_first == n).  The filter bank is
+    padded with zero rows to a multiple of 32 internally.  fp16 / bf16, C a multiple of 64, dilation 1, groups 1."""
+    nd = len(kernel)
+    n = weight.shape[0]
+    npad = (n + 31) // 32 * 32
+    if npad != n:
+        weight = torch.cat([weight, weight.new_zeros((npad - n,) + tuple(weight.shape[1:]))], 0)
+        bias = torch.cat([bias, bias.new_zeros(npad - n)], 0)
+    weight, bias = weight.contiguous(), bias.contiguous()
+    _validate([("input", input), ("weight", weight), ("bias", bias)], weight, kernel, 1, nd)
+    g = _geom(input, weight, kernel, stride, pad, (1,) * nd, 1, 1, False, True)
+    g.path = 2
+    shape = _out_shape(g, input, weight)
+    with torch.cuda.device(input.device):
+        out1 = torch.empty((shape[0], n_first) + shape[2:], dtype=input.dtype, device=input.device)
+        out2 = torch.empty((shape[0], n - n_first) + shape[2:], dtype=input.dtype, device=input.device) \
+            if n_first < n else None
+        need = int(_lib.mdconv_workspace_bytes(ctypes.byref(g), 0))
+        ex = _FwdExtra()
+        ex.regular_grid = 1
+        ex.c_out_valid = n
+        ex.output2 = out2.data_ptr() if out2 is not None else None
+        ex.split = n_first if out2 is not None else 0
+        if prelaid is not None and prelaid.device == input.device:
+            # the channels-last copy at the head of the deformable conv's workspace is shared; the re-ordered
+            # producer filters go to a workspace of their own (same head offset, so only the tail is written)
+            ex.input_channels_last = prelaid.data_ptr()
+            need = (weight.numel() * weight.element_size() + 255) // 256 * 256
+        ws = torch.empty(need, dtype=torch.uint8, device=input.device)
+        rc = _lib.mdconv_forward_ex(ctypes.byref(g), _ptr(input), _ptr(weight), _ptr(bias), None, None, _ptr(out1),
+                                    _ptr(ws), need, ctypes.byref(ex),
+                                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _check(rc, "mdconv_forward_ex(regular_grid)")
+    return out1, out2
+
+
+def producer_conv_supported(input, n_out, kernel, stride, pad) -> bool:
+    if not input.is_cuda or input.dtype not in (torch.float16, torch.bfloat16) or not input.is_contiguous():
+        return False
+    npad = (n_out + 31) // 32 * 32
+    w = torch.empty((npad, input.shape[1]) + tuple(kernel), dtype=input.dtype, device="meta")
+    g = _geom(input, w, tuple(kernel), tuple(stride), tuple(pad), (1,) * len(kernel), 1, 1, False, True)
+    g.path = 0
+    return int(_lib.mdconv_selected_path(ctypes.byref(g), 0)) == 2
 
 
 def backward_ex(input, weight, bias, offset, mask, grad_output, kernel, stride, pad, dil, group, deformable_group,

@@ -202,24 +202,68 @@ size_t mdconv_workspace_bytes(const mdconv_geom_t* gi, int backward) {
 int mdconv_forward(const mdconv_geom_t* gi, const void* input, const void* weight, const void* bias,
                    const void* offset, const void* mask, void* output, void* workspace, size_t workspace_bytes,
                    void* stream) {
+  return mdconv_forward_ex(gi, input, weight, bias, offset, mask, output, workspace, workspace_bytes, nullptr, stream);
+}
+
+int mdconv_forward_ex(const mdconv_geom_t* gi, const void* input, const void* weight, const void* bias,
+                      const void* offset, const void* mask, void* output, void* workspace, size_t workspace_bytes,
+                      const mdconv_fwd_extra_t* extra, void* stream) {
   DevGeom g;
   int rc = resolve(gi, g);
   if (rc != MDCONV_OK) return rc;
-  if (!input || !weight || !offset || !output) return MDCONV_ERR_NULL_POINTER;
+  FwdExtra ex;
+  if (extra != nullptr) {
+    ex.xt = extra->input_channels_last;
+    ex.grid = extra->regular_grid ? 1 : 0;
+    ex.co_valid = extra->c_out_valid;
+    ex.y2 = extra->output2;
+    ex.split = extra->split;
+  }
+  if (ex.grid) {
+    if (g.modulated || g.dg != 1 || g.cl || offset != nullptr || mask != nullptr) return MDCONV_ERR_BAD_GEOMETRY;
+    if (ex.co_valid < 0 || ex.co_valid > g.Co || (ex.y2 != nullptr && (ex.split < 1 || ex.split >= (ex.co_valid ? ex.co_valid : g.Co))))
+      return MDCONV_ERR_BAD_GEOMETRY;
+    if (g.g != 1 && ex.co_valid != 0 && ex.co_valid != g.Co) return MDCONV_ERR_BAD_GEOMETRY;
+  } else if (ex.y2 != nullptr || ex.co_valid != 0) {
+    return MDCONV_ERR_BAD_GEOMETRY;
+  }
+  if (!input || !weight || !output || (!offset && !ex.grid)) return MDCONV_ERR_NULL_POINTER;
   if (g.modulated && !mask) return MDCONV_ERR_NULL_POINTER;
   if (g.with_bias && !bias) return MDCONV_ERR_NULL_POINTER;
   const int path = pick_path(gi, g, 0);
   if (path < 0) return MDCONV_ERR_BAD_GEOMETRY;
-  const size_t need = path == MDCONV_PATH_TENSOR ? tensor_workspace_bytes(g, gi->dtype, 0)
-                                                 : generic_workspace_bytes(g, gi->dtype, 0);
+  if ((ex.grid || ex.xt != nullptr) && path != MDCONV_PATH_TENSOR) return MDCONV_ERR_BAD_GEOMETRY;   // tcgen05 kernels only
+  if (ex.xt != nullptr && g.cl) return MDCONV_ERR_BAD_GEOMETRY;
+  size_t need = path == MDCONV_PATH_TENSOR ? tensor_workspace_bytes(g, gi->dtype, 0)
+                                           : generic_workspace_bytes(g, gi->dtype, 0);
+  if (ex.xt != nullptr && ex.xt != workspace) need = tensor_weight_layout_bytes(g);   // only the re-ordered weight
   if (need > 0 && (workspace == nullptr || workspace_bytes < need || ((uintptr_t)workspace & 255)))
     return MDCONV_ERR_WORKSPACE;
   LaunchCtx ctx{(cudaStream_t)stream, 0, cudaSuccess};
   (void)cudaGetLastError();
   if (path == MDCONV_PATH_TENSOR)
-    tensor_forward(g, gi->dtype, input, weight, bias, offset, mask, output, workspace, ctx);
+    tensor_forward(g, gi->dtype, input, weight, bias, offset, mask, output, workspace, ex, ctx);
   else
     generic_forward(g, gi->dtype, input, weight, bias, offset, mask, output, ctx);
+  return finish(ctx);
+}
+
+size_t mdconv_channels_last_bytes(const mdconv_geom_t* gi) {
+  DevGeom g;
+  if (resolve(gi, g) != MDCONV_OK || g.cl) return 0;
+  if (pick_path(gi, g, 0) != MDCONV_PATH_TENSOR) return 0;
+  return tensor_channels_last_bytes(g);
+}
+
+int mdconv_to_channels_last(const mdconv_geom_t* gi, const void* input, void* channels_last, void* stream) {
+  DevGeom g;
+  int rc = resolve(gi, g);
+  if (rc != MDCONV_OK) return rc;
+  if (!input || !channels_last) return MDCONV_ERR_NULL_POINTER;
+  if (g.cl || pick_path(gi, g, 0) != MDCONV_PATH_TENSOR || ((uintptr_t)channels_last & 255)) return MDCONV_ERR_BAD_GEOMETRY;
+  LaunchCtx ctx{(cudaStream_t)stream, 0, cudaSuccess};
+  (void)cudaGetLastError();
+  tensor_to_channels_last(g, gi->dtype, input, channels_last, ctx);
   return finish(ctx);
 }
 

@@ -189,6 +189,34 @@ __device__ __forceinline__ PlanEntry<ND> make_plan_entry(const DevGeom& g, const
   return plan_from_pos<T, ND>(g, rc, sp, C8);
 }
 
+// Regular-grid plan (plain convolution): tap (row, tap) reads ONE input position, base + tap * dilation, or the
+// all-zero position when that lies in the padding.  Only idx[0] is used by the consumer.
+template <typename T, int ND>
+__device__ __forceinline__ PlanEntry<ND> make_grid_entry(const DevGeom& g, const RowCoord<ND>& rc, int tap, int C8) {
+  PlanEntry<ND> e;
+  const int zero_pos = (g.cl ? rc.b : g.B) * g.IN * C8;
+#pragma unroll
+  for (int c = 0; c < (1 << ND); ++c) { e.idx[c] = zero_pos; e.w[c] = 0u; }
+  if (!rc.valid) return e;
+  int tt[3];
+  if (ND == 2) {
+    tt[0] = fdiv(tap, g.fd_k[1]); tt[1] = tap - tt[0] * g.k[1];
+  } else {
+    const int q = fdiv(tap, g.fd_k[2]); tt[2] = tap - q * g.k[2];
+    tt[0] = fdiv(q, g.fd_k[1]); tt[1] = q - tt[0] * g.k[1];
+  }
+  bool ok = true;
+  int pix = 0;
+#pragma unroll
+  for (int a = 0; a < ND; ++a) {
+    const int ia = rc.base[a] + tt[a] * g.d[a];
+    ok = ok && ia >= 0 && ia < g.in[a];
+    pix = pix * g.in[a] + ia;
+  }
+  if (ok) e.idx[0] = (rc.b * g.IN + pix) * C8;
+  return e;
+}
+
 template <int ND>
 __device__ __forceinline__ void store_plan(uint32_t saddr, const PlanEntry<ND>& e) {
   const uint4* q = reinterpret_cast<const uint4*>(&e);

@@ -279,7 +279,9 @@ template <> struct Acc8<__nv_bfloat16> {
   }
 };
 
-template <typename T>
+// CL: the caller's activations are channels-last (grad_output is gathered in place, grad_input leaves through TMA
+// stores); a compile-time switch so the NCHW instantiation carries none of that epilogue's registers or code.
+template <typename T, bool CL>
 __global__ void __launch_bounds__(GI_THREADS, 1)
 k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const __grid_constant__ CUtensorMap tmap_gx,
                 const TcGiParams prm) {
@@ -288,7 +290,7 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const __grid_consta
   uint8_t* sA = smem;
   uint8_t* sB = sA + GI_STAGES * GI_A_BYTES;
   uint8_t* sStage = sB + GI_STAGES * GI_B_BYTES;   // two output staging tiles, channels-last callers only
-  GiPlanRow* sPlan = reinterpret_cast<GiPlanRow*>(sStage + (prm.g.cl ? 2 * CL_STAGE_BYTES : 0));
+  GiPlanRow* sPlan = reinterpret_cast<GiPlanRow*>(sStage + (CL ? 2 * CL_STAGE_BYTES : 0));
   uint64_t* bars = reinterpret_cast<uint64_t*>(sPlan + GI_PLAN_SLOTS * GI_BM);
   uint64_t* full_a = bars;
   uint64_t* full_b = full_a + GI_STAGES;
@@ -305,7 +307,7 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const __grid_consta
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_wt);
-    if (prm.g.cl) ptx::prefetch_tensormap(&tmap_gx);
+    if (CL) ptx::prefetch_tensormap(&tmap_gx);
     for (int s = 0; s < GI_STAGES; ++s) {
       ptx::mbar_init(&full_a[s], ptx::arrivals(GI_GATHER_THREADS));
       ptx::mbar_init(&full_b[s], 1);
@@ -399,7 +401,7 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const __grid_consta
       ptx::mbar_wait_relaxed(&tmem_full[as], aph);
       ptx::tc_fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * GI_MAX_BN);
-      if (g.cl) {
+      if (CL) {
         // channels-last grad_input [B*IN][C]: 64-channel chunks through shared memory and TMA stores
         epilogue_store_channels_last<T>(taddr, BN, nullptr, sStage, cl_buf, &tmap_gx, nt * BN, mt * GI_BM,
                                         ew * 32 + lane, ew == 0 && lane == 0, 1);
@@ -418,7 +420,7 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const __grid_consta
       ptx::mbar_arrive_warp(&tmem_empty[as]);
       if (++as == 2) { as = 0; aph ^= 1; }
     }
-    if (g.cl && ew == 0 && lane == 0) ptx::bulk_wait_group<0>();   // the staging tiles must outlive their stores
+    if (CL && ew == 0 && lane == 0) ptx::bulk_wait_group<0>();   // the staging tiles must outlive their stores
   } else if (warp < GI_GATHER_WARP0) {
     // ===================== plan producers =====================
     ptx::reg_dealloc<GI_REGS_PLAN>();
@@ -745,12 +747,14 @@ void tensor_grad_input(const DevGeom& g, const void* w, const void* go, void* gx
     return;
   }
   const size_t smem = smem_bytes_gi(g.cl != 0);
-  static std::atomic<unsigned long long> configured{0};
-  opt_in_dynamic_smem(k_tc_grad_input<T>, smem_bytes_gi(true), configured, ctx);   // the larger of the two
+  static std::atomic<unsigned long long> configured{0}, configured_cl{0};
+  if (g.cl) opt_in_dynamic_smem(k_tc_grad_input<T, true>, smem, configured_cl, ctx);
+  else opt_in_dynamic_smem(k_tc_grad_input<T, false>, smem, configured, ctx);
   const int sms = sm_count() - ctx.spare_sms > 0 ? sm_count() - ctx.spare_sms : 1;
   const int grid = prm.total_tiles < sms ? prm.total_tiles : sms;
   ProfScope prof(ctx, "tc_grad_input");
-  k_tc_grad_input<T><<<grid, GI_THREADS, smem, ctx.stream>>>(tmap, tmap_gx, prm);
+  if (g.cl) k_tc_grad_input<T, true><<<grid, GI_THREADS, smem, ctx.stream>>>(tmap, tmap_gx, prm);
+  else k_tc_grad_input<T, false><<<grid, GI_THREADS, smem, ctx.stream>>>(tmap, tmap_gx, prm);
   MDCONV_CHECK_LAUNCH(ctx);
 }
 

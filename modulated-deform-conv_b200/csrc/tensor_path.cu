@@ -59,6 +59,9 @@ struct TcFwdParams {
   const void* mask;
   const void* bias;
   void* y;
+  void* y2;          // regular-grid producer: channels [split, co_valid) go here ([B][co_valid - split][P]), else NULL
+  int split;         // first channel of y2 (co_valid when there is no second output)
+  int co_valid;      // output channels that are really stored (the rest are zero-filter padding up to a multiple of 32)
   int BN;            // output channels per tile
   int m_tiles, n_tiles, total_tiles;
   int ccs;           // channel blocks per group (Cg / 64)
@@ -121,7 +124,12 @@ static_assert(128 * (TC_REGS_CTL + TC_REGS_EPI + TC_REGS_PLAN) + TC_GATHER_THREA
                   TC_THREADS * TC_REGS_LAUNCH,
               "setmaxnreg.inc would wait forever: the CTA does not own that many registers");
 
-template <typename T, int ND, bool MOD>
+// GRID: no offset tensor -- every tap samples its integer grid position (a plain convolution: the offset / mask
+// producer of the Pack modules, reference modulated_deform_conv.py:734-738,759-768).  One corner per (position, tap),
+// weight 1, no interpolation arithmetic; everything else (roles, rings, MMA, epilogue) is the deformable kernel.
+// CL: the caller's activations are channels-last (the output leaves through TMA stores); compile-time so the NCHW
+// instantiation carries none of that epilogue's registers or code.
+template <typename T, int ND, bool MOD, bool GRID, bool CL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_y,
              const TcFwdParams prm) {
@@ -132,7 +140,7 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
   uint8_t* sA = smem;
   uint8_t* sB = sA + TC_STAGES * TC_A_BYTES;
   uint8_t* sStage = sB + TC_STAGES * TC_B_BYTES;
-  PlanEntry<ND>* sPlan = reinterpret_cast<PlanEntry<ND>*>(sStage + (prm.g.cl ? 2 * tc::CL_STAGE_BYTES : 0));
+  PlanEntry<ND>* sPlan = reinterpret_cast<PlanEntry<ND>*>(sStage + (CL ? 2 * tc::CL_STAGE_BYTES : 0));
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sPlan) +
                                                TC_PLAN_SLOTS * TC_BM * sizeof(PlanEntry<ND>));
   uint64_t* full_a = bars;
@@ -150,7 +158,7 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_w);
-    if (prm.g.cl) ptx::prefetch_tensormap(&tmap_y);
+    if (CL) ptx::prefetch_tensormap(&tmap_y);
     for (int s = 0; s < TC_STAGES; ++s) {
       ptx::mbar_init(&full_a[s], ptx::arrivals(TC_GATHER_THREADS));
       ptx::mbar_init(&full_b[s], 1);
@@ -249,7 +257,7 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
       ptx::mbar_wait_relaxed(&tmem_full[as], aph);
       ptx::tc_fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * TC_MAX_BN);
-      if (g.cl) {
+      if (CL) {
         // channels-last output [B*P][Co]: 64-channel chunks through shared memory and TMA stores
         tc::epilogue_store_channels_last<T>(taddr, BN, g.with_bias ? bias + co0 : nullptr, sStage, cl_buf, &tmap_y, co0,
                                             mt * TC_BM, ew * 32 + lane, ew == 0 && lane == 0, 1);
@@ -259,11 +267,27 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
           ptx::tmem_ld_32x16(taddr + c0, v);
           ptx::tmem_ld_wait();
           if (valid) {
+            if (!GRID) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float f = __uint_as_float(v[j]);
-              if (g.with_bias) f += ld_as<float>(bias + co0 + c0 + j);
-              yrow[(size_t)(c0 + j) * g.P] = cvt_to<T, float>(f);
+              for (int j = 0; j < 16; ++j) {
+                float f = __uint_as_float(v[j]);
+                if (g.with_bias) f += ld_as<float>(bias + co0 + c0 + j);
+                yrow[(size_t)(c0 + j) * g.P] = cvt_to<T, float>(f);
+              }
+            } else {
+              // producer: only co_valid channels exist; channels >= split belong to the second tensor
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int co = co0 + c0 + j;
+                if (co < prm.co_valid) {
+                  float f = __uint_as_float(v[j]);
+                  if (g.with_bias) f += ld_as<float>(bias + co);
+                  T* dst = co < prm.split
+                               ? y + ((size_t)b * prm.split + co) * g.P + p
+                               : reinterpret_cast<T*>(prm.y2) + ((size_t)b * (prm.co_valid - prm.split) + (co - prm.split)) * g.P + p;
+                  *dst = cvt_to<T, float>(f);
+                }
+              }
             }
           }
         }
@@ -272,7 +296,7 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
       ptx::mbar_arrive_warp(&tmem_empty[as]);
       if (++as == 2) { as = 0; aph ^= 1; }
     }
-    if (g.cl && ew == 0 && lane == 0) ptx::bulk_wait_group<0>();   // the staging tiles must outlive their stores
+    if (CL && ew == 0 && lane == 0) ptx::bulk_wait_group<0>();   // the staging tiles must outlive their stores
   } else if (warp < TC_GATHER_WARP0) {
     // ===================== plan producers =====================
     ptx::reg_dealloc<TC_REGS_PLAN>();
@@ -294,7 +318,8 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
       tc::decode_row<ND>(g, v ? (int)(gp / g.P) : 0, v ? (int)(gp % g.P) : 0, v, rc);
       for_each_kblock(prm, grp, [&](int cc, int tap, bool first, int) {
         if (!first) return;
-        const PlanEntry<ND> e = tc::make_plan_entry<T, ND, MOD>(g, off, mask, rc, grp * g.Cg + cc * TC_BK, tap, C8);
+        const PlanEntry<ND> e = GRID ? tc::make_grid_entry<T, ND>(g, rc, tap, C8)
+                                     : tc::make_plan_entry<T, ND, MOD>(g, off, mask, rc, grp * g.Cg + cc * TC_BK, tap, C8);
         ptx::mbar_wait_relaxed(&plan_empty[ps], pph ^ 1);
         tc::store_plan<ND>(ptx::smem_u32(sPlan + ps * TC_BM + row), e);
         ptx::mbar_arrive_warp(&plan_full[ps]);
@@ -307,7 +332,8 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
     // 16 warps x 2 passes x 4 rows = 128 rows per K-block; 8 lanes x 16 bytes cover the 64 channels
     // of one corner.  Software-pipelined one K-block deep: the corner loads of K-block k+1 are in
     // flight while K-block k is interpolated and stored (two register buffers, ping-pong).
-    constexpr int NC = 1 << ND;
+    constexpr int NC = GRID ? 1 : (1 << ND);          // corners per sample
+    constexpr int NQ = (1 << ND) / 4;                 // 16-byte words of a plan row's index (and weight) block
     const int gw = warp - TC_GATHER_WARP0;
     const int chunk = lane & 7;
     const int row0 = gw * 8 + (lane >> 3);
@@ -325,9 +351,9 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
       if (it.first()) ptx::mbar_wait(&plan_full[ips], ipph);
       const uint32_t pa = plan_row + ips * kSlotBytes;
       const uint4* xc = xq + ((it.grp * g.Cg + it.cc * TC_BK) >> 3) + chunk;
-      int i0[NC], i1[NC];
+      int i0[4 * NQ], i1[4 * NQ];
 #pragma unroll
-      for (int q = 0; q < NC / 4; ++q) {
+      for (int q = 0; q < (GRID ? 1 : NQ); ++q) {
         const uint4 a = tc::lds128(pa + 16 * q), b = tc::lds128(pa + kRow4 + 16 * q);
         i0[4 * q] = (int)a.x; i0[4 * q + 1] = (int)a.y; i0[4 * q + 2] = (int)a.z; i0[4 * q + 3] = (int)a.w;
         i1[4 * q] = (int)b.x; i1[4 * q + 1] = (int)b.y; i1[4 * q + 2] = (int)b.z; i1[4 * q + 3] = (int)b.w;
@@ -342,18 +368,24 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
     };
     // interpolate K-block `it` from (v0, v1) into the A stage, publish it, release the plan slot
     auto finish = [&](const KbIter& it, const uint4 (&v0)[NC], const uint4 (&v1)[NC]) {
-      const uint32_t pa = plan_row + cps * kSlotBytes + 4 * NC;  // weights follow the indices
-      uint32_t w0[NC], w1[NC];
-#pragma unroll
-      for (int q = 0; q < NC / 4; ++q) {
-        const uint4 a = tc::lds128(pa + 16 * q), b = tc::lds128(pa + kRow4 + 16 * q);
-        w0[4 * q] = a.x; w0[4 * q + 1] = a.y; w0[4 * q + 2] = a.z; w0[4 * q + 3] = a.w;
-        w1[4 * q] = b.x; w1[4 * q + 1] = b.y; w1[4 * q + 2] = b.z; w1[4 * q + 3] = b.w;
-      }
       ptx::mbar_wait(&empty[s], ph ^ 1);            // MMA has finished reading A[s]
       const uint32_t a_addr = ptx::smem_u32(sA + s * TC_A_BYTES);
-      tc::sts128(a_addr + tc::sw128(row0, chunk), tc::interp8(v0, w0, NC, T()));
-      tc::sts128(a_addr + tc::sw128(row0 + 4, chunk), tc::interp8(v1, w1, NC, T()));
+      if (GRID) {
+        // the loaded vector IS the column value (absent taps were pointed at the all-zero position)
+        tc::sts128(a_addr + tc::sw128(row0, chunk), v0[0]);
+        tc::sts128(a_addr + tc::sw128(row0 + 4, chunk), v1[0]);
+      } else {
+        const uint32_t pa = plan_row + cps * kSlotBytes + 4 * (1 << ND);  // weights follow the indices
+        uint32_t w0[4 * NQ], w1[4 * NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const uint4 a = tc::lds128(pa + 16 * q), b = tc::lds128(pa + kRow4 + 16 * q);
+          w0[4 * q] = a.x; w0[4 * q + 1] = a.y; w0[4 * q + 2] = a.z; w0[4 * q + 3] = a.w;
+          w1[4 * q] = b.x; w1[4 * q + 1] = b.y; w1[4 * q + 2] = b.z; w1[4 * q + 3] = b.w;
+        }
+        tc::sts128(a_addr + tc::sw128(row0, chunk), tc::interp8(v0, w0, NC, T()));
+        tc::sts128(a_addr + tc::sw128(row0 + 4, chunk), tc::interp8(v1, w1, NC, T()));
+      }
       ptx::fence_proxy_async_smem();
       ptx::mbar_arrive_warp(&full_a[s]);
       if (++s == TC_STAGES) { s = 0; ph ^= 1; }
@@ -365,7 +397,7 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
 
     KbIter ka, kb2;
     ka.set_tile(prm, blockIdx.x);
-    if (ND == 2) {
+    if (ND == 2 || GRID) {
       uint4 a0[NC], a1[NC], b0[NC], b1[NC];
       if (ka.valid) issue(ka, a0, a1);
       while (ka.valid) {
@@ -488,28 +520,40 @@ size_t fwd_smem_bytes(bool cl) {
          16;
 }
 
-template <typename T, int ND, bool MOD>
-void launch_tc_forward(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const TcFwdParams& prm, LaunchCtx& ctx) {
-  const size_t smem = fwd_smem_bytes<ND>(prm.g.cl != 0);
+template <typename T, int ND, bool MOD, bool GRID, bool CL>
+void launch_tc_forward_cl(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const TcFwdParams& prm, LaunchCtx& ctx) {
+  const size_t smem = fwd_smem_bytes<ND>(CL);
   static std::atomic<unsigned long long> configured{0};
-  tc::opt_in_dynamic_smem(k_tc_forward<T, ND, MOD>, fwd_smem_bytes<ND>(true), configured, ctx);   // the larger of the two
+  tc::opt_in_dynamic_smem(k_tc_forward<T, ND, MOD, GRID, CL>, smem, configured, ctx);
   const int grid = prm.total_tiles < tc::sm_count() ? prm.total_tiles : tc::sm_count();
-  ProfScope prof(ctx, "tc_forward");
-  k_tc_forward<T, ND, MOD><<<grid, TC_THREADS, smem, ctx.stream>>>(tmap, tmap_y, prm);
+  ProfScope prof(ctx, GRID ? "tc_producer_conv" : "tc_forward");
+  k_tc_forward<T, ND, MOD, GRID, CL><<<grid, TC_THREADS, smem, ctx.stream>>>(tmap, tmap_y, prm);
   MDCONV_CHECK_LAUNCH(ctx);
+}
+template <typename T, int ND, bool MOD, bool GRID = false>
+void launch_tc_forward(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const TcFwdParams& prm, LaunchCtx& ctx) {
+  if (!GRID && prm.g.cl) launch_tc_forward_cl<T, ND, MOD, false, !GRID>(tmap, tmap_y, prm, ctx);
+  else launch_tc_forward_cl<T, ND, MOD, GRID, false>(tmap, tmap_y, prm, ctx);
 }
 
 template <typename T>
 void tensor_forward_t(const DevGeom& g, const void* x, const void* w, const void* bias, const void* off,
-                      const void* mask, void* y, void* ws, LaunchCtx& ctx) {
-  // channels-last callers are gathered from in place; NCHW callers get a channels-last copy in the workspace
+                      const void* mask, void* y, void* ws, const FwdExtra& ex, LaunchCtx& ctx) {
+  // channels-last callers are gathered from in place; NCHW callers get a channels-last copy in the workspace,
+  // unless an earlier call already made one (FwdExtra::xt)
   const T* xt = g.cl ? reinterpret_cast<const T*>(x) : reinterpret_cast<const T*>(ws);
-  T* wr = reinterpret_cast<T*>(reinterpret_cast<char*>(ws) + tc::xt_bytes(g));
-  if (!g.cl) tc::launch_to_channels_last<T>((const T*)x, reinterpret_cast<T*>(ws), g.B, g.C, g.IN, ctx, /*zero_row=*/true);
+  // (a channels-last copy that lives OUTSIDE this workspace leaves only the re-ordered weight here, at offset 0)
+  const bool xt_elsewhere = !g.cl && ex.xt != nullptr && ex.xt != ws;
+  T* wr = reinterpret_cast<T*>(reinterpret_cast<char*>(ws) + (xt_elsewhere ? 0 : tc::xt_bytes(g)));
+  if (!g.cl && ex.xt != nullptr) xt = reinterpret_cast<const T*>(ex.xt);
+  else if (!g.cl) tc::launch_to_channels_last<T>((const T*)x, reinterpret_cast<T*>(ws), g.B, g.C, g.IN, ctx, /*zero_row=*/true);
   tc::launch_reorder_weight<T>((const T*)w, wr, g.Co, g.Cg, g.K, ctx);
   TcFwdParams prm;
   prm.g = g;
   prm.xt = xt; prm.off = off; prm.mask = mask; prm.bias = bias; prm.y = y;
+  prm.y2 = ex.y2;
+  prm.co_valid = ex.co_valid > 0 ? ex.co_valid : g.Co;
+  prm.split = ex.y2 != nullptr ? ex.split : prm.co_valid;
   prm.BN = pick_bn(g);
   const long long total_pix = (long long)g.B * g.P;
   prm.m_tiles = (int)((total_pix + TC_BM - 1) / TC_BM);
@@ -543,7 +587,10 @@ void tensor_forward_t(const DevGeom& g, const void* x, const void* w, const void
     if (ctx.err == cudaSuccess) ctx.err = cudaErrorInvalidValue;
     return;
   }
-  if (g.nd == 2) {
+  if (ex.grid) {
+    if (g.nd == 2) launch_tc_forward<T, 2, false, true>(tmap, tmap_y, prm, ctx);
+    else launch_tc_forward<T, 3, false, true>(tmap, tmap_y, prm, ctx);
+  } else if (g.nd == 2) {
     if (g.modulated) launch_tc_forward<T, 2, true>(tmap, tmap_y, prm, ctx);
     else launch_tc_forward<T, 2, false>(tmap, tmap_y, prm, ctx);
   } else {
@@ -674,9 +721,19 @@ size_t tensor_workspace_bytes(const DevGeom& g, int dtype, int backward) {
 }
 
 void tensor_forward(const DevGeom& g, int dtype, const void* x, const void* w, const void* bias, const void* off,
-                    const void* mask, void* y, void* ws, LaunchCtx& ctx) {
-  if (dtype == MDCONV_F16) tensor_forward_t<__half>(g, x, w, bias, off, mask, y, ws, ctx);
-  else tensor_forward_t<__nv_bfloat16>(g, x, w, bias, off, mask, y, ws, ctx);
+                    const void* mask, void* y, void* ws, const FwdExtra& ex, LaunchCtx& ctx) {
+  if (dtype == MDCONV_F16) tensor_forward_t<__half>(g, x, w, bias, off, mask, y, ws, ex, ctx);
+  else tensor_forward_t<__nv_bfloat16>(g, x, w, bias, off, mask, y, ws, ex, ctx);
+}
+
+size_t tensor_channels_last_bytes(const DevGeom& g) { return tc::xt_bytes(g); }
+size_t tensor_weight_layout_bytes(const DevGeom& g) { return align256((size_t)g.Co * g.Kg * 2); }
+void tensor_to_channels_last(const DevGeom& g, int dtype, const void* x, void* xt, LaunchCtx& ctx) {
+  if (dtype == MDCONV_F16)
+    tc::launch_to_channels_last<__half>((const __half*)x, (__half*)xt, g.B, g.C, g.IN, ctx, /*zero_row=*/true);
+  else
+    tc::launch_to_channels_last<__nv_bfloat16>((const __nv_bfloat16*)x, (__nv_bfloat16*)xt, g.B, g.C, g.IN, ctx,
+                                               /*zero_row=*/true);
 }
 
 void tensor_backward(const DevGeom& g, int dtype, const void* x, const void* w, const void* off, const void* mask,

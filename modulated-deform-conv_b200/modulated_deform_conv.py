@@ -60,14 +60,15 @@ def _needs_grad(*tensors):
 # checkpointing) see it; MDCONV_CUDA.set_keep_layouts(False) / MDCONV_B200_KEEP_LAYOUTS=0 drops it (the backward then
 # rebuilds the layouts: two more kernels, ~4 % of a cfg2 step, for one input-sized buffer less between the calls).
 def _forward_common(ctx, ntuple, modulated, input, offset, mask, weight, bias, stride, padding, dilation, groups,
-                    deformable_groups, in_step, grad_sync):
+                    deformable_groups, in_step, grad_sync, prelaid=None):
     ctx.grad_sync = grad_sync
     ctx.modulated = modulated
     with_bias_tensor = bias
     bias = _setup(ctx, ntuple, input, bias, stride, padding, dilation, groups, deformable_groups, in_step)
     keep = _needs_grad(input, offset, mask, weight, with_bias_tensor)
     out = MDCONV_CUDA.forward_ex(input, weight, bias, offset, mask, None, weight.shape[2:], ctx.stride, ctx.padding,
-                                 ctx.dilation, ctx.groups, ctx.deformable_groups, ctx.with_bias, keep=keep)
+                                 ctx.dilation, ctx.groups, ctx.deformable_groups, ctx.with_bias, keep=keep,
+                                 prelaid=prelaid)
     if not keep:
         return out
     out, layouts = out
@@ -104,20 +105,20 @@ def _backward_common(ctx, grad_output):
 
 def _plain_grads(ctx, g):
     return (g["grad_input"], g["grad_offset"], g["grad_weight"], g["grad_bias"] if ctx.with_bias else None,
-            None, None, None, None, None, None, None)
+            None, None, None, None, None, None, None, None)
 
 
 def _modulated_grads(ctx, g):
     return (g["grad_input"], g["grad_offset"], g["grad_mask"], g["grad_weight"],
-            g["grad_bias"] if ctx.with_bias else None, None, None, None, None, None, None, None)
+            g["grad_bias"] if ctx.with_bias else None, None, None, None, None, None, None, None, None)
 
 
 class DeformConv2dFunction(Function):
     @staticmethod
     def forward(ctx, input, offset, weight, bias=None, stride=1, padding=0, dilation=1,
-                groups=1, deformable_groups=1, in_step=64, grad_sync=None):
+                groups=1, deformable_groups=1, in_step=64, grad_sync=None, prelaid=None):
         return _forward_common(ctx, _pair, False, input, offset, None, weight, bias, stride, padding, dilation,
-                               groups, deformable_groups, in_step, grad_sync)
+                               groups, deformable_groups, in_step, grad_sync, prelaid)
 
     @staticmethod
     @once_differentiable
@@ -128,9 +129,9 @@ class DeformConv2dFunction(Function):
 class ModulatedDeformConv2dFunction(Function):
     @staticmethod
     def forward(ctx, input, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1,
-                groups=1, deformable_groups=1, in_step=64, grad_sync=None):
+                groups=1, deformable_groups=1, in_step=64, grad_sync=None, prelaid=None):
         return _forward_common(ctx, _pair, True, input, offset, mask, weight, bias, stride, padding, dilation,
-                               groups, deformable_groups, in_step, grad_sync)
+                               groups, deformable_groups, in_step, grad_sync, prelaid)
 
     @staticmethod
     @once_differentiable
@@ -141,9 +142,9 @@ class ModulatedDeformConv2dFunction(Function):
 class DeformConv3dFunction(Function):
     @staticmethod
     def forward(ctx, input, offset, weight, bias=None, stride=1, padding=0, dilation=1,
-                groups=1, deformable_groups=1, in_step=64, grad_sync=None):
+                groups=1, deformable_groups=1, in_step=64, grad_sync=None, prelaid=None):
         return _forward_common(ctx, _triple, False, input, offset, None, weight, bias, stride, padding, dilation,
-                               groups, deformable_groups, in_step, grad_sync)
+                               groups, deformable_groups, in_step, grad_sync, prelaid)
 
     @staticmethod
     @once_differentiable
@@ -154,9 +155,9 @@ class DeformConv3dFunction(Function):
 class ModulatedDeformConv3dFunction(Function):
     @staticmethod
     def forward(ctx, input, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1,
-                groups=1, deformable_groups=1, in_step=64, grad_sync=None):
+                groups=1, deformable_groups=1, in_step=64, grad_sync=None, prelaid=None):
         return _forward_common(ctx, _triple, True, input, offset, mask, weight, bias, stride, padding, dilation,
-                               groups, deformable_groups, in_step, grad_sync)
+                               groups, deformable_groups, in_step, grad_sync, prelaid)
 
     @staticmethod
     @once_differentiable
@@ -177,31 +178,31 @@ def _amp(*tensors):
 # The reference binds these four names to ``Function.apply`` (modulated_deform_conv.py:349-352); same call
 # signatures here, plus the autocast handling above.
 def deform_conv2d(input, offset, weight, bias=None, stride=1, padding=0, dilation=1, groups=1,
-                  deformable_groups=1, in_step=64, grad_sync=None):
+                  deformable_groups=1, in_step=64, grad_sync=None, prelaid=None):
     input, offset, weight, bias = _amp(input, offset, weight, bias)
     return DeformConv2dFunction.apply(input, offset, weight, bias, stride, padding, dilation, groups,
-                                      deformable_groups, in_step, grad_sync)
+                                      deformable_groups, in_step, grad_sync, prelaid)
 
 
 def modulated_deform_conv2d(input, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1, groups=1,
-                            deformable_groups=1, in_step=64, grad_sync=None):
+                            deformable_groups=1, in_step=64, grad_sync=None, prelaid=None):
     input, offset, mask, weight, bias = _amp(input, offset, mask, weight, bias)
     return ModulatedDeformConv2dFunction.apply(input, offset, mask, weight, bias, stride, padding, dilation, groups,
-                                               deformable_groups, in_step, grad_sync)
+                                               deformable_groups, in_step, grad_sync, prelaid)
 
 
 def deform_conv3d(input, offset, weight, bias=None, stride=1, padding=0, dilation=1, groups=1,
-                  deformable_groups=1, in_step=64, grad_sync=None):
+                  deformable_groups=1, in_step=64, grad_sync=None, prelaid=None):
     input, offset, weight, bias = _amp(input, offset, weight, bias)
     return DeformConv3dFunction.apply(input, offset, weight, bias, stride, padding, dilation, groups,
-                                      deformable_groups, in_step, grad_sync)
+                                      deformable_groups, in_step, grad_sync, prelaid)
 
 
 def modulated_deform_conv3d(input, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1, groups=1,
-                            deformable_groups=1, in_step=64, grad_sync=None):
+                            deformable_groups=1, in_step=64, grad_sync=None, prelaid=None):
     input, offset, mask, weight, bias = _amp(input, offset, mask, weight, bias)
     return ModulatedDeformConv3dFunction.apply(input, offset, mask, weight, bias, stride, padding, dilation, groups,
-                                               deformable_groups, in_step, grad_sync)
+                                               deformable_groups, in_step, grad_sync, prelaid)
 
 
 class _DeformConvNd(nn.Module):
@@ -332,13 +333,97 @@ def _offset_and_mask(mod, x):
     return both[:, :n].contiguous(), both[:, n:].contiguous()
 
 
+class _ProducerConv(Function):
+    """The offset (+ mask) producer of a Pack module as ONE convolution over the concatenated filter banks, run on
+    the deformable forward kernel in regular-grid mode (MDCONV_CUDA.producer_conv) from the SAME channels-last copy
+    of x the deformable convolution then gathers from (``prelaid``).  Backward: the ordinary convolution gradients
+    (aten::convolution_backward), split back onto the two banks."""
+
+    @staticmethod
+    def forward(ctx, x, w_off, b_off, w_mask, b_mask, stride, padding, prelaid):
+        has_mask = w_mask is not None
+        w = torch.cat([w_off, w_mask], 0) if has_mask else w_off
+        b = torch.cat([b_off, b_mask], 0) if has_mask else b_off
+        ctx.stride, ctx.padding, ctx.n_off, ctx.has_mask = tuple(stride), tuple(padding), w_off.shape[0], has_mask
+        ctx.save_for_backward(x, w)
+        off, msk = MDCONV_CUDA.producer_conv(x, w, b, w_off.shape[0], tuple(w.shape[2:]), ctx.stride, ctx.padding,
+                                             prelaid=prelaid)
+        if has_mask:
+            return off, msk
+        return off
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_off, g_mask=None):
+        x, w = ctx.saved_tensors
+        g = torch.cat([g_off, g_mask], 1) if ctx.has_mask else g_off
+        nd = x.dim() - 2
+        gx, gw, gb = torch.ops.aten.convolution_backward(
+            g.contiguous(), x, w, [w.shape[0]], list(ctx.stride), list(ctx.padding), [1] * nd, False, [0] * nd, 1,
+            [ctx.needs_input_grad[0], True, True])
+        n = ctx.n_off
+        if ctx.has_mask:
+            return gx, gw[:n], gb[:n], gw[n:], gb[n:], None, None, None
+        return gx, gw, gb, None, None, None, None, None
+
+
+def _fused_pack_ok(mod, x, producers):
+    """The fused route needs the tcgen05 kernels for BOTH the deformable convolution and the producer (CUDA, fp16 /
+    bf16, NCHW-contiguous x, channels multiples of 64 ...), plain producers with identical geometry, and no autocast
+    re-typing in between."""
+    if not getattr(mod, "fuse_producers", True) or torch.is_autocast_enabled("cuda") or torch.jit.is_scripting():
+        return False
+    if not (x.is_cuda and x.is_contiguous() and x.dtype in (torch.float16, torch.bfloat16)):
+        return False
+    if any(not _plain_producer(c) or c.weight.dtype != x.dtype for c in producers):
+        return False
+    c0 = producers[0]
+    if any(c.stride != c0.stride or c.padding != c0.padding or c.kernel_size != c0.kernel_size
+           or c.in_channels != c0.in_channels for c in producers[1:]):
+        return False
+    if mod.weight.dtype != x.dtype:
+        return False
+    n_out = sum(c.out_channels for c in producers)
+    return MDCONV_CUDA.producer_conv_supported(x, n_out, c0.kernel_size, c0.stride, c0.padding)
+
+
+def _pack_forward(mod, x, modulated):
+    """Forward of the four Pack modules (reference: modulated_deform_conv.py:750-753, :781-785, :806-809, :835-839):
+    offset (and mask) = conv_offset(x) (, conv_mask(x)), then the deformable convolution.
+
+    Fused route: x is laid out channels-last ONCE; the producers run as one regular-grid pass of the deformable
+    forward kernel over that copy (27 / 18 / 81 ... output channels, padded to a multiple of 32) and the deformable
+    convolution gathers from the same copy.  Anything the fused route does not cover -- hooks, pruning, a replaced
+    producer, different stride / padding between the two, fp32, CPU -- goes through the submodules' own forward()
+    exactly as the reference does."""
+    producers = [mod.conv_offset] + ([mod.conv_mask] if modulated else [])
+    fn = {(2, False): deform_conv2d, (2, True): modulated_deform_conv2d,
+          (3, False): deform_conv3d, (3, True): modulated_deform_conv3d}[(len(mod.kernel_size), modulated)]
+    prelaid = None
+    if _fused_pack_ok(mod, x, producers):
+        prelaid = MDCONV_CUDA.to_channels_last(x, mod.weight, mod.kernel_size, mod.stride, mod.padding, mod.dilation,
+                                               mod.groups, mod.deformable_groups, modulated, mod.bias is not None)
+    if prelaid is not None:
+        co = mod.conv_offset
+        cm = mod.conv_mask if modulated else None
+        out = _ProducerConv.apply(x, co.weight, co.bias, cm.weight if cm is not None else None,
+                                  cm.bias if cm is not None else None, co.stride, co.padding, prelaid)
+        offset, mask = out if modulated else (out, None)
+    elif modulated:
+        offset, mask = _offset_and_mask(mod, x)
+    else:
+        offset, mask = mod.conv_offset(x), None
+    args = (x, offset, mask) if modulated else (x, offset)
+    return fn(*args, *mod._conv_args(), prelaid=prelaid)
+
+
 class DeformConv2dPack(DeformConv2d):
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
         self.conv_offset = _make_producer(self, 2)
 
     def forward(self, x):
-        return deform_conv2d(x, self.conv_offset(x), *self._conv_args())
+        return _pack_forward(self, x, False)
 
 
 class ModulatedDeformConv2dPack(ModulatedDeformConv2d):
@@ -349,8 +434,7 @@ class ModulatedDeformConv2dPack(ModulatedDeformConv2d):
 
     def forward(self, x):
         # as in the reference the mask is the raw conv output (no sigmoid), :781-785
-        offset, mask = _offset_and_mask(self, x)
-        return modulated_deform_conv2d(x, offset, mask, *self._conv_args())
+        return _pack_forward(self, x, True)
 
 
 class DeformConv3dPack(DeformConv3d):
@@ -359,7 +443,7 @@ class DeformConv3dPack(DeformConv3d):
         self.conv_offset = _make_producer(self, 3)
 
     def forward(self, x):
-        return deform_conv3d(x, self.conv_offset(x), *self._conv_args())
+        return _pack_forward(self, x, False)
 
 
 class ModulatedDeformConv3dPack(ModulatedDeformConv3d):
@@ -369,5 +453,4 @@ class ModulatedDeformConv3dPack(ModulatedDeformConv3d):
         self.conv_mask = _make_producer(self, 1)
 
     def forward(self, x):
-        offset, mask = _offset_and_mask(self, x)
-        return modulated_deform_conv3d(x, offset, mask, *self._conv_args())
+        return _pack_forward(self, x, True)

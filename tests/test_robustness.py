@@ -184,3 +184,115 @@ def test_channels_last_input_on_an_unsupported_shape_falls_back_to_a_copy():
     y1 = mdc.modulated_deform_conv2d(xcl, d["offset"], d["mask"], d["weight"], d["bias"], case.s, case.p, case.d)
     y1.sum().backward()
     assert torch.equal(y0, y1) and xcl.grad is not None and xcl.grad.shape == xcl.shape
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16], ids=["f16", "bf16"])
+@pytest.mark.parametrize("kind", ["m2d", "d2d", "m3d"])
+def test_fused_pack_producer(kind, dtype):
+    """the Pack modules' conv_offset / conv_mask run as ONE regular-grid pass of the deformable
+    forward kernel over the channels-last copy of x that the deformable convolution then reuses (one re-layout pass,
+    no cuDNN call in the forward).  The producer equals the two reference convolutions (fp32 cuDNN on the same
+    values), the whole module equals the unfused route, and every parameter receives its gradient."""
+    import torch.nn.functional as F
+    import MDCONV_CUDA as M
+    import modulated_deform_conv as mdc
+    torch.manual_seed(11)
+    if kind == "m3d":
+        mod = mdc.ModulatedDeformConv3dPack(64, 64, 3, padding=1, deformable_groups=1, bias=True)
+        x = torch.randn(1, 64, 6, 8, 8)
+        conv = F.conv3d
+    elif kind == "m2d":
+        mod = mdc.ModulatedDeformConv2dPack(128, 64, 3, stride=1, padding=1, deformable_groups=2, bias=True)
+        x = torch.randn(2, 128, 12, 10)
+        conv = F.conv2d
+    else:
+        mod = mdc.DeformConv2dPack(64, 64, 3, stride=2, padding=1)
+        x = torch.randn(2, 64, 13, 11)
+        conv = F.conv2d
+    mod = mod.cuda().to(dtype)
+    with torch.no_grad():
+        for nme, p_ in mod.named_parameters():
+            p_.copy_(torch.randn_like(p_) * (0.01 if nme.startswith("conv_") else 0.05))   # offsets of ~1 px
+    x = x.cuda().to(dtype)
+    tol = 1e-2 if dtype == torch.float16 else 3e-2
+    # 1. the producer alone against fp32 convolutions of the same 16-bit values
+    producers = [mod.conv_offset] + ([mod.conv_mask] if kind != "d2d" else [])
+    w = torch.cat([c.weight for c in producers], 0).detach()
+    b = torch.cat([c.bias for c in producers], 0).detach()
+    o1, o2 = M.producer_conv(x, w, b, mod.conv_offset.out_channels, mod.kernel_size, mod.conv_offset.stride,
+                             mod.conv_offset.padding)
+    ref = conv(x.float(), w.float(), b.float(), mod.conv_offset.stride, mod.conv_offset.padding)
+    n = mod.conv_offset.out_channels
+    assert rel_err(o1.float().cpu().numpy(), ref[:, :n].cpu().numpy()) < tol
+    if o2 is not None:
+        assert rel_err(o2.float().cpu().numpy(), ref[:, n:].cpu().numpy()) < tol
+
+    # 2. the module: fused vs unfused route, forward and every gradient
+    def run(fuse):
+        mod.fuse_producers = fuse
+        for p_ in mod.parameters():
+            p_.grad = None
+        xx = x.clone().requires_grad_()
+        M.profile_enable(True)
+        try:
+            y = mod(xx)
+            names = [nm for nm, _ in M.profile_read()]
+        finally:
+            M.profile_enable(False)
+        y.float().square().mean().backward()
+        torch.cuda.synchronize()
+        return y.detach(), xx.grad, {k: v.grad.clone() for k, v in mod.named_parameters()}, names
+
+    y1, gx1, gp1, names1 = run(True)
+    y0, gx0, gp0, names0 = run(False)
+    assert "tc_producer_conv" in names1 and names1.count("to_channels_last") == 1, names1
+    assert "tc_producer_conv" not in names0
+    loose = 5 * tol   # the two routes round the offsets differently; the deformable conv amplifies that slightly
+    assert rel_err(y1.float().cpu().numpy(), y0.float().cpu().numpy()) < loose
+    assert float((gx1.double() - gx0.double()).norm() / gx0.double().norm()) < 4 * loose
+    # parameter gradients: relative L2 (the offset gradients are piecewise: an offset that rounds to the other side
+    # of a pixel boundary in one route flips a few terms, which max-norm on a small tensor over-weights)
+    # (the two routes round the offsets differently -- cuDNN vs this kernel -- and d(output)/d(offset) jumps at pixel
+    # boundaries, so everything downstream of the offsets gets the looser bar)
+    for k in gp0:
+        assert gp1[k] is not None, k
+        a, r = gp1[k].double(), gp0[k].double()
+        bar = 4 * loose if k.startswith("conv_offset") else loose
+        assert float((a - r).norm() / r.norm()) < bar, (k, float((a - r).norm() / r.norm()))
+
+
+def test_pack_hooks_and_wrapped_producers_take_the_reference_route():
+    """A forward hook on conv_offset must fire (it never did through the merged-filter shortcut), a pruned producer
+    must use its recomputed weight, and a replaced producer must be called: each of these disables the fused route."""
+    import torch.nn as nn
+    import torch.nn.utils.prune as prune
+    import modulated_deform_conv as mdc
+    torch.manual_seed(12)
+    mod = mdc.ModulatedDeformConv2dPack(64, 64, 3, padding=1).cuda().half()
+    x = torch.randn(1, 64, 8, 8, device="cuda").half()
+    seen = []
+    h = mod.conv_offset.register_forward_hook(lambda m, i, o: seen.append(tuple(o.shape)))
+    mod(x)
+    h.remove()
+    assert seen == [(1, 18, 8, 8)]
+    prune.l1_unstructured(mod.conv_mask, "weight", amount=0.9)
+    y_pruned = mod(x)
+    ref_mask = mod.conv_mask(x)
+    assert float((ref_mask == mod.conv_mask.bias.view(1, -1, 1, 1)).float().mean()) < 1.0   # still a convolution
+    prune.remove(mod.conv_mask, "weight")
+    y_again = mod(x)                       # plain again: fused route, same pruned weights
+    assert rel_err(y_again.detach().float().cpu().numpy(), y_pruned.detach().float().cpu().numpy()) < 5e-2
+    calls = []
+
+    class Wrapped(nn.Module):
+        def __init__(self, inner):
+            super().__init__()
+            self.inner = inner
+
+        def forward(self, t):
+            calls.append(1)
+            return self.inner(t)
+
+    mod.conv_offset = Wrapped(mod.conv_offset)
+    mod(x)
+    assert calls == [1]
