@@ -211,6 +211,12 @@ int mdconv_backward_ex(const mdconv_geom_t* g, const void* input, const void* we
  * Match it to the CTA count of the communicator (e.g. NCCL max_ctas).  Returns the previous value. */
 int mdconv_set_comm_sms(int sms);
 
+/* fp32 calls whose channel counts qualify run their contractions on the tensor cores with every operand split into
+ * two bf16 halves (hi*hi + hi*lo + lo*hi, fp32 accumulation: ~2^-17 relative per product, results within the 1e-4
+ * bar of the exact-fp32 kernels).  on = 0 sends fp32 back to the exact SIMT kernels; MDCONV_B200_FP32_TC=0 in the
+ * environment does the same.  Returns the previous setting. */
+int mdconv_set_fp32_tensor_cores(int on);
+
 /* ---- The reference's eight entry points, C ABI form --------------------------------------
  * Argument order follows the reference signatures; tensor handles become device pointers and the
  * sizes the reference read from the tensors are passed explicitly (batch, channels, spatial

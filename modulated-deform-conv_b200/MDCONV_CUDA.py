@@ -130,6 +130,16 @@ def library_path() -> str:
     return _LIB_PATH
 
 
+_lib.mdconv_set_fp32_tensor_cores.restype = _i
+_lib.mdconv_set_fp32_tensor_cores.argtypes = [_i]
+
+
+def set_fp32_tensor_cores(on: bool) -> bool:
+    """fp32 calls on the split-bf16 tensor-core path (default) or on the exact-fp32 SIMT kernels.  Returns the
+    previous setting."""
+    return bool(_lib.mdconv_set_fp32_tensor_cores(1 if on else 0))
+
+
 def set_comm_sms(sms: int) -> int:
     """SMs the persistent data-gradient kernels leave free for a concurrent collective once the parameter
     gradients are final (see mdconv_set_comm_sms).  Returns the previous value."""

@@ -68,6 +68,7 @@ int resolve(const mdconv_geom_t* in, DevGeom& g) {
   if (in->io_layout != MDCONV_LAYOUT_NCHW && in->io_layout != MDCONV_LAYOUT_CHANNELS_LAST)
     return MDCONV_ERR_BAD_GEOMETRY;
   g.cl = in->io_layout == MDCONV_LAYOUT_CHANNELS_LAST ? 1 : 0;
+  g.esize = in->dtype == MDCONV_F32 ? 4 : (in->dtype == MDCONV_F64 ? 8 : 2);
   for (int a = 0; a < 3; ++a) {
     g.fd_out[a] = make_fastdiv(g.out[a]);
     g.fd_k[a] = make_fastdiv(g.k[a]);
@@ -336,6 +337,7 @@ int mdconv_backward_ex(const mdconv_geom_t* gi, const void* input, const void* w
 }
 
 int mdconv_set_comm_sms(int sms) { return mdconv::set_comm_spare_sms(sms); }
+int mdconv_set_fp32_tensor_cores(int on) { return mdconv::set_fp32_on_tensor_cores(on); }
 
 // ---- legacy-named entry points -----------------------------------------------------------------
 static mdconv_geom_t legacy_geom(int nd, int modulated, int batch, int channels, int height, int width, int length,

@@ -49,6 +49,7 @@ struct DevGeom {
   int Cg, Cog, Cdg;
   int Kg;   // Cg * K, reduction length of the per-group contraction
   int modulated, rule, with_bias;
+  int esize;  // bytes per element of the call's dtype
   int cl;   // 1: activations (input, output, grad_output, grad_input) are channels-last [B, spatial..., C]
   FastDiv fd_out[3], fd_k[3];  // divisors out[a], k[a]
   FastDiv fd_K, fd_Cdg;        // divisors K (taps), Cdg (channels per deformable group)
@@ -225,6 +226,7 @@ struct LaunchCtx {
 // SMs left to a concurrent collective after the weight-ready event (MDCONV_B200_COMM_SMS, default 8; api.cu)
 int comm_spare_sms();
 int set_comm_spare_sms(int sms);   // returns the previous value
+int set_fp32_on_tensor_cores(int on);   // returns the previous value (tensor_path.cu)
 inline void signal_weight_ready(LaunchCtx& ctx) {
   if (ctx.weight_ready != nullptr) {
     cudaError_t e = cudaEventRecord(ctx.weight_ready, ctx.stream);

@@ -18,7 +18,9 @@ inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 // plans point every absent corner (sample out of range, corner outside the input) at that position: the reference
 // returns an exact 0 there WITHOUT reading the input (src/mdeformable_conv.cu:19-29,80), so an Inf/NaN elsewhere in x
 // must not turn into 0 * Inf = NaN through a zero-weight load of some unrelated pixel.
-inline size_t xt_bytes(const DevGeom& g) { return g.cl ? 0 : align256(((size_t)g.B * g.IN + 1) * g.C * 2); }
+inline size_t xt_bytes(const DevGeom& g) { return g.cl ? 0 : align256(((size_t)g.B * g.IN + 1) * g.C * g.esize); }
+// re-ordered filter bank(s): one [Co][Kg] 16-bit bank, or two (bf16 hi, bf16 lo) for fp32 callers
+inline size_t wr_bytes(const DevGeom& g) { return align256((size_t)g.Co * g.Kg * 2) * (g.esize == 4 ? 2 : 1); }
 
 // Shared by the forward and grad_input epilogues when the caller's activations are channels-last: one 64-channel
 // chunk of a 128-row accumulator tile goes TMEM -> registers -> (+bias, convert) -> a 128B-swizzled staging tile in
@@ -81,6 +83,7 @@ __device__ __forceinline__ uint32_t pack_w(float w, __half) {
   __half2 h = __float2half2_rn(w);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ uint32_t pack_w(float w, float) { return __float_as_uint(w); }   // fp32 callers: as is
 __device__ __forceinline__ uint32_t pack_w(float w, __nv_bfloat16) {
   __nv_bfloat162 h = __float2bfloat162_rn(w);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -323,7 +326,7 @@ __device__ __forceinline__ void epilogue_store_channels_last(uint32_t taddr, int
 template <typename T> void launch_to_channels_last(const T* x, T* xt, int B, int C, int IN, LaunchCtx& ctx,
                                                    bool zero_row = false, int out_ld = 0);
 // W [Co][Cg][K] -> Wr [Co][(cc*K + tap)*64 + ci]   (c = cc*64 + ci)
-template <typename T> void launch_reorder_weight(const T* w, T* wr, int Co, int Cg, int K, LaunchCtx& ctx);
+template <typename T> void launch_reorder_weight(const T* w, void* wr, int Co, int Cg, int K, LaunchCtx& ctx);
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -369,6 +372,7 @@ template <typename T>
 inline CUtensorMapDataType tmap_dtype() {
   return std::is_same<T, __half>::value ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
 }
+bool fp32_on_tensor_cores();
 template <typename T>
 constexpr int umma_fmt() {
   return std::is_same<T, __nv_bfloat16>::value ? 1 : 0;

@@ -401,7 +401,7 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const __grid_consta
       ptx::mbar_wait_relaxed(&tmem_full[as], aph);
       ptx::tc_fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * GI_MAX_BN);
-      if (CL) {
+      if constexpr (CL) {
         // channels-last grad_input [B*IN][C]: 64-channel chunks through shared memory and TMA stores
         epilogue_store_channels_last<T>(taddr, BN, nullptr, sStage, cl_buf, &tmap_gx, nt * BN, mt * GI_BM,
                                         ew * 32 + lane, ew == 0 && lane == 0, 1);

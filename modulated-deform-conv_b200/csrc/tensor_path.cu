@@ -116,6 +116,40 @@ struct KbIter {
   __device__ __forceinline__ bool last() const { return cc == run_end - 1; }
 };
 
+// fp32 callers (T = float) run the SAME implicit GEMM on the bf16 tensor pipe with every operand split in two:
+// v = hi + lo, hi = bf16(v), lo = bf16(v - hi) (16 mantissa bits together), and three products per K step,
+// hi*hi + hi*lo + lo*hi, accumulated in the fp32 TMEM tile; the dropped lo*lo term and the split residue are
+// ~2^-17 relative per product, far inside the 1e-4 bar (what the reference gets from an SGEMM,
+// src/deformable_conv.cu:176-178).  The gathered column tile is interpolated in fp32 and split on its way into
+// shared memory (two A tiles per stage), the filters are split once by the re-order pass (two B tiles per stage).
+template <typename T> struct FwdCfg {
+  static constexpr bool F32 = false;
+  static constexpr int A_STAGE = TC_A_BYTES, PLAN_SLOTS = TC_PLAN_SLOTS, MAX_BN = TC_MAX_BN;
+};
+template <> struct FwdCfg<float> {
+  static constexpr bool F32 = true;
+  static constexpr int A_STAGE = 2 * TC_A_BYTES, PLAN_SLOTS = 2, MAX_BN = 128;   // B stage: hi rows, then lo rows
+};
+__device__ __forceinline__ uint32_t bf16x2_bits(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+// 8 fp32 values -> their bf16 "hi" parts and the bf16 of what is left
+__device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo) {
+  float r[8];
+  uint32_t* h = reinterpret_cast<uint32_t*>(&hi);
+  uint32_t* l = reinterpret_cast<uint32_t*>(&lo);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    const float2 back = __bfloat1622float2(hh);
+    r[2 * i] = v[2 * i] - back.x;
+    r[2 * i + 1] = v[2 * i + 1] - back.y;
+    l[i] = bf16x2_bits(r[2 * i], r[2 * i + 1]);
+  }
+}
+
 // Register budget after setmaxnreg: the CTA owns TC_THREADS x 72 registers (what it is launched with);
 // the control / epilogue / plan warpgroups give some back, the gather warpgroups take them.
 constexpr uint32_t TC_REGS_LAUNCH = 72;
@@ -132,23 +166,27 @@ static_assert(128 * (TC_REGS_CTL + TC_REGS_EPI + TC_REGS_PLAN) + TC_GATHER_THREA
 template <typename T, int ND, bool MOD, bool GRID, bool CL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_y,
-             const TcFwdParams prm) {
+             const __grid_constant__ CUtensorMap tmap_w2, const TcFwdParams prm) {
+  constexpr bool F32 = FwdCfg<T>::F32;
+  constexpr int A_STAGE = FwdCfg<T>::A_STAGE;
+  constexpr int PLAN_SLOTS = FwdCfg<T>::PLAN_SLOTS;
+  static_assert(!(F32 && (GRID || CL)), "the fp32 split path has no producer / channels-last variant");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve-up (all stage buffers 1024-byte aligned for the 128B swizzle); the two output staging tiles exist only
   // for channels-last callers (the launch asks for the extra shared memory only then)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
-  uint8_t* sB = sA + TC_STAGES * TC_A_BYTES;
+  uint8_t* sB = sA + TC_STAGES * A_STAGE;
   uint8_t* sStage = sB + TC_STAGES * TC_B_BYTES;
   PlanEntry<ND>* sPlan = reinterpret_cast<PlanEntry<ND>*>(sStage + (CL ? 2 * tc::CL_STAGE_BYTES : 0));
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sPlan) +
-                                               TC_PLAN_SLOTS * TC_BM * sizeof(PlanEntry<ND>));
+                                               PLAN_SLOTS * TC_BM * sizeof(PlanEntry<ND>));
   uint64_t* full_a = bars;
   uint64_t* full_b = full_a + TC_STAGES;
   uint64_t* empty = full_b + TC_STAGES;
   uint64_t* plan_full = empty + TC_STAGES;
-  uint64_t* plan_empty = plan_full + TC_PLAN_SLOTS;
-  uint64_t* tmem_full = plan_empty + TC_PLAN_SLOTS;
+  uint64_t* plan_empty = plan_full + PLAN_SLOTS;
+  uint64_t* tmem_full = plan_empty + PLAN_SLOTS;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -159,12 +197,13 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_w);
     if (CL) ptx::prefetch_tensormap(&tmap_y);
+    if (F32) ptx::prefetch_tensormap(&tmap_w2);
     for (int s = 0; s < TC_STAGES; ++s) {
       ptx::mbar_init(&full_a[s], ptx::arrivals(TC_GATHER_THREADS));
       ptx::mbar_init(&full_b[s], 1);
       ptx::mbar_init(&empty[s], 1);
     }
-    for (int s = 0; s < TC_PLAN_SLOTS; ++s) {
+    for (int s = 0; s < PLAN_SLOTS; ++s) {
       ptx::mbar_init(&plan_full[s], ptx::arrivals(TC_BM));
       ptx::mbar_init(&plan_empty[s], ptx::arrivals(TC_GATHER_THREADS));
     }
@@ -196,8 +235,10 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
         const int row0 = grp * g.Cog + nt * BN;
         for_each_kblock(prm, grp, [&](int cc, int tap, bool, int) {
           ptx::mbar_wait_relaxed(&empty[s], ph ^ 1, 64);
-          ptx::mbar_arrive_expect_tx(&full_b[s], (uint32_t)BN * 128u);
+          ptx::mbar_arrive_expect_tx(&full_b[s], (uint32_t)BN * 128u * (F32 ? 2u : 1u));
           ptx::tma_load_2d(sB + s * TC_B_BYTES, &tmap_w, &full_b[s], (cc * g.K + tap) * TC_BK, row0);
+          if (F32)   // the "lo" halves of the same filter slice
+            ptx::tma_load_2d(sB + s * TC_B_BYTES + TC_B_BYTES / 2, &tmap_w2, &full_b[s], (cc * g.K + tap) * TC_BK, row0);
           if (++s == TC_STAGES) { s = 0; ph ^= 1; }
         });
       }
@@ -205,7 +246,7 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr int fmt = tc::umma_fmt<T>();
+      constexpr int fmt = F32 ? 1 : tc::umma_fmt<T>();   // fp32 callers: bf16 halves
       const uint32_t idesc = ptx::umma_idesc_f16(fmt, 0, 0, TC_BM, BN);
       int s = 0;
       uint32_t ph = 0;
@@ -219,13 +260,19 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
           ptx::mbar_wait(&full_b[s], ph);
           ptx::mbar_wait(&full_a[s], ph);
           ptx::tc_fence_after_sync();
-          const uint32_t a_addr = ptx::smem_u32(sA + s * TC_A_BYTES);
+          const uint32_t a_addr = ptx::smem_u32(sA + s * A_STAGE);
           const uint32_t b_addr = ptx::smem_u32(sB + s * TC_B_BYTES);
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
             const uint64_t ad = ptx::umma_smem_desc_sw128(a_addr + k * 32, 0, 1024);
             const uint64_t bd = ptx::umma_smem_desc_sw128(b_addr + k * 32, 0, 1024);
             ptx::umma_f16(d_tmem, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if (F32) {   // + hi*lo + lo*hi
+              const uint64_t al = ptx::umma_smem_desc_sw128(a_addr + TC_A_BYTES + k * 32, 0, 1024);
+              const uint64_t bl = ptx::umma_smem_desc_sw128(b_addr + TC_B_BYTES / 2 + k * 32, 0, 1024);
+              ptx::umma_f16(d_tmem, ad, bl, idesc, 1u);
+              ptx::umma_f16(d_tmem, al, bd, idesc, 1u);
+            }
           }
           ptx::umma_commit(&empty[s]);
           if (++s == TC_STAGES) { s = 0; ph ^= 1; }
@@ -257,7 +304,7 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
       ptx::mbar_wait_relaxed(&tmem_full[as], aph);
       ptx::tc_fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * TC_MAX_BN);
-      if (CL) {
+      if constexpr (CL) {
         // channels-last output [B*P][Co]: 64-channel chunks through shared memory and TMA stores
         tc::epilogue_store_channels_last<T>(taddr, BN, g.with_bias ? bias + co0 : nullptr, sStage, cl_buf, &tmap_y, co0,
                                             mt * TC_BM, ew * 32 + lane, ew == 0 && lane == 0, 1);
@@ -306,7 +353,7 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
     const int row = threadIdx.x - TC_PLAN_WARP0 * 32;
     const T* __restrict__ off = reinterpret_cast<const T*>(prm.off);
     const T* __restrict__ mask = reinterpret_cast<const T*>(prm.mask);
-    const int C8 = g.C >> 3;
+    const int C8 = F32 ? g.C >> 2 : g.C >> 3;   // 16-byte vectors per position
     int ps = 0;
     uint32_t pph = 0;
     for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x) {
@@ -323,7 +370,7 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
         ptx::mbar_wait_relaxed(&plan_empty[ps], pph ^ 1);
         tc::store_plan<ND>(ptx::smem_u32(sPlan + ps * TC_BM + row), e);
         ptx::mbar_arrive_warp(&plan_full[ps]);
-        if (++ps == TC_PLAN_SLOTS) { ps = 0; pph ^= 1; }
+        if (++ps == PLAN_SLOTS) { ps = 0; pph ^= 1; }
       });
     }
   } else {
@@ -348,6 +395,7 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
 
     // issue the corner loads of K-block `it` into (v0, v1)
     auto issue = [&](const KbIter& it, uint4 (&v0)[NC], uint4 (&v1)[NC]) {
+      if constexpr (F32) return;
       if (it.first()) ptx::mbar_wait(&plan_full[ips], ipph);
       const uint32_t pa = plan_row + ips * kSlotBytes;
       const uint4* xc = xq + ((it.grp * g.Cg + it.cc * TC_BK) >> 3) + chunk;
@@ -363,13 +411,13 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
 #pragma unroll
       for (int c = 0; c < NC; ++c) v1[c] = __ldg(xc + i1[c]);
       if (it.last()) {
-        if (++ips == TC_PLAN_SLOTS) { ips = 0; ipph ^= 1; }
+        if (++ips == PLAN_SLOTS) { ips = 0; ipph ^= 1; }
       }
     };
     // interpolate K-block `it` from (v0, v1) into the A stage, publish it, release the plan slot
     auto finish = [&](const KbIter& it, const uint4 (&v0)[NC], const uint4 (&v1)[NC]) {
       ptx::mbar_wait(&empty[s], ph ^ 1);            // MMA has finished reading A[s]
-      const uint32_t a_addr = ptx::smem_u32(sA + s * TC_A_BYTES);
+      const uint32_t a_addr = ptx::smem_u32(sA + s * A_STAGE);
       if (GRID) {
         // the loaded vector IS the column value (absent taps were pointed at the all-zero position)
         tc::sts128(a_addr + tc::sw128(row0, chunk), v0[0]);
@@ -383,21 +431,76 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
           w0[4 * q] = a.x; w0[4 * q + 1] = a.y; w0[4 * q + 2] = a.z; w0[4 * q + 3] = a.w;
           w1[4 * q] = b.x; w1[4 * q + 1] = b.y; w1[4 * q + 2] = b.z; w1[4 * q + 3] = b.w;
         }
-        tc::sts128(a_addr + tc::sw128(row0, chunk), tc::interp8(v0, w0, NC, T()));
-        tc::sts128(a_addr + tc::sw128(row0 + 4, chunk), tc::interp8(v1, w1, NC, T()));
+        if constexpr (!F32) {
+          tc::sts128(a_addr + tc::sw128(row0, chunk), tc::interp8(v0, w0, NC, T()));
+          tc::sts128(a_addr + tc::sw128(row0 + 4, chunk), tc::interp8(v1, w1, NC, T()));
+        }
       }
       ptx::fence_proxy_async_smem();
       ptx::mbar_arrive_warp(&full_a[s]);
       if (++s == TC_STAGES) { s = 0; ph ^= 1; }
       if (it.last()) {
         ptx::mbar_arrive_warp(&plan_empty[cps]);
-        if (++cps == TC_PLAN_SLOTS) cps = 0;
+        if (++cps == PLAN_SLOTS) cps = 0;
+      }
+    };
+    // fp32: one K-block start to finish (no look-ahead: 8 channels of a corner are two 16-byte loads, a row's
+    // corners already fill the registers).  Each of the thread's two rows: load, interpolate in fp32, split into
+    // hi / lo bf16, store both tiles.
+    auto block_f32 = [&](const KbIter& it) {
+      if (it.first()) ptx::mbar_wait(&plan_full[ips], ipph);
+      const uint32_t pa = plan_row + ips * kSlotBytes;
+      const uint4* xc = xq + ((it.grp * g.Cg + it.cc * TC_BK) >> 2) + 2 * chunk;
+      ptx::mbar_wait(&empty[s], ph ^ 1);            // MMA has finished reading A[s]
+      const uint32_t a_addr = ptx::smem_u32(sA + s * A_STAGE);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const uint4 iv = tc::lds128(pa + r * kRow4 + 16 * q);
+          const uint4 wv = tc::lds128(pa + r * kRow4 + 4 * (1 << ND) + 16 * q);
+          const int idx[4] = {(int)iv.x, (int)iv.y, (int)iv.z, (int)iv.w};
+          const float wgt[4] = {__uint_as_float(wv.x), __uint_as_float(wv.y), __uint_as_float(wv.z), __uint_as_float(wv.w)};
+          uint4 va[4], vb[4];   // channels 0-3 and 4-7 of this lane's 8, for four corners
+#pragma unroll
+          for (int c = 0; c < 4; ++c) { va[c] = __ldg(xc + idx[c]); vb[c] = __ldg(xc + idx[c] + 1); }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            acc[0] = fmaf(wgt[c], __uint_as_float(va[c].x), acc[0]);
+            acc[1] = fmaf(wgt[c], __uint_as_float(va[c].y), acc[1]);
+            acc[2] = fmaf(wgt[c], __uint_as_float(va[c].z), acc[2]);
+            acc[3] = fmaf(wgt[c], __uint_as_float(va[c].w), acc[3]);
+            acc[4] = fmaf(wgt[c], __uint_as_float(vb[c].x), acc[4]);
+            acc[5] = fmaf(wgt[c], __uint_as_float(vb[c].y), acc[5]);
+            acc[6] = fmaf(wgt[c], __uint_as_float(vb[c].z), acc[6]);
+            acc[7] = fmaf(wgt[c], __uint_as_float(vb[c].w), acc[7]);
+          }
+        }
+        uint4 hi, lo;
+        split8(acc, hi, lo);
+        tc::sts128(a_addr + tc::sw128(row0 + 4 * r, chunk), hi);
+        tc::sts128(a_addr + TC_A_BYTES + tc::sw128(row0 + 4 * r, chunk), lo);
+      }
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive_warp(&full_a[s]);
+      if (++s == TC_STAGES) { s = 0; ph ^= 1; }
+      if (it.last()) {
+        ptx::mbar_arrive_warp(&plan_empty[ips]);
+        if (++ips == PLAN_SLOTS) { ips = 0; ipph ^= 1; }
       }
     };
 
     KbIter ka, kb2;
     ka.set_tile(prm, blockIdx.x);
-    if (ND == 2 || GRID) {
+    if (F32) {
+      while (ka.valid) {
+        block_f32(ka);
+        ka.advance(prm, gridDim.x);
+      }
+    } else if (ND == 2 || GRID) {
       uint4 a0[NC], a1[NC], b0[NC], b1[NC];
       if (ka.valid) issue(ka, a0, a1);
       while (ka.valid) {
@@ -510,44 +613,87 @@ __global__ void k_reorder_weight(const T* __restrict__ w, T* __restrict__ wr, in
   }
 }
 
-// ---- host side --------------------------------------------------------------------------------
-int pick_bn(const DevGeom& g) { return g.Cog <= TC_MAX_BN ? g.Cog : TC_MAX_BN; }
-
-template <int ND>
-size_t fwd_smem_bytes(bool cl) {
-  return 1024 + (size_t)TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + (cl ? 2 * tc::CL_STAGE_BYTES : 0) +
-         (size_t)TC_PLAN_SLOTS * TC_BM * sizeof(PlanEntry<ND>) + (3 * TC_STAGES + 2 * TC_PLAN_SLOTS + 4) * sizeof(uint64_t) +
-         16;
+// fp32 filters: the same re-order, split into bf16 hi / lo banks (w = hi + lo up to 2^-17 relative)
+__global__ void k_reorder_weight_split(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
+                                       __nv_bfloat16* __restrict__ lo, int Co, int Cg, int K) {
+  const size_t n = (size_t)Co * Cg * K;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int Kg = Cg * K;
+    const int co = (int)(i / Kg);
+    const int r = (int)(i % Kg);
+    const int ci = r & 63;
+    const int q = r >> 6;
+    const int tap = q % K, cc = q / K;
+    const float v = w[(size_t)co * Kg + (size_t)(cc * 64 + ci) * K + tap];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
 }
 
+// ---- host side --------------------------------------------------------------------------------
+int pick_bn(const DevGeom& g) {
+  const int mx = g.esize == 4 ? FwdCfg<float>::MAX_BN : TC_MAX_BN;
+  return g.Cog <= mx ? g.Cog : mx;
+}
+
+template <typename T, int ND>
+size_t fwd_smem_bytes(bool cl) {
+  return 1024 + (size_t)TC_STAGES * (FwdCfg<T>::A_STAGE + TC_B_BYTES) + (cl ? 2 * tc::CL_STAGE_BYTES : 0) +
+         (size_t)FwdCfg<T>::PLAN_SLOTS * TC_BM * sizeof(PlanEntry<ND>) +
+         (3 * TC_STAGES + 2 * FwdCfg<T>::PLAN_SLOTS + 4) * sizeof(uint64_t) + 16;
+}
+
+struct FwdMaps {
+  CUtensorMap w, y, w2;   // filters (hi for fp32), channels-last output, filters lo (fp32 only)
+};
 template <typename T, int ND, bool MOD, bool GRID, bool CL>
-void launch_tc_forward_cl(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const TcFwdParams& prm, LaunchCtx& ctx) {
-  const size_t smem = fwd_smem_bytes<ND>(CL);
+void launch_tc_forward_cl(const FwdMaps& m, const TcFwdParams& prm, LaunchCtx& ctx) {
+  const size_t smem = fwd_smem_bytes<T, ND>(CL);
   static std::atomic<unsigned long long> configured{0};
   tc::opt_in_dynamic_smem(k_tc_forward<T, ND, MOD, GRID, CL>, smem, configured, ctx);
   const int grid = prm.total_tiles < tc::sm_count() ? prm.total_tiles : tc::sm_count();
   ProfScope prof(ctx, GRID ? "tc_producer_conv" : "tc_forward");
-  k_tc_forward<T, ND, MOD, GRID, CL><<<grid, TC_THREADS, smem, ctx.stream>>>(tmap, tmap_y, prm);
+  k_tc_forward<T, ND, MOD, GRID, CL><<<grid, TC_THREADS, smem, ctx.stream>>>(m.w, m.y, m.w2, prm);
   MDCONV_CHECK_LAUNCH(ctx);
 }
 template <typename T, int ND, bool MOD, bool GRID = false>
-void launch_tc_forward(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const TcFwdParams& prm, LaunchCtx& ctx) {
-  if (!GRID && prm.g.cl) launch_tc_forward_cl<T, ND, MOD, false, !GRID>(tmap, tmap_y, prm, ctx);
-  else launch_tc_forward_cl<T, ND, MOD, GRID, false>(tmap, tmap_y, prm, ctx);
+void launch_tc_forward(const FwdMaps& m, const TcFwdParams& prm, LaunchCtx& ctx) {
+  if constexpr (std::is_same<T, float>::value) {
+    launch_tc_forward_cl<T, ND, MOD, false, false>(m, prm, ctx);
+  } else {
+    if (!GRID && prm.g.cl) launch_tc_forward_cl<T, ND, MOD, false, !GRID>(m, prm, ctx);
+    else launch_tc_forward_cl<T, ND, MOD, GRID, false>(m, prm, ctx);
+  }
+}
+
+// bf16 tensor map over a re-ordered filter bank [Co][Kg], box = 64 K-elements x BN rows
+template <typename E>
+static bool encode_filter_map(CUtensorMap* m, const void* wr, const DevGeom& g, int BN) {
+  tc::PFN_encodeTiled enc = tc::get_encode_fn();
+  if (!enc) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)g.Kg, (cuuint64_t)g.Co};
+  const cuuint64_t strides[1] = {(cuuint64_t)g.Kg * sizeof(E)};
+  const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)BN};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(m, tc::tmap_dtype<E>(), 2, const_cast<void*>(wr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 template <typename T>
 void tensor_forward_t(const DevGeom& g, const void* x, const void* w, const void* bias, const void* off,
                       const void* mask, void* y, void* ws, const FwdExtra& ex, LaunchCtx& ctx) {
+  constexpr bool F32 = std::is_same<T, float>::value;
   // channels-last callers are gathered from in place; NCHW callers get a channels-last copy in the workspace,
   // unless an earlier call already made one (FwdExtra::xt)
   const T* xt = g.cl ? reinterpret_cast<const T*>(x) : reinterpret_cast<const T*>(ws);
   // (a channels-last copy that lives OUTSIDE this workspace leaves only the re-ordered weight here, at offset 0)
   const bool xt_elsewhere = !g.cl && ex.xt != nullptr && ex.xt != ws;
-  T* wr = reinterpret_cast<T*>(reinterpret_cast<char*>(ws) + (xt_elsewhere ? 0 : tc::xt_bytes(g)));
+  char* wr = reinterpret_cast<char*>(ws) + (xt_elsewhere ? 0 : tc::xt_bytes(g));
   if (!g.cl && ex.xt != nullptr) xt = reinterpret_cast<const T*>(ex.xt);
   else if (!g.cl) tc::launch_to_channels_last<T>((const T*)x, reinterpret_cast<T*>(ws), g.B, g.C, g.IN, ctx, /*zero_row=*/true);
-  tc::launch_reorder_weight<T>((const T*)w, wr, g.Co, g.Cg, g.K, ctx);
+  tc::launch_reorder_weight<T>((const T*)w, wr, g.Co, g.Cg, g.K, ctx);   // fp32: hi bank, then lo bank
   TcFwdParams prm;
   prm.g = g;
   prm.xt = xt; prm.off = off; prm.mask = mask; prm.bias = bias; prm.y = y;
@@ -563,39 +709,33 @@ void tensor_forward_t(const DevGeom& g, const void* x, const void* w, const void
   prm.bpd = g.Cdg / TC_BK;
   prm.kblocks = prm.ccs * g.K;
 
-  tc::PFN_encodeTiled enc = tc::get_encode_fn();
-  if (!enc) {
-    if (ctx.err == cudaSuccess) ctx.err = cudaErrorNotSupported;
-    return;
-  }
-  CUtensorMap tmap;
-  const cuuint64_t dims[2] = {(cuuint64_t)g.Kg, (cuuint64_t)g.Co};
-  const cuuint64_t strides[1] = {(cuuint64_t)g.Kg * sizeof(T)};
-  const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)prm.BN};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUtensorMapDataType dt = tc::tmap_dtype<T>();
-  const CUresult r = enc(&tmap, dt, 2, wr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    if (ctx.err == cudaSuccess) ctx.err = cudaErrorInvalidValue;
-    return;
-  }
-  CUtensorMap tmap_y;
-  memset(&tmap_y, 0, sizeof(tmap_y));
-  if (g.cl && !tc::encode_rows_by_channels<T>(&tmap_y, y, (size_t)g.B * g.P, g.Co)) {
-    if (ctx.err == cudaSuccess) ctx.err = cudaErrorInvalidValue;
-    return;
-  }
-  if (ex.grid) {
-    if (g.nd == 2) launch_tc_forward<T, 2, false, true>(tmap, tmap_y, prm, ctx);
-    else launch_tc_forward<T, 3, false, true>(tmap, tmap_y, prm, ctx);
-  } else if (g.nd == 2) {
-    if (g.modulated) launch_tc_forward<T, 2, true>(tmap, tmap_y, prm, ctx);
-    else launch_tc_forward<T, 2, false>(tmap, tmap_y, prm, ctx);
+  FwdMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  bool ok;
+  if constexpr (F32) {
+    ok = encode_filter_map<__nv_bfloat16>(&maps.w, wr, g, prm.BN) &&
+         encode_filter_map<__nv_bfloat16>(&maps.w2, wr + tc::wr_bytes(g) / 2, g, prm.BN);
   } else {
-    if (g.modulated) launch_tc_forward<T, 3, true>(tmap, tmap_y, prm, ctx);
-    else launch_tc_forward<T, 3, false>(tmap, tmap_y, prm, ctx);
+    ok = encode_filter_map<T>(&maps.w, wr, g, prm.BN);
+    if (ok && g.cl) ok = tc::encode_rows_by_channels<T>(&maps.y, y, (size_t)g.B * g.P, g.Co);
+  }
+  if (!ok) {
+    if (ctx.err == cudaSuccess) ctx.err = cudaErrorInvalidValue;
+    return;
+  }
+  if constexpr (!F32) {
+    if (ex.grid) {
+      if (g.nd == 2) launch_tc_forward<T, 2, false, true>(maps, prm, ctx);
+      else launch_tc_forward<T, 3, false, true>(maps, prm, ctx);
+      return;
+    }
+  }
+  if (g.nd == 2) {
+    if (g.modulated) launch_tc_forward<T, 2, true>(maps, prm, ctx);
+    else launch_tc_forward<T, 2, false>(maps, prm, ctx);
+  } else {
+    if (g.modulated) launch_tc_forward<T, 3, true>(maps, prm, ctx);
+    else launch_tc_forward<T, 3, false>(maps, prm, ctx);
   }
 }
 
@@ -665,28 +805,56 @@ void launch_to_channels_last(const T* x, T* xt, int B, int C, int IN, LaunchCtx&
   ProfScope prof(ctx, out_ld > 0 ? "from_channels_last" : "to_channels_last");
   if (out_ld <= 0) out_ld = C;
   dim3 grid((unsigned)((IN + 63) / 64), (unsigned)((C + 63) / 64), (unsigned)B);
-  const bool vec = IN % 8 == 0 && C % 8 == 0 && out_ld % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)xt & 15) == 0;
+  const bool vec = sizeof(T) == 2 && IN % 8 == 0 && C % 8 == 0 && out_ld % 8 == 0 && ((uintptr_t)x & 15) == 0 &&
+                   ((uintptr_t)xt & 15) == 0;   // the 16-byte form moves 8 two-byte elements per access
   if (vec) k_to_channels_last<T, true><<<grid, 256, 0, ctx.stream>>>(x, xt, C, IN, zero_row ? 1 : 0, out_ld);
   else k_to_channels_last<T, false><<<grid, 256, 0, ctx.stream>>>(x, xt, C, IN, zero_row ? 1 : 0, out_ld);
   MDCONV_CHECK_LAUNCH(ctx);
 }
 template <typename T>
-void launch_reorder_weight(const T* w, T* wr, int Co, int Cg, int K, LaunchCtx& ctx) {
+void launch_reorder_weight(const T* w, void* wr, int Co, int Cg, int K, LaunchCtx& ctx) {
   ProfScope prof(ctx, "reorder_weight");
   const size_t n = (size_t)Co * Cg * K;
   const int blocks = (int)((n + 255) / 256 > 1184 ? 1184 : (n + 255) / 256);
-  k_reorder_weight<T><<<blocks, 256, 0, ctx.stream>>>(w, wr, Co, Cg, K);
+  if constexpr (std::is_same<T, float>::value) {
+    // two bf16 banks, hi then lo, each align256(Co * Kg * 2) bytes (wr_bytes)
+    __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(wr);
+    __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(wr) + align256(n * 2));
+    k_reorder_weight_split<<<blocks, 256, 0, ctx.stream>>>(w, hi, lo, Co, Cg, K);
+  } else {
+    k_reorder_weight<T><<<blocks, 256, 0, ctx.stream>>>(w, reinterpret_cast<T*>(wr), Co, Cg, K);
+  }
   MDCONV_CHECK_LAUNCH(ctx);
 }
 template void launch_to_channels_last<__half>(const __half*, __half*, int, int, int, LaunchCtx&, bool, int);
 template void launch_to_channels_last<__nv_bfloat16>(const __nv_bfloat16*, __nv_bfloat16*, int, int, int, LaunchCtx&,
                                                      bool, int);
-template void launch_reorder_weight<__half>(const __half*, __half*, int, int, int, LaunchCtx&);
-template void launch_reorder_weight<__nv_bfloat16>(const __nv_bfloat16*, __nv_bfloat16*, int, int, int, LaunchCtx&);
+template void launch_to_channels_last<float>(const float*, float*, int, int, int, LaunchCtx&, bool, int);
+template void launch_reorder_weight<__half>(const __half*, void*, int, int, int, LaunchCtx&);
+template void launch_reorder_weight<__nv_bfloat16>(const __nv_bfloat16*, void*, int, int, int, LaunchCtx&);
+template void launch_reorder_weight<float>(const float*, void*, int, int, int, LaunchCtx&);
 
 }  // namespace tc
 
 static std::atomic<int> g_comm_sms{-1};   // -1: not set yet -> MDCONV_B200_COMM_SMS or 8
+// fp32 calls take the split-bf16 tensor-core path by default; MDCONV_B200_FP32_TC=0 (or mdconv_set_fp32_tensor_cores)
+// sends them back to the exact-fp32 SIMT kernels.
+static std::atomic<int> g_fp32_tc{-1};
+bool fp32_on_tensor_cores() {
+  int v = g_fp32_tc.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("MDCONV_B200_FP32_TC");
+    v = (e && e[0] == '0') ? 0 : 1;
+    g_fp32_tc.store(v, std::memory_order_relaxed);
+  }
+  return v != 0;
+}
+int set_fp32_on_tensor_cores(int on) {
+  const int prev = fp32_on_tensor_cores() ? 1 : 0;
+  g_fp32_tc.store(on ? 1 : 0, std::memory_order_relaxed);
+  return prev;
+}
+
 int comm_spare_sms() {
   int v = g_comm_sms.load(std::memory_order_relaxed);
   if (v < 0) {
@@ -704,49 +872,57 @@ int set_comm_spare_sms(int sms) {
 }
 
 bool tensor_path_supported(const DevGeom& g, int dtype, int backward) {
-  if (dtype != MDCONV_F16 && dtype != MDCONV_BF16) return false;
+  if (dtype != MDCONV_F16 && dtype != MDCONV_BF16 && dtype != MDCONV_F32) return false;
   if (g.Cg % TC_BK != 0 || g.Cdg % TC_BK != 0) return false;
-  if (((long long)g.B * g.IN + 1) * (g.C / 8) > 2147483647LL) return false;
-  if (g.cl && (g.Cog % 64 != 0 || g.Co % 8 != 0 || g.C % 8 != 0)) return false;   // 64-channel TMA store chunks
+  const int vec = dtype == MDCONV_F32 ? 4 : 8;   // elements per 16-byte vector
+  if (((long long)g.B * g.IN + 1) * (g.C / vec) > 2147483647LL) return false;
+  if (g.cl && (dtype == MDCONV_F32 || g.Cog % 64 != 0 || g.Co % 8 != 0 || g.C % 8 != 0)) return false;   // 64-channel TMA store chunks
+  if (dtype == MDCONV_F32 && !fp32_on_tensor_cores()) return false;
   if (backward) return tc::tensor_backward_supported(g, dtype);
   if (g.Cog % 32 != 0) return false;
-  if (g.Cog > TC_MAX_BN && g.Cog % TC_MAX_BN != 0) return false;
+  const int mx = dtype == MDCONV_F32 ? FwdCfg<float>::MAX_BN : TC_MAX_BN;
+  if (g.Cog > mx && g.Cog % mx != 0) return false;
   return true;
 }
 
 size_t tensor_workspace_bytes(const DevGeom& g, int dtype, int backward) {
   (void)dtype;
   if (backward) return tc::tensor_backward_workspace(g);
-  return tc::xt_bytes(g) + align256((size_t)g.Co * g.Kg * 2);
+  return tc::xt_bytes(g) + tc::wr_bytes(g);
 }
 
 void tensor_forward(const DevGeom& g, int dtype, const void* x, const void* w, const void* bias, const void* off,
                     const void* mask, void* y, void* ws, const FwdExtra& ex, LaunchCtx& ctx) {
   if (dtype == MDCONV_F16) tensor_forward_t<__half>(g, x, w, bias, off, mask, y, ws, ex, ctx);
-  else tensor_forward_t<__nv_bfloat16>(g, x, w, bias, off, mask, y, ws, ex, ctx);
+  else if (dtype == MDCONV_BF16) tensor_forward_t<__nv_bfloat16>(g, x, w, bias, off, mask, y, ws, ex, ctx);
+  else tensor_forward_t<float>(g, x, w, bias, off, mask, y, ws, ex, ctx);
 }
 
 size_t tensor_channels_last_bytes(const DevGeom& g) { return tc::xt_bytes(g); }
-size_t tensor_weight_layout_bytes(const DevGeom& g) { return align256((size_t)g.Co * g.Kg * 2); }
+size_t tensor_weight_layout_bytes(const DevGeom& g) { return tc::wr_bytes(g); }
 void tensor_to_channels_last(const DevGeom& g, int dtype, const void* x, void* xt, LaunchCtx& ctx) {
   if (dtype == MDCONV_F16)
     tc::launch_to_channels_last<__half>((const __half*)x, (__half*)xt, g.B, g.C, g.IN, ctx, /*zero_row=*/true);
-  else
+  else if (dtype == MDCONV_BF16)
     tc::launch_to_channels_last<__nv_bfloat16>((const __nv_bfloat16*)x, (__nv_bfloat16*)xt, g.B, g.C, g.IN, ctx,
                                                /*zero_row=*/true);
+  else
+    tc::launch_to_channels_last<float>((const float*)x, (float*)xt, g.B, g.C, g.IN, ctx, /*zero_row=*/true);
 }
 
 void tensor_backward(const DevGeom& g, int dtype, const void* x, const void* w, const void* off, const void* mask,
                      const void* go, void* gx, void* gw, void* gb, void* goff, void* gmask, void* ws, const void* saved,
                      LaunchCtx& ctx) {
   if (dtype == MDCONV_F16) tc::tensor_backward_t<__half>(g, x, w, off, mask, go, gx, gw, gb, goff, gmask, ws, saved, ctx);
-  else tc::tensor_backward_t<__nv_bfloat16>(g, x, w, off, mask, go, gx, gw, gb, goff, gmask, ws, saved, ctx);
+  else if (dtype == MDCONV_BF16)
+    tc::tensor_backward_t<__nv_bfloat16>(g, x, w, off, mask, go, gx, gw, gb, goff, gmask, ws, saved, ctx);
+  else tc::tensor_backward_t<float>(g, x, w, off, mask, go, gx, gw, gb, goff, gmask, ws, saved, ctx);
 }
 
 // forward workspace prefix the backward can reuse: [channels-last input | re-ordered weight]
 size_t tensor_saved_bytes(const DevGeom& g, int dtype) {
   (void)dtype;
-  return tc::xt_bytes(g) + align256((size_t)g.Co * g.Kg * 2);
+  return tc::xt_bytes(g) + tc::wr_bytes(g);
 }
 
 }  // namespace mdconv

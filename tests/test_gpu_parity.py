@@ -206,6 +206,46 @@ def test_tensor_path_matches_oracle(case, dtype):
     _compare(ours, _oracle(case, t), TOL[dtype], f"{case.name}/{dtype} (bwd path {bwd})")
 
 
+@pytest.mark.parametrize("case", TENSOR_CASES, ids=lambda c: c.name)
+def test_fp32_tensor_path_matches_oracle(case):
+    """fp32 on the tensor cores (operands split into bf16 hi / lo, three products per K step, fp32 accumulation):
+    forward and grad_weight on the tcgen05 kernels, the data gradients on the exact SIMT kernel; BASELINE.json's
+    fp32 bar, 1e-4 rel, against the fp64 oracle."""
+    import ctypes
+    import MDCONV_CUDA
+    t = make_inputs(case, torch.float32)
+    g = MDCONV_CUDA._geom(t["x"], t["weight"], case.k, case.s, case.p, case.d, case.g, case.dg, case.modulated,
+                          case.bias)
+    g.path = 2
+    if MDCONV_CUDA._lib.mdconv_selected_path(ctypes.byref(g), 0) != 2:
+        pytest.skip("shape not taken by the fp32 tensor path (output-channel tile)")
+    MDCONV_CUDA.profile_enable(True)
+    try:
+        ours = _run_ours(case, t, fwd_path=2, bwd_path=2)
+        names = {n for n, _ in MDCONV_CUDA.profile_read()}
+    finally:
+        MDCONV_CUDA.profile_enable(False)
+        MDCONV_CUDA.set_path(0)
+    assert {"tc_forward", "tc_grad_weight", "generic_bwd_data"} <= names, names
+    _compare(ours, _oracle(case, t), TOL[torch.float32], f"{case.name}/fp32 tensor path")
+
+
+def test_fp32_tensor_cores_can_be_switched_off():
+    import MDCONV_CUDA
+    case = {c.name: c for c in TENSOR_CASES}["tc_m2d_c64"]
+    t = make_inputs(case, torch.float32)
+    prev = MDCONV_CUDA.set_fp32_tensor_cores(False)
+    try:
+        MDCONV_CUDA.profile_enable(True)
+        ours = _run_ours(case, t)
+        names = {n for n, _ in MDCONV_CUDA.profile_read()}
+    finally:
+        MDCONV_CUDA.profile_enable(False)
+        MDCONV_CUDA.set_fp32_tensor_cores(prev)
+    assert "generic_forward" in names and "tc_forward" not in names
+    _compare(ours, _oracle(case, t), TOL[torch.float32], "fp32 SIMT")
+
+
 def test_saved_layouts_hand_off_is_bit_identical_and_skips_two_passes():
     """Forward -> backward hand-off of the channels-last input / re-ordered weight (mdconv_backward_saved): same
     bits as the stateless backward, two launches fewer; the legacy-named stateless entry points stay equivalent."""
