@@ -333,6 +333,9 @@ def main():
     ap.add_argument("--comm-ctas", type=int, default=4,
                     help="N>1: CTAs of the dedicated NCCL communicator for the gradient all-reduce = SMs the "
                          "data-gradient kernels leave free (0: default communicator, library default of 8 SMs)")
+    ap.add_argument("--channels-last", action="store_true",
+                    help="x and grad_output in torch.channels_last / channels_last_3d (SURVEY 8(f) rank 4): no re-layout "
+                         "pass of x, TMA-store epilogues; NOT the BASELINE configuration (which is NCHW)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
     args = ap.parse_args()
@@ -381,6 +384,10 @@ def main():
 
     host = make_host_inputs(w, B, 100 + rank, dtype, pin=True)
     d = {k: (None if v is None else v.to(dev)) for k, v in host.items()}
+    if args.channels_last:
+        fmt = torch.channels_last if w["nd"] == 2 else torch.channels_last_3d
+        d["x"] = d["x"].contiguous(memory_format=fmt)
+        d["grad_output"] = d["grad_output"].contiguous(memory_format=fmt)
     leaves = {k: d[k].clone().requires_grad_() for k in ("x", "offset") + (("mask",) if w["modulated"] else ())}
 
     launches = [0]
@@ -663,7 +670,8 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": K_steps, "warmup": W,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": w["dtype"], "data": "synthetic",
-                "config": {"workload": w["desc"], "global_batch": B * world, "per_gpu_batch": B,
+                "config": {"workload": w["desc"] + (" [channels-last activations]" if args.channels_last else ""),
+                           "global_batch": B * world, "per_gpu_batch": B,
                            "parallelism": f"batch-shard x{world}",
                            "l2": "working set (277 MB at cfg2) exceeds the 126 MB L2; no explicit flush",
                            "path": {0: "auto", 1: "generic", 2: "tensor"}[args.path],

@@ -378,6 +378,25 @@ constexpr int umma_fmt() {
   return std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
 }
 
+// Tail split of a persistent tile loop (see TcFwdParams): `tiles` 128-row tiles dealt round-robin to
+// min(tiles, sms) CTAs.  If the last, incomplete round holds at most half a grid of tiles, each of them is cut into
+// up to 4 row ranges (multiples of 8 rows: one gather warp owns 8 rows) so the ranges fill the grid.
+inline void plan_tail_split(int tiles, int sms, bool allowed, int& full_tiles, int& tail_tiles, int& split, int& rows) {
+  const int grid = tiles < sms ? tiles : sms;
+  full_tiles = grid > 0 ? (tiles / grid) * grid : 0;
+  tail_tiles = tiles - full_tiles;
+  split = 1;
+  if (allowed && tail_tiles > 0) {
+    split = grid / tail_tiles;
+    if (split > 4) split = 4;
+    if (split < 1) split = 1;
+  }
+  rows = ((128 + split - 1) / split + 7) & ~7;
+  if (split > 1 && rows * (split - 1) >= 128) {   // the last range would be empty: fewer, fuller ranges
+    split = (128 + rows - 1) / rows;
+  }
+}
+
 // Side stream of the current device (created on first use) + fork/join helpers: small independent
 // passes (the inverse-index build) run beside the layout passes of the main stream.
 struct SideStream {

@@ -64,6 +64,12 @@ struct TcFwdParams {
   int co_valid;      // output channels that are really stored (the rest are zero-filter padding up to a multiple of 32)
   int BN;            // output channels per tile
   int m_tiles, n_tiles, total_tiles;
+  // Tail split: the tiles are dealt round-robin to the persistent CTAs; when the last round would keep only a
+  // fraction of them busy (784 tiles on 148 SMs: 44 of 148), each of its `tail_tiles` tiles is cut into `tail_split`
+  // row ranges of `tail_rows` rows and every range goes to its own CTA.  The kernels are paced by the gather, whose
+  // cost follows the number of live rows, so the last round then takes ~1/tail_split of a full one.
+  int full_tiles;    // tiles dealt in complete rounds (a multiple of the grid size)
+  int tail_tiles, tail_split, tail_rows;
   int ccs;           // channel blocks per group (Cg / 64)
   int bpd;           // channel blocks per deformable group (Cdg / 64)
   int kblocks;       // ccs * K
@@ -86,6 +92,20 @@ __device__ __forceinline__ void for_each_kblock(const TcFwdParams& prm, int grp,
   }
 }
 
+// Work items of a CTA: tiles blockIdx.x, +gridDim.x, ... through the complete rounds, then at most ONE row range
+// of a tail tile (tile index >= full_tiles marks it; its rows are a per-CTA constant, see tail_rows_of_cta).
+__device__ __forceinline__ int next_tile(const TcFwdParams& prm, int t) {   // -1: no more work
+  if (t >= prm.full_tiles) return -1;                       // the tail item is always the last one
+  const int n = t + (int)gridDim.x;
+  if (n < prm.full_tiles) return n;
+  const int j = (int)blockIdx.x;                            // == n - full_tiles
+  return j < prm.tail_tiles * prm.tail_split ? prm.full_tiles + j / prm.tail_split : -1;
+}
+__device__ __forceinline__ void tail_rows_of_cta(const TcFwdParams& prm, int& lo, int& hi) {
+  lo = ((int)blockIdx.x % prm.tail_split) * prm.tail_rows;
+  hi = min(TC_BM, lo + prm.tail_rows);
+}
+
 // The same sequence as for_each_kblock, but as an explicit iterator over (tile, run, tap, channel
 // block) so the gather warps can look one K-block ahead (loads of K-block k+1 are issued before
 // K-block k is interpolated).
@@ -99,18 +119,18 @@ struct KbIter {
   }
   __device__ __forceinline__ void set_tile(const TcFwdParams& prm, int tile) {
     t = tile;
-    valid = tile < prm.total_tiles;
+    valid = tile >= 0;
     grp = valid ? (tile / prm.m_tiles) / prm.n_tiles : 0;
     tap = 0;
     set_run(prm, 0);
     cc = 0;
   }
-  __device__ __forceinline__ void advance(const TcFwdParams& prm, int tile_stride) {
+  __device__ __forceinline__ void advance(const TcFwdParams& prm) {
     if (++cc < run_end) return;
     if (++tap < prm.g.K) { cc = run0; return; }
     tap = 0;
     if (run_end < prm.ccs) { set_run(prm, run_end); cc = run0; return; }
-    set_tile(prm, t + tile_stride);
+    set_tile(prm, next_tile(prm, t));
   }
   __device__ __forceinline__ bool first() const { return cc == run0; }
   __device__ __forceinline__ bool last() const { return cc == run_end - 1; }
@@ -229,7 +249,7 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x) {
+      for (int t = blockIdx.x; t >= 0; t = next_tile(prm, t)) {
         const int rest = t / prm.m_tiles;
         const int nt = rest % prm.n_tiles, grp = rest / prm.n_tiles;
         const int row0 = grp * g.Cog + nt * BN;
@@ -252,7 +272,7 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
       uint32_t ph = 0;
       int as = 0;
       uint32_t aph = 0;
-      for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x) {
+      for (int t = blockIdx.x; t >= 0; t = next_tile(prm, t)) {
         ptx::mbar_wait(&tmem_empty[as], aph ^ 1);
         ptx::tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * TC_MAX_BN);
@@ -291,12 +311,16 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
     int as = 0;
     uint32_t aph = 0;
     int cl_buf = 0;
-    for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x) {
+    int tail_lo, tail_hi;
+    tail_rows_of_cta(prm, tail_lo, tail_hi);
+    const int trow = ew * 32 + lane;
+    const bool in_tail_rows = trow >= tail_lo && trow < tail_hi;
+    for (int t = blockIdx.x; t >= 0; t = next_tile(prm, t)) {
       const int mt = t % prm.m_tiles;
       const int rest = t / prm.m_tiles;
       const int nt = rest % prm.n_tiles, grp = rest / prm.n_tiles;
-      const long long gp = (long long)mt * TC_BM + ew * 32 + lane;
-      const bool valid = gp < total_pix;
+      const long long gp = (long long)mt * TC_BM + trow;
+      const bool valid = gp < total_pix && (t < prm.full_tiles || in_tail_rows);
       const int b = valid ? (int)(gp / g.P) : 0;
       const int p = valid ? (int)(gp % g.P) : 0;
       const int co0 = grp * g.Cog + nt * BN;
@@ -356,11 +380,14 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
     const int C8 = F32 ? g.C >> 2 : g.C >> 3;   // 16-byte vectors per position
     int ps = 0;
     uint32_t pph = 0;
-    for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x) {
+    int tail_lo, tail_hi;
+    tail_rows_of_cta(prm, tail_lo, tail_hi);
+    const bool in_tail_rows = row >= tail_lo && row < tail_hi;
+    for (int t = blockIdx.x; t >= 0; t = next_tile(prm, t)) {
       const int mt = t % prm.m_tiles;
       const int grp = (t / prm.m_tiles) / prm.n_tiles;
       const long long gp = (long long)mt * TC_BM + row;
-      const bool v = gp < total_pix;
+      const bool v = gp < total_pix && (t < prm.full_tiles || in_tail_rows);
       RowCoord<ND> rc;
       tc::decode_row<ND>(g, v ? (int)(gp / g.P) : 0, v ? (int)(gp % g.P) : 0, v, rc);
       for_each_kblock(prm, grp, [&](int cc, int tap, bool first, int) {
@@ -392,6 +419,8 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
     uint32_t ph = 0;
     int ips = 0, cps = 0;      // plan ring positions: issue side / consume side
     uint32_t ipph = 0;
+    // (rows outside a tail item's range carry an all-zero plan: their loads all hit the one cached all-zero
+    // position, a quarter of the L1 wavefronts of a live row, and nothing reads the rows back)
 
     // issue the corner loads of K-block `it` into (v0, v1)
     auto issue = [&](const KbIter& it, uint4 (&v0)[NC], uint4 (&v1)[NC]) {
@@ -498,19 +527,19 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
     if (F32) {
       while (ka.valid) {
         block_f32(ka);
-        ka.advance(prm, gridDim.x);
+        ka.advance(prm);
       }
     } else if (ND == 2 || GRID) {
       uint4 a0[NC], a1[NC], b0[NC], b1[NC];
       if (ka.valid) issue(ka, a0, a1);
       while (ka.valid) {
         kb2 = ka;
-        kb2.advance(prm, gridDim.x);
+        kb2.advance(prm);
         if (kb2.valid) issue(kb2, b0, b1);
         finish(ka, a0, a1);
         if (!kb2.valid) break;
         ka = kb2;
-        ka.advance(prm, gridDim.x);
+        ka.advance(prm);
         if (ka.valid) issue(ka, a0, a1);
         finish(kb2, b0, b1);
       }
@@ -520,7 +549,7 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
       while (ka.valid) {
         issue(ka, a0, a1);
         finish(ka, a0, a1);
-        ka.advance(prm, gridDim.x);
+        ka.advance(prm);
       }
     }
   }
@@ -708,6 +737,8 @@ void tensor_forward_t(const DevGeom& g, const void* x, const void* w, const void
   prm.ccs = g.Cg / TC_BK;
   prm.bpd = g.Cdg / TC_BK;
   prm.kblocks = prm.ccs * g.K;
+  tc::plan_tail_split(prm.total_tiles, tc::sm_count(), !g.cl, prm.full_tiles, prm.tail_tiles, prm.tail_split,
+                      prm.tail_rows);
 
   FwdMaps maps;
   memset(&maps, 0, sizeof(maps));
