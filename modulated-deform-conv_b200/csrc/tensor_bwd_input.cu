@@ -289,8 +289,7 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = sA + GI_STAGES * GI_A_BYTES;
-  uint8_t* sStage = sB + GI_STAGES * GI_B_BYTES;   // two output staging tiles, channels-last callers only
-  GiPlanRow* sPlan = reinterpret_cast<GiPlanRow*>(sStage + (CL ? 2 * CL_STAGE_BYTES : 0));
+  GiPlanRow* sPlan = reinterpret_cast<GiPlanRow*>(sB + GI_STAGES * GI_B_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sPlan + GI_PLAN_SLOTS * GI_BM);
   uint64_t* full_a = bars;
   uint64_t* full_b = full_a + GI_STAGES;
@@ -307,7 +306,7 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const __grid_consta
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_wt);
-    if (CL) ptx::prefetch_tensormap(&tmap_gx);
+    (void)tmap_gx;
     for (int s = 0; s < GI_STAGES; ++s) {
       ptx::mbar_init(&full_a[s], ptx::arrivals(GI_GATHER_THREADS));
       ptx::mbar_init(&full_b[s], 1);
@@ -389,7 +388,6 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const __grid_consta
     T* __restrict__ gx = reinterpret_cast<T*>(prm.gx);
     int as = 0;
     uint32_t aph = 0;
-    int cl_buf = 0;
     for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x) {
       const int mt = t % prm.m_tiles;
       const int nt = t / prm.m_tiles;
@@ -402,9 +400,29 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const __grid_consta
       ptx::tc_fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * GI_MAX_BN);
       if constexpr (CL) {
-        // channels-last grad_input [B*IN][C]: 64-channel chunks through shared memory and TMA stores
-        epilogue_store_channels_last<T>(taddr, BN, nullptr, sStage, cl_buf, &tmap_gx, nt * BN, mt * GI_BM,
-                                        ew * 32 + lane, ew == 0 && lane == 0, 1);
+        // channels-last grad_input [B*IN][C]: the thread's row is contiguous in memory -- 16-byte stores straight
+        // from the converted accumulator (no staging tile: the 32 KB it would take halve the L1 left to the
+        // inverse-index gather, which costs more than the TMA store saves; the forward's epilogue, whose gather is
+        // less L1-sensitive, does go through shared memory and cp.async.bulk.tensor)
+        T* crow = gx + (size_t)(valid ? gp : 0) * g.C + (size_t)nt * BN;
+        for (int cc = 0; cc < BN; cc += 16) {
+          uint32_t v[16];
+          ptx::tmem_ld_32x16(taddr + cc, v);
+          ptx::tmem_ld_wait();
+          if (valid) {
+            uint4 o0, o1;
+            o0.x = pack2_storage(__uint_as_float(v[0]), __uint_as_float(v[1]), T());
+            o0.y = pack2_storage(__uint_as_float(v[2]), __uint_as_float(v[3]), T());
+            o0.z = pack2_storage(__uint_as_float(v[4]), __uint_as_float(v[5]), T());
+            o0.w = pack2_storage(__uint_as_float(v[6]), __uint_as_float(v[7]), T());
+            o1.x = pack2_storage(__uint_as_float(v[8]), __uint_as_float(v[9]), T());
+            o1.y = pack2_storage(__uint_as_float(v[10]), __uint_as_float(v[11]), T());
+            o1.z = pack2_storage(__uint_as_float(v[12]), __uint_as_float(v[13]), T());
+            o1.w = pack2_storage(__uint_as_float(v[14]), __uint_as_float(v[15]), T());
+            *reinterpret_cast<uint4*>(crow + cc) = o0;
+            *reinterpret_cast<uint4*>(crow + cc + 8) = o1;
+          }
+        }
       } else {
         for (int cc = 0; cc < BN; cc += 16) {
           uint32_t v[16];
@@ -420,7 +438,6 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const __grid_consta
       ptx::mbar_arrive_warp(&tmem_empty[as]);
       if (++as == 2) { as = 0; aph ^= 1; }
     }
-    if (CL && ew == 0 && lane == 0) ptx::bulk_wait_group<0>();   // the staging tiles must outlive their stores
   } else if (warp < GI_GATHER_WARP0) {
     // ===================== plan producers =====================
     ptx::reg_dealloc<GI_REGS_PLAN>();
@@ -569,8 +586,9 @@ __global__ void k_transpose_weight(const T* __restrict__ w, T* __restrict__ wt, 
 }
 
 size_t smem_bytes_gi(bool cl) {
-  return 1024 + (size_t)GI_STAGES * (GI_A_BYTES + GI_B_BYTES) + (cl ? 2 * CL_STAGE_BYTES : 0) +
-         (size_t)GI_PLAN_SLOTS * GI_BM * sizeof(GiPlanRow) + (3 * GI_STAGES + 2 * GI_PLAN_SLOTS + 4) * sizeof(uint64_t) + 16;
+  (void)cl;
+  return 1024 + (size_t)GI_STAGES * (GI_A_BYTES + GI_B_BYTES) + (size_t)GI_PLAN_SLOTS * GI_BM * sizeof(GiPlanRow) +
+         (3 * GI_STAGES + 2 * GI_PLAN_SLOTS + 4) * sizeof(uint64_t) + 16;
 }
 
 int pick_bn_gi(const DevGeom& g) {
