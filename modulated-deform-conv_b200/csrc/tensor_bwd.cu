@@ -26,7 +26,10 @@ constexpr int GW_GATHER_WARP0 = 12;  // warps 12-27: gather producers
 constexpr int GW_GATHER_WARPS = 16;
 constexpr int GW_GATHER_THREADS = GW_GATHER_WARPS * 32;
 constexpr int GW_THREADS = (GW_GATHER_WARP0 + GW_GATHER_WARPS) * 32;  // 896
-constexpr int GW_STAGES = 3;
+#ifndef MDCONV_GW_STAGES
+#define MDCONV_GW_STAGES 3
+#endif
+constexpr int GW_STAGES = MDCONV_GW_STAGES;
 constexpr int GW_PLAN_SLOTS = 4;
 constexpr int GW_NB = 2;                       // 64-wide kk blocks per CTA tile (N = 128)
 constexpr int GW_GO_BYTES = 2 * 128 * 128;     // two M tiles of [128 co x 64 pos]

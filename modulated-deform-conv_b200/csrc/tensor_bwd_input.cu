@@ -31,7 +31,10 @@ namespace tc {
 namespace {
 
 constexpr int GI_BM = 128;
-constexpr int GI_STAGES = 3;
+#ifndef MDCONV_GI_STAGES
+#define MDCONV_GI_STAGES 3
+#endif
+constexpr int GI_STAGES = MDCONV_GI_STAGES;
 constexpr int GI_PLAN_SLOTS = 2;
 constexpr int GI_MAX_BN = 256;
 constexpr int GI_PLAN_WARP0 = 8;      // warps 8-11: plan producers (bin heads -> smem)

@@ -38,11 +38,27 @@ constexpr int GS_DOT_WARP0 = 8;
 constexpr int GS_DOT_WARPS = 16;
 constexpr int GS_DOT_THREADS = GS_DOT_WARPS * 32;
 constexpr int GS_THREADS = (GS_DOT_WARP0 + GS_DOT_WARPS) * 32;  // 768
-constexpr int GS_STAGES = 4;
+#ifndef MDCONV_GS_STAGES
+#define MDCONV_GS_STAGES 3
+#endif
+constexpr int GS_STAGES = MDCONV_GS_STAGES;
 constexpr int GS_KCO = 32;                // output channels per K-block
 constexpr int GS_A_BYTES = 2 * GS_KCO * 128;  // two [32 co x 64 pos] blocks
 constexpr int GS_B_BYTES = 4 * GS_KCO * 128;  // up to four [32 co x 64 kk] blocks
 constexpr int GS_T_BYTES = 128 * 128;     // one [128 pos x 64 ch] block in the storage dtype
+// registers after setmaxnreg (the CTA owns GS_THREADS x 80): 3D gives the dot warps all it can (their two rows x 8
+// corner vectors are 64 registers on their own); 2D keeps the movers whole (their TMEM read + sampling entry spill
+// below 80) and hands the dot warps what the control warps free
+#ifndef MDCONV_GS3_CTL
+#define MDCONV_GS3_CTL 24
+#define MDCONV_GS3_MOVER 72
+#define MDCONV_GS3_DOT 96
+#endif
+template <int ND> struct GsRegs {
+  static constexpr bool REBALANCE = ND == 3;   // 2D: every warp keeps its launch-time 80 (the split only costs there)
+  static constexpr uint32_t CTL = MDCONV_GS3_CTL, MOVER = MDCONV_GS3_MOVER, DOT = MDCONV_GS3_DOT;
+  static_assert(128 * (CTL + MOVER) + GS_DOT_THREADS * DOT <= GS_THREADS * 80, "setmaxnreg.inc would wait forever");
+};
 
 template <int ND>
 struct __align__(16) SampleEntry {
@@ -157,6 +173,10 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
   const int t_first = (int)(item0 / phases), phs_first = (int)(item0 - (long long)t_first * phases);
   const int n_items = (int)(item1 - item0);
 
+  // Register re-balancing (the CTA owns GS_THREADS x 80): the control warpgroup and the movers give registers to the
+  // dot warps, whose corner-load buffers (2 rows x 4 / 8 corners x 16 bytes in flight) set the pace.
+  if (warp < 4) {
+  if constexpr (GsRegs<ND>::REBALANCE) ptx::reg_dealloc<GsRegs<ND>::CTL>();
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -230,8 +250,10 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
         }
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  }
+  } else if (warp < 8) {
     // ===================== movers: sampling entries + TMEM -> smem re-layout =====================
+    if constexpr (GsRegs<ND>::REBALANCE) ptx::reg_dealloc<GsRegs<ND>::MOVER>();
     const int row = threadIdx.x - 128;  // TMEM lane == tile row
     const T* __restrict__ off = reinterpret_cast<const T*>(prm.off);
     const T* __restrict__ mask = reinterpret_cast<const T*>(prm.mask);
@@ -331,8 +353,9 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
       }
       if (++phs == phases) { phs = 0; ++t; new_tile = true; }
     }
-  } else if (warp >= GS_DOT_WARP0) {
+  } else {
     // ===================== dot warps =====================
+    if constexpr (GsRegs<ND>::REBALANCE) ptx::reg_alloc<GsRegs<ND>::DOT>();
     const int dw = warp - GS_DOT_WARP0;
     const int rq = lane >> 3;  // row inside a pass
     const int j = lane & 7;    // 8-channel chunk
@@ -365,17 +388,46 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
         for (int i = 0; i < 2; ++i)
 #pragma unroll
           for (int c = 0; c < NC; ++c) S[i][c] = 0.f;
-        for (int sub = 0; sub < nsub; ++sub) {
-          for (int jb = 0; jb < nb; ++jb) {
-            const int c0 = (dgi * bpd + sub * nb + jb) * 64;  // first channel of this block
-            const uint4* xc = xq + (c0 >> 3) + j;
-            // the corner values do not depend on the accumulator: issue the loads before waiting for it
+        // Software pipeline over the (64-channel block, row pass) steps of the item: while one row's dot products
+        // run, the corner loads of the NEXT step are in flight (two register buffers; the corner values do not
+        // depend on the accumulator, only their use waits for the T tile).
+        const int nblk = nsub * nb;   // 64-channel blocks of this (deformable group, tap)
+        auto load_row = [&](int blk, int i, uint4 (&v)[NC]) {
+          const uint4* xc = xq + (((dgi * bpd + blk) * 64) >> 3) + j;
+#pragma unroll
+          for (int c = 0; c < NC; ++c) v[c] = idx[i][c] >= 0 ? __ldg(xc + idx[i][c]) : make_uint4(0u, 0u, 0u, 0u);
+        };
+#ifndef MDCONV_GS_ROLL3D
+#define MDCONV_GS_ROLL3D 0
+#endif
+        if constexpr (ND == 2 || MDCONV_GS_ROLL3D) {
+          uint4 va[NC], vb[NC];
+          load_row(0, 0, va);
+          for (int blk = 0; blk < nblk; ++blk) {
+            load_row(blk, 1, vb);
+            ptx::mbar_wait(&t_full[ts], tph);
+            const uint32_t tb = ptx::smem_u32(sT + ts * GS_T_BYTES);
+            {
+              const uint4 gc = lds128(tb + sw128(row0, j));
+#pragma unroll
+              for (int c = 0; c < NC; ++c) S[0][c] += dot8(gc, va[c], T());
+            }
+            if (blk + 1 < nblk) load_row(blk + 1, 0, va);
+            {
+              const uint4 gc = lds128(tb + sw128(row0 + 4, j));
+#pragma unroll
+              for (int c = 0; c < NC; ++c) S[1][c] += dot8(gc, vb[c], T());
+            }
+            ptx::mbar_arrive_warp(&t_empty[ts]);
+            if (++ts == 2) { ts = 0; tph ^= 1; }
+          }
+        } else {
+          // 3D: 8 corners per row -- the rolling form needs more live registers than the dot warps have (it
+          // spills and runs a third slower); both rows' loads are issued together ahead of the wait instead
+          for (int blk = 0; blk < nblk; ++blk) {
             uint4 xv[2][NC];
-#pragma unroll
-            for (int i = 0; i < 2; ++i)
-#pragma unroll
-              for (int c = 0; c < NC; ++c)
-                xv[i][c] = idx[i][c] >= 0 ? __ldg(xc + idx[i][c]) : make_uint4(0u, 0u, 0u, 0u);
+            load_row(blk, 0, xv[0]);
+            load_row(blk, 1, xv[1]);
             ptx::mbar_wait(&t_full[ts], tph);
             const uint32_t tb = ptx::smem_u32(sT + ts * GS_T_BYTES);
 #pragma unroll

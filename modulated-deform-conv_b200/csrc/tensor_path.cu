@@ -39,7 +39,10 @@ namespace {
 
 constexpr int TC_BM = 128;        // pixels per tile (UMMA M)
 constexpr int TC_BK = tc::BK;     // K elements per block = 128 bytes = one swizzle row
-constexpr int TC_STAGES = 3;      // A/B operand ring
+#ifndef MDCONV_TC_STAGES
+#define MDCONV_TC_STAGES 3
+#endif
+constexpr int TC_STAGES = MDCONV_TC_STAGES;      // A/B operand ring
 constexpr int TC_PLAN_SLOTS = 4;  // sampling-plan ring
 constexpr int TC_MAX_BN = 256;
 constexpr int TC_PLAN_WARP0 = 8;      // warps 8-11: plan producers (one tile row per thread)
