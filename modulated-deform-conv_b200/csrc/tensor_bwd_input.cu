@@ -284,20 +284,22 @@ template <> struct Acc8<__nv_bfloat16> {
 
 // CL: the caller's activations are channels-last (grad_output is gathered in place, grad_input leaves through TMA
 // stores); a compile-time switch so the NCHW instantiation carries none of that epilogue's registers or code.
-template <typename T, bool CL>
+// STAGES: depth of the A/B operand ring.  3 for 2D; 2 for 3D, whose bins are twice as long (8 corners per sample):
+// there the 48 KB a third stage takes are worth more as L1 for the inverse-index gather (measured at cfg4).
+template <typename T, bool CL, int STAGES>
 __global__ void __launch_bounds__(GI_THREADS, 1)
 k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const __grid_constant__ CUtensorMap tmap_gx,
                 const TcGiParams prm) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
-  uint8_t* sB = sA + GI_STAGES * GI_A_BYTES;
-  GiPlanRow* sPlan = reinterpret_cast<GiPlanRow*>(sB + GI_STAGES * GI_B_BYTES);
+  uint8_t* sB = sA + STAGES * GI_A_BYTES;
+  GiPlanRow* sPlan = reinterpret_cast<GiPlanRow*>(sB + STAGES * GI_B_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sPlan + GI_PLAN_SLOTS * GI_BM);
   uint64_t* full_a = bars;
-  uint64_t* full_b = full_a + GI_STAGES;
-  uint64_t* empty = full_b + GI_STAGES;
-  uint64_t* plan_full = empty + GI_STAGES;
+  uint64_t* full_b = full_a + STAGES;
+  uint64_t* empty = full_b + STAGES;
+  uint64_t* plan_full = empty + STAGES;
   uint64_t* plan_empty = plan_full + GI_PLAN_SLOTS;
   uint64_t* tmem_full = plan_empty + GI_PLAN_SLOTS;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -310,7 +312,7 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const __grid_consta
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_wt);
     (void)tmap_gx;
-    for (int s = 0; s < GI_STAGES; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(&full_a[s], ptx::arrivals(GI_GATHER_THREADS));
       ptx::mbar_init(&full_b[s], 1);
       ptx::mbar_init(&empty[s], 1);
@@ -348,7 +350,7 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const __grid_consta
           ptx::mbar_wait_relaxed(&empty[s], ph ^ 1, 64);
           ptx::mbar_arrive_expect_tx(&full_b[s], (uint32_t)BN * 128u);
           ptx::tma_load_2d(sB + s * GI_B_BYTES, &tmap_wt, &full_b[s], kb * 64, c0);
-          if (++s == GI_STAGES) { s = 0; ph ^= 1; }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -377,7 +379,7 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const __grid_consta
             ptx::umma_f16(d_tmem, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
           ptx::umma_commit(&empty[s]);
-          if (++s == GI_STAGES) { s = 0; ph ^= 1; }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
         ptx::umma_commit(&tmem_full[as]);
         if (++as == 2) { as = 0; aph ^= 1; }
@@ -542,8 +544,8 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const __grid_consta
 #pragma unroll
           for (int i = 0; i < GI_NE; ++i)
             if (i < n) acc.fma(v[i], wh[i]);
-          for (int e = GI_NE; e < n; ++e) {   // rare: bins longer than the staged head
-            const int2 ee = __ldg(entries2 + (int)meta.y + e);
+          for (int e = GI_NE; e < n; ++e) {   // bins longer than the staged head (kept serial: unrolling it spills
+            const int2 ee = __ldg(entries2 + (int)meta.y + e);   // the ping-pong load buffers of the common path)
             acc.fma(__ldg(reinterpret_cast<const uint4*>(base + (size_t)ee.x * (size_t)(g.Co * 2))),
                     __int_as_float(ee.y));
           }
@@ -559,7 +561,7 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const __grid_consta
           finish(vb, 1, gcb, a_addr);
           ptx::fence_proxy_async_smem();
           ptx::mbar_arrive_warp(&full_a[s]);
-          if (++s == GI_STAGES) { s = 0; ph ^= 1; }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
           gcb += 128;
         }
         ptx::mbar_arrive_warp(&plan_empty[ps]);
@@ -588,10 +590,20 @@ __global__ void k_transpose_weight(const T* __restrict__ w, T* __restrict__ wt, 
   }
 }
 
-size_t smem_bytes_gi(bool cl) {
-  (void)cl;
-  return 1024 + (size_t)GI_STAGES * (GI_A_BYTES + GI_B_BYTES) + (size_t)GI_PLAN_SLOTS * GI_BM * sizeof(GiPlanRow) +
-         (3 * GI_STAGES + 2 * GI_PLAN_SLOTS + 4) * sizeof(uint64_t) + 16;
+size_t smem_bytes_gi(int stages) {
+  return 1024 + (size_t)stages * (GI_A_BYTES + GI_B_BYTES) + (size_t)GI_PLAN_SLOTS * GI_BM * sizeof(GiPlanRow) +
+         (3 * stages + 2 * GI_PLAN_SLOTS + 4) * sizeof(uint64_t) + 16;
+}
+
+template <typename T, bool CL, int STAGES>
+void launch_grad_input(const CUtensorMap& tmap, const CUtensorMap& tmap_gx, const TcGiParams& prm, int grid,
+                       LaunchCtx& ctx) {
+  const size_t smem = smem_bytes_gi(STAGES);
+  static std::atomic<unsigned long long> configured{0};
+  opt_in_dynamic_smem(k_tc_grad_input<T, CL, STAGES>, smem, configured, ctx);
+  ProfScope prof(ctx, "tc_grad_input");
+  k_tc_grad_input<T, CL, STAGES><<<grid, GI_THREADS, smem, ctx.stream>>>(tmap, tmap_gx, prm);
+  MDCONV_CHECK_LAUNCH(ctx);
 }
 
 int pick_bn_gi(const DevGeom& g) {
@@ -767,16 +779,15 @@ void tensor_grad_input(const DevGeom& g, const void* w, const void* go, void* gx
     if (ctx.err == cudaSuccess) ctx.err = cudaErrorInvalidValue;
     return;
   }
-  const size_t smem = smem_bytes_gi(g.cl != 0);
-  static std::atomic<unsigned long long> configured{0}, configured_cl{0};
-  if (g.cl) opt_in_dynamic_smem(k_tc_grad_input<T, true>, smem, configured_cl, ctx);
-  else opt_in_dynamic_smem(k_tc_grad_input<T, false>, smem, configured, ctx);
   const int sms = sm_count() - ctx.spare_sms > 0 ? sm_count() - ctx.spare_sms : 1;
   const int grid = prm.total_tiles < sms ? prm.total_tiles : sms;
-  ProfScope prof(ctx, "tc_grad_input");
-  if (g.cl) k_tc_grad_input<T, true><<<grid, GI_THREADS, smem, ctx.stream>>>(tmap, tmap_gx, prm);
-  else k_tc_grad_input<T, false><<<grid, GI_THREADS, smem, ctx.stream>>>(tmap, tmap_gx, prm);
-  MDCONV_CHECK_LAUNCH(ctx);
+  if (g.nd == 3) {
+    if (g.cl) launch_grad_input<T, true, 2>(tmap, tmap_gx, prm, grid, ctx);
+    else launch_grad_input<T, false, 2>(tmap, tmap_gx, prm, grid, ctx);
+  } else {
+    if (g.cl) launch_grad_input<T, true, GI_STAGES>(tmap, tmap_gx, prm, grid, ctx);
+    else launch_grad_input<T, false, GI_STAGES>(tmap, tmap_gx, prm, grid, ctx);
+  }
 }
 
 template void tensor_grad_input<__half>(const DevGeom&, const void*, const void*, void*, void*, LaunchCtx&);
