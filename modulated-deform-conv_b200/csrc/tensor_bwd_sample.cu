@@ -27,6 +27,8 @@
 //                (all in flight together), dot products against gcol (HFMA2 quads folded into fp32 for
 //                fp16, fp32 FMAs for bf16), warp-shuffle reduction over the 8 lanes, final combine and
 //                store of grad_offset / grad_mask
+#include <string.h>
+
 #include "tc_common.cuh"
 
 namespace mdconv {
@@ -60,6 +62,14 @@ template <int ND> struct GsRegs {
   static_assert(128 * (CTL + MOVER) + GS_DOT_THREADS * DOT <= GS_THREADS * 80, "setmaxnreg.inc would wait forever");
 };
 
+// Offset / mask slab ring (north_star: "TMA bulk loads of ... offset/mask slabs into shared memory"): per work item
+// (128-position tile = two 64-position blocks, one tap) the ND offset rows and the mask row of each block arrive by
+// cp.async.bulk.tensor straight from the caller's NCHW tensors, OM_SLOTS items ahead of the movers, so the sampling
+// entries are built from shared memory instead of behind 3-4 dependent global loads per item.
+constexpr int GS_OM_SLOTS = 4;
+constexpr int GS_OM_ROW_BYTES = 128;                       // 64 positions x 2 bytes
+template <int ND> constexpr int gs_om_slot_bytes() { return 2 * (ND + 1) * GS_OM_ROW_BYTES; }   // 2 blocks x (ND offsets + mask)
+
 template <int ND>
 struct __align__(16) SampleEntry {
   int idx[1 << ND];  // uint4 index of the corner's 8-channel vector (channel offset excluded), -1: value is 0
@@ -82,6 +92,7 @@ struct TcGsParams {
   int total_pb;      // B * pbi
   int m_tiles;       // ceil(total_pb / 2)
   long long items;   // m_tiles * dg * K (tile, phase) work items, split evenly over the CTAs
+  int om_tma;        // 1: offset / mask slabs come by TMA (needs P % 8 == 0: 16-byte global strides), 0: global loads
 };
 
 // dot product of two 8-element vectors stored in the tensor dtype
@@ -105,6 +116,8 @@ __device__ __forceinline__ float dot8(const uint4& a, const uint4& b, __nv_bfloa
   const float2 f = __bfloat1622float2(p);
   return f.x + f.y;
 }
+__device__ __forceinline__ float cvt_from_storage(__half v) { return __half2float(v); }
+__device__ __forceinline__ float cvt_from_storage(__nv_bfloat16 v) { return __bfloat162float(v); }
 __device__ __forceinline__ uint32_t pack2(float a, float b, __half) {
   const __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
@@ -117,6 +130,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, __nv_bfloat16) {
 template <typename T, int ND, bool MOD>
 __global__ void __launch_bounds__(GS_THREADS, 1)
 k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_constant__ CUtensorMap tmap_w,
+                 const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ CUtensorMap tmap_mask,
                  const TcGsParams prm) {
   constexpr int NC = 1 << ND;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -134,7 +148,10 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
   uint64_t* t_empty = t_full + 2;           // [2]          dot warps -> movers
   uint64_t* plan_full = t_empty + 2;        // [2]          movers -> dot warps
   uint64_t* plan_empty = plan_full + 2;     // [2]          dot warps -> movers
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(plan_empty + 2);
+  uint64_t* om_full = plan_empty + 2;       // [GS_OM_SLOTS] TMA -> movers (offset / mask slabs)
+  uint64_t* om_empty = om_full + GS_OM_SLOTS;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(om_empty + GS_OM_SLOTS);
+  uint8_t* sOM = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_ptr + 4) + 127) & ~(uintptr_t)127);
 
   const DevGeom& g = prm.g;
   const int warp = threadIdx.x >> 5;
@@ -154,6 +171,14 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
       ptx::mbar_init(&t_empty[s], ptx::arrivals(GS_DOT_THREADS));
       ptx::mbar_init(&plan_full[s], ptx::arrivals(128));
       ptx::mbar_init(&plan_empty[s], ptx::arrivals(GS_DOT_THREADS));
+    }
+    for (int s = 0; s < GS_OM_SLOTS; ++s) {
+      ptx::mbar_init(&om_full[s], 1);
+      ptx::mbar_init(&om_empty[s], ptx::arrivals(128));
+    }
+    if (prm.om_tma) {
+      ptx::prefetch_tensormap(&tmap_off);
+      if (MOD) ptx::prefetch_tensormap(&tmap_mask);
     }
     ptx::fence_barrier_init();
   }
@@ -250,6 +275,30 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
         }
       }
     }
+  } else if (warp == 3) {
+    // ===================== TMA producer: offset / mask slabs =====================
+    if (lane == 0 && prm.om_tma) {
+      int os = 0;
+      uint32_t oph = 0;
+      int t = t_first, phs = phs_first;
+      for (int it = 0; it < n_items; ++it) {
+        const int dgi = phs / g.K, tap = phs - dgi * g.K;
+        ptx::mbar_wait_relaxed(&om_empty[os], oph ^ 1, 64);
+        ptx::mbar_arrive_expect_tx(&om_full[os], (uint32_t)(2 * (ND + (MOD ? 1 : 0)) * GS_OM_ROW_BYTES));
+        uint8_t* slot = sOM + os * gs_om_slot_bytes<ND>();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int pb = 2 * t + h;
+          const int b = pb < prm.total_pb ? pb / prm.pbi : g.B;        // b == B: out of bounds -> zero fill
+          const int p0 = pb < prm.total_pb ? (pb % prm.pbi) * 64 : 0;
+          uint8_t* dst = slot + h * (ND + 1) * GS_OM_ROW_BYTES;
+          ptx::tma_load_3d(dst, &tmap_off, &om_full[os], p0, (dgi * g.K + tap) * ND, b);
+          if (MOD) ptx::tma_load_3d(dst + ND * GS_OM_ROW_BYTES, &tmap_mask, &om_full[os], p0, dgi * g.K + tap, b);
+        }
+        if (++os == GS_OM_SLOTS) { os = 0; oph ^= 1; }
+        if (++phs == phases) { phs = 0; ++t; }
+      }
+    }
   }
   } else if (warp < 8) {
     // ===================== movers: sampling entries + TMEM -> smem re-layout =====================
@@ -259,8 +308,8 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
     const T* __restrict__ mask = reinterpret_cast<const T*>(prm.mask);
     const int C8 = g.C >> 3;
     const bool rule_b = g.rule != 0;
-    int as = 0, ts = 0, ps = 0;
-    uint32_t aph = 0, tph = 0, pph = 0;
+    int as = 0, ts = 0, ps = 0, os = 0;
+    uint32_t aph = 0, tph = 0, pph = 0, oph = 0;
     int t = t_first, phs = phs_first;
     bool new_tile = true;
     bool valid = false;
@@ -284,9 +333,23 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
           for (int a = 0; a < ND; ++a) e.fr[a] = 0.f;
           e.m = 0.f;
           e.flags = 0u;
+          RawSample<ND> raw;
+          if (prm.om_tma) {
+            // this row's offsets / mask of the item, from the slab the TMA warp fetched ahead
+            ptx::mbar_wait(&om_full[os], oph);
+            const T* srow = reinterpret_cast<const T*>(sOM + os * gs_om_slot_bytes<ND>() +
+                                                       (row >> 6) * (ND + 1) * GS_OM_ROW_BYTES) + (row & 63);
+#pragma unroll
+            for (int a = 0; a < ND; ++a) raw.o[a] = cvt_from_storage(srow[a * 64]);
+            raw.m = MOD ? cvt_from_storage(srow[ND * 64]) : 1.f;
+            ptx::mbar_arrive_warp(&om_empty[os]);
+            if (++os == GS_OM_SLOTS) { os = 0; oph ^= 1; }
+          } else if (valid) {
+            raw = fetch_sample<T, ND, MOD>(g, off, mask, rc, dgi, tap);
+          }
           if (valid) {
             SamplePos<ND> sp;
-            sample_pos<T, ND, MOD>(g, off, mask, rc, dgi, tap, sp);
+            build_pos<ND>(g, rc, tap, raw, sp);
             bool lo_ok[ND], hi_ld[ND];
 #pragma unroll
             for (int a = 0; a < ND; ++a) {
@@ -519,18 +582,19 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
 template <int ND>
 size_t gs_smem_bytes() {
   return 1024 + (size_t)GS_STAGES * (GS_A_BYTES + GS_B_BYTES) + 2 * GS_T_BYTES + 2 * 128 * sizeof(SampleEntry<ND>) +
-         (2 * GS_STAGES + 12) * sizeof(uint64_t) + 16;
+         (2 * GS_STAGES + 12 + 2 * GS_OM_SLOTS) * sizeof(uint64_t) + 160 + (size_t)GS_OM_SLOTS * gs_om_slot_bytes<ND>();
 }
 
 template <typename T, int ND, bool MOD>
-void launch_grad_sample(const CUtensorMap& tmap_go, const CUtensorMap& tmap_w, const TcGsParams& prm, LaunchCtx& ctx) {
+void launch_grad_sample(const CUtensorMap& tmap_go, const CUtensorMap& tmap_w, const CUtensorMap& tmap_off,
+                        const CUtensorMap& tmap_mask, const TcGsParams& prm, LaunchCtx& ctx) {
   const size_t smem = gs_smem_bytes<ND>();
   static std::atomic<unsigned long long> configured{0};
   opt_in_dynamic_smem(k_tc_grad_sample<T, ND, MOD>, smem, configured, ctx);
   const int sms = sm_count() - ctx.spare_sms > 0 ? sm_count() - ctx.spare_sms : 1;
   const int grid = prm.items < sms ? (int)prm.items : sms;
   ProfScope prof(ctx, "tc_grad_sample");
-  k_tc_grad_sample<T, ND, MOD><<<grid, GS_THREADS, smem, ctx.stream>>>(tmap_go, tmap_w, prm);
+  k_tc_grad_sample<T, ND, MOD><<<grid, GS_THREADS, smem, ctx.stream>>>(tmap_go, tmap_w, tmap_off, tmap_mask, prm);
   MDCONV_CHECK_LAUNCH(ctx);
 }
 
@@ -591,12 +655,35 @@ void tensor_grad_sample(const DevGeom& g, const T* xt, const T* wr, const void* 
       return;
     }
   }
+  // offset [B][dg*K*nd][P] and mask [B][dg*K][P] as 3D maps, un-swizzled boxes of 64 positions x (nd | 1) channels
+  CUtensorMap tmap_off, tmap_mask;
+  memset(&tmap_off, 0, sizeof(tmap_off));
+  memset(&tmap_mask, 0, sizeof(tmap_mask));
+  prm.om_tma = (g.P % 8 == 0 && ((uintptr_t)off & 15) == 0 && (!g.modulated || ((uintptr_t)mask & 15) == 0)) ? 1 : 0;
+  if (prm.om_tma) {
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const cuuint64_t odims[3] = {(cuuint64_t)g.P, (cuuint64_t)g.dg * g.K * g.nd, (cuuint64_t)g.B};
+    const cuuint64_t ostr[2] = {(cuuint64_t)g.P * sizeof(T), (cuuint64_t)g.dg * g.K * g.nd * g.P * sizeof(T)};
+    const cuuint32_t obox[3] = {64, (cuuint32_t)g.nd, 1};
+    CUresult r = enc(&tmap_off, tmap_dtype<T>(), 3, const_cast<void*>(off), odims, ostr, obox, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS && g.modulated) {
+      const cuuint64_t mdims[3] = {(cuuint64_t)g.P, (cuuint64_t)g.dg * g.K, (cuuint64_t)g.B};
+      const cuuint64_t mstr[2] = {(cuuint64_t)g.P * sizeof(T), (cuuint64_t)g.dg * g.K * g.P * sizeof(T)};
+      const cuuint32_t mbox[3] = {64, 1, 1};
+      r = enc(&tmap_mask, tmap_dtype<T>(), 3, const_cast<void*>(mask), mdims, mstr, mbox, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS) prm.om_tma = 0;   // fall back to global loads
+  }
   if (g.nd == 2) {
-    if (g.modulated) launch_grad_sample<T, 2, true>(tmap_go, tmap_w, prm, ctx);
-    else launch_grad_sample<T, 2, false>(tmap_go, tmap_w, prm, ctx);
+    if (g.modulated) launch_grad_sample<T, 2, true>(tmap_go, tmap_w, tmap_off, tmap_mask, prm, ctx);
+    else launch_grad_sample<T, 2, false>(tmap_go, tmap_w, tmap_off, tmap_mask, prm, ctx);
   } else {
-    if (g.modulated) launch_grad_sample<T, 3, true>(tmap_go, tmap_w, prm, ctx);
-    else launch_grad_sample<T, 3, false>(tmap_go, tmap_w, prm, ctx);
+    if (g.modulated) launch_grad_sample<T, 3, true>(tmap_go, tmap_w, tmap_off, tmap_mask, prm, ctx);
+    else launch_grad_sample<T, 3, false>(tmap_go, tmap_w, tmap_off, tmap_mask, prm, ctx);
   }
 }
 
