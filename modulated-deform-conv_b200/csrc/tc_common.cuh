@@ -417,8 +417,8 @@ bool tensor_backward_supported(const DevGeom& g, int dtype);
 // grad_offset / grad_mask (tensor_bwd_sample.cu)
 bool grad_sample_supported(const DevGeom& g);
 template <typename T>
-void tensor_grad_sample(const DevGeom& g, const T* xt, const T* wr, const void* off, const void* mask, const void* go,
-                        int go_ld, void* goff, void* gmask, LaunchCtx& ctx);
+void tensor_grad_sample(const DevGeom& g, const T* xt, const void* wr, const void* off, const void* mask, const void* go,
+                        const void* go_lo, int go_ld, void* goff, void* gmask, LaunchCtx& ctx);
 // grad_input (tensor_bwd_input.cu)
 bool grad_input_supported(const DevGeom& g);
 size_t grad_input_workspace(const DevGeom& g);

@@ -496,10 +496,10 @@ static size_t go_pad_bytes(const DevGeom& g) {
   return (g.P % 8 == 0 && !g.cl) ? 0 : align256((size_t)g.B * g.Co * go_ld(g) * 2);
 }
 
-// grad_offset / grad_mask / grad_input on the tensor kernels: 16-bit callers whose shapes those two kernels take;
-// fp32 callers keep the exact SIMT data-gradient kernel (their grad_weight is the tensor-core part)
+// grad_offset / grad_mask / grad_input on the tensor kernels: callers (16-bit, or fp32 as split bf16) whose shapes
+// those two kernels take; everything else keeps the SIMT data-gradient kernel
 static bool data_on_tensor_cores(const DevGeom& g) {
-  return g.esize == 2 && grad_sample_supported(g) && grad_input_supported(g);
+  return (g.esize == 2 || g.esize == 4) && grad_sample_supported(g) && grad_input_supported(g);
 }
 
 size_t tensor_backward_workspace(const DevGeom& g) {
@@ -567,9 +567,7 @@ void tensor_backward_t(const DevGeom& g, const void* x, const void* w, const voi
 
   // the inverse index of grad_input only needs offset/mask: build it on the side stream, beside the
   // layout passes and ahead of the big kernels
-  if constexpr (!F32) {
-    if (data_tc) tensor_grad_input_prepare<T>(g, off, mask, data_ws, ctx);
-  }
+  if (data_tc) tensor_grad_input_prepare<T>(g, off, mask, data_ws, ctx);
   if (saved == nullptr) {
     if (!g.cl) launch_to_channels_last<T>((const T*)x, const_cast<T*>(xt), g.B, g.C, g.IN, ctx, /*zero_row=*/true);
     if (data_tc) launch_reorder_weight<T>((const T*)w, const_cast<void*>(wr), g.Co, g.Cg, g.K, ctx);
@@ -632,12 +630,10 @@ void tensor_backward_t(const DevGeom& g, const void* x, const void* w, const voi
   signal_weight_ready(ctx);
 
   // ---- grad_offset / grad_mask / grad_input ----
-  if constexpr (!F32) {
-    if (data_tc) {
-      tensor_grad_sample<T>(g, xt, reinterpret_cast<const T*>(wr), off, mask, go_tma, ld, goff, gmask, ctx);
-      tensor_grad_input<T>(g, w, go, gx, data_ws, ctx);
-      return;
-    }
+  if (data_tc) {
+    tensor_grad_sample<T>(g, xt, wr, off, mask, go_tma, go_tma_lo, ld, goff, gmask, ctx);
+    tensor_grad_input<T>(g, w, go, gx, data_ws, ctx);
+    return;
   }
   generic_backward(g, dtype, x, w, off, mask, go, gx, gw, gb, goff, gmask, data_ws, ctx, GENERIC_BWD_DATA);
 }

@@ -54,6 +54,39 @@ struct __align__(16) GiPlanRow {
   int e0;              // index of the bin's first entry (for bins longer than GI_NE)
 };
 static_assert(sizeof(GiPlanRow) == 64, "GiPlanRow must be 64 bytes");
+// fp32 callers: the same row with fp32 weights (the gather accumulates in fp32 and splits the sum into bf16 hi / lo)
+struct __align__(16) GiPlanRowF32 {
+  uint32_t idx[GI_NE];
+  float w[GI_NE];
+  int n;
+  int e0;
+  int pad[2];
+};
+static_assert(sizeof(GiPlanRowF32) == 80, "GiPlanRowF32 must be 80 bytes");
+// fp32 callers run the contraction as split bf16 (see tensor_path.cu, FwdCfg): two A tiles and two B tiles per stage,
+// three products per K step, at most 128 channels per tile.
+template <typename T> struct GiCfg {
+  static constexpr bool F32 = false;
+  static constexpr int A_STAGE = GI_A_BYTES, MAX_BN_T = GI_MAX_BN;
+  using Row = GiPlanRow;
+};
+template <> struct GiCfg<float> {
+  static constexpr bool F32 = true;
+  static constexpr int A_STAGE = 2 * GI_A_BYTES, MAX_BN_T = 128;
+  using Row = GiPlanRowF32;
+};
+__device__ __forceinline__ void gi_split8(const float (&v)[8], uint4& hi, uint4& lo) {
+  uint32_t* h = reinterpret_cast<uint32_t*>(&hi);
+  uint32_t* l = reinterpret_cast<uint32_t*>(&lo);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    const float2 back = __bfloat1622float2(hh);
+    const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * i] - back.x, v[2 * i + 1] - back.y);
+    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+}
 // registers after setmaxnreg (the CTA owns GI_THREADS x 72)
 constexpr uint32_t GI_REGS_CTL = 32, GI_REGS_EPI = 40, GI_REGS_PLAN = 48, GI_REGS_GATHER = 96;
 static_assert(128 * (GI_REGS_CTL + GI_REGS_EPI + GI_REGS_PLAN) + GI_GATHER_THREADS * GI_REGS_GATHER <= GI_THREADS * 72,
@@ -282,6 +315,12 @@ template <> struct Acc8<__nv_bfloat16> {
   }
 };
 
+template <> struct Acc8<float> {   // placeholder: the fp32 gather has its own accumulation (never instantiated paths)
+  __device__ __forceinline__ void clear() {}
+  __device__ __forceinline__ void fma(const uint4&, float) {}
+  __device__ __forceinline__ uint4 pack() const { return make_uint4(0u, 0u, 0u, 0u); }
+};
+
 // CL: the caller's activations are channels-last (grad_output is gathered in place, grad_input leaves through TMA
 // stores); a compile-time switch so the NCHW instantiation carries none of that epilogue's registers or code.
 // STAGES: depth of the A/B operand ring.  3 for 2D; 2 for 3D, whose bins are twice as long (8 corners per sample):
@@ -289,12 +328,16 @@ template <> struct Acc8<__nv_bfloat16> {
 template <typename T, bool CL, int STAGES>
 __global__ void __launch_bounds__(GI_THREADS, 1)
 k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const __grid_constant__ CUtensorMap tmap_gx,
-                const TcGiParams prm) {
+                const __grid_constant__ CUtensorMap tmap_wt2, const TcGiParams prm) {
+  constexpr bool F32 = GiCfg<T>::F32;
+  constexpr int A_STAGE = GiCfg<T>::A_STAGE;
+  using PlanRow = typename GiCfg<T>::Row;
+  static_assert(!(F32 && CL), "no channels-last variant of the fp32 split path");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
-  uint8_t* sB = sA + STAGES * GI_A_BYTES;
-  GiPlanRow* sPlan = reinterpret_cast<GiPlanRow*>(sB + STAGES * GI_B_BYTES);
+  uint8_t* sB = sA + STAGES * A_STAGE;
+  PlanRow* sPlan = reinterpret_cast<PlanRow*>(sB + STAGES * GI_B_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sPlan + GI_PLAN_SLOTS * GI_BM);
   uint64_t* full_a = bars;
   uint64_t* full_b = full_a + STAGES;
@@ -311,6 +354,7 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const __grid_consta
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_wt);
+    if (F32) ptx::prefetch_tensormap(&tmap_wt2);
     (void)tmap_gx;
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(&full_a[s], ptx::arrivals(GI_GATHER_THREADS));
@@ -348,8 +392,9 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const __grid_consta
         const int c0 = nt * BN;
         for (int kb = 0; kb < prm.kblocks; ++kb) {
           ptx::mbar_wait_relaxed(&empty[s], ph ^ 1, 64);
-          ptx::mbar_arrive_expect_tx(&full_b[s], (uint32_t)BN * 128u);
+          ptx::mbar_arrive_expect_tx(&full_b[s], (uint32_t)BN * 128u * (F32 ? 2u : 1u));
           ptx::tma_load_2d(sB + s * GI_B_BYTES, &tmap_wt, &full_b[s], kb * 64, c0);
+          if (F32) ptx::tma_load_2d(sB + s * GI_B_BYTES + GI_B_BYTES / 2, &tmap_wt2, &full_b[s], kb * 64, c0);   // lo halves
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -357,7 +402,7 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const __grid_consta
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = ptx::umma_idesc_f16(umma_fmt<T>(), 0, 0, GI_BM, BN);
+      const uint32_t idesc = ptx::umma_idesc_f16(F32 ? 1 : umma_fmt<T>(), 0, 0, GI_BM, BN);
       int s = 0;
       uint32_t ph = 0;
       int as = 0;
@@ -370,13 +415,19 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const __grid_consta
           ptx::mbar_wait(&full_b[s], ph);
           ptx::mbar_wait(&full_a[s], ph);
           ptx::tc_fence_after_sync();
-          const uint32_t a_addr = ptx::smem_u32(sA + s * GI_A_BYTES);
+          const uint32_t a_addr = ptx::smem_u32(sA + s * A_STAGE);
           const uint32_t b_addr = ptx::smem_u32(sB + s * GI_B_BYTES);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint64_t ad = ptx::umma_smem_desc_sw128(a_addr + k * 32, 0, 1024);
             const uint64_t bd = ptx::umma_smem_desc_sw128(b_addr + k * 32, 0, 1024);
             ptx::umma_f16(d_tmem, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if (F32) {   // + hi*lo + lo*hi
+              const uint64_t al = ptx::umma_smem_desc_sw128(a_addr + GI_A_BYTES + k * 32, 0, 1024);
+              const uint64_t bl = ptx::umma_smem_desc_sw128(b_addr + GI_B_BYTES / 2 + k * 32, 0, 1024);
+              ptx::umma_f16(d_tmem, ad, bl, idesc, 1u);
+              ptx::umma_f16(d_tmem, al, bd, idesc, 1u);
+            }
           }
           ptx::umma_commit(&empty[s]);
           if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -475,7 +526,7 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const __grid_consta
           const long long nb = bin0 + (long long)(tap + 2) * g.IN;
           n_lo = __ldg(bin_start + nb); n_hi = __ldg(bin_start + nb + 1);
         }
-        GiPlanRow r;
+        PlanRow r;
 #pragma unroll
         for (int i = 0; i < GI_NE; ++i) { r.idx[i] = 0u; r.w[i] = 0; }
         r.n = n;
@@ -484,16 +535,20 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const __grid_consta
         for (int i = 0; i < GI_NE; ++i) {
           if (i < n) {
             const int2 ev = __ldg(entries2 + e0 + i);
-            r.idx[i] = (uint32_t)ev.x * (uint32_t)(g.Co * 2);
-            const T wt = cvt_to<T, float>(__int_as_float(ev.y));
-            r.w[i] = *reinterpret_cast<const uint16_t*>(&wt);
+            r.idx[i] = (uint32_t)ev.x * (uint32_t)(g.Co * sizeof(T));
+            if constexpr (F32) {
+              r.w[i] = __int_as_float(ev.y);
+            } else {
+              const T wt = cvt_to<T, float>(__int_as_float(ev.y));
+              r.w[i] = *reinterpret_cast<const uint16_t*>(&wt);
+            }
           }
         }
         ptx::mbar_wait_relaxed(&plan_empty[ps], pph ^ 1, 128);
         const uint32_t pa = ptx::smem_u32(sPlan + ps * GI_BM + row);
         const uint4* q = reinterpret_cast<const uint4*>(&r);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) sts128(pa + 16 * i, q[i]);
+        for (int i = 0; i < (int)(sizeof(PlanRow) / 16); ++i) sts128(pa + 16 * i, q[i]);
         ptx::mbar_arrive_warp(&plan_full[ps]);
         if (++ps == GI_PLAN_SLOTS) { ps = 0; pph ^= 1; }
       }
@@ -521,12 +576,65 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const __grid_consta
         const uint32_t plan_addr = ptx::smem_u32(sPlan + ps * GI_BM + row0);
         // byte address of this lane's 8 channels in row 0 of output-channel block 0; entries add a 32-bit
         // row offset, every further block 128 bytes
-        const char* gcb = reinterpret_cast<const char*>(gq + ((grp * g.Cog) >> 3) + chunk);
+        const char* gcb = reinterpret_cast<const char*>(prm.got) + ((size_t)grp * g.Cog + chunk * 8) * sizeof(T);
+        if constexpr (F32) {
+          // fp32: per (output-channel block, pass) the bin head's rows are loaded (2 x 16 bytes = 8 channels each),
+          // accumulated in fp32, split into bf16 hi / lo and stored into the two A tiles; no ping-pong (the loads of
+          // one pass already fill the registers)
+          for (int cob = 0; cob < prm.cobs; ++cob) {
+            ptx::mbar_wait(&empty[s], ph ^ 1);
+            const uint32_t a_addr = ptx::smem_u32(sA + s * A_STAGE);
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+              const uint32_t pa = plan_addr + pass * 4 * (uint32_t)sizeof(PlanRow);
+              const uint4 i0 = lds128(pa), i1 = lds128(pa + 16), w0 = lds128(pa + 32), w1 = lds128(pa + 48),
+                          meta = lds128(pa + 64);
+              const uint32_t idx[GI_NE] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+              const uint32_t wb[GI_NE] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+              const int n = (int)meta.x;
+              uint4 va[GI_NE], vb[GI_NE];
+#pragma unroll
+              for (int i = 0; i < GI_NE; ++i)
+                if (i < n) {
+                  va[i] = __ldg(reinterpret_cast<const uint4*>(gcb + idx[i]));
+                  vb[i] = __ldg(reinterpret_cast<const uint4*>(gcb + idx[i]) + 1);
+                }
+              float acc[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+              auto fma8 = [&](const uint4& a, const uint4& b, float w) {
+                acc[0] = fmaf(w, __uint_as_float(a.x), acc[0]); acc[1] = fmaf(w, __uint_as_float(a.y), acc[1]);
+                acc[2] = fmaf(w, __uint_as_float(a.z), acc[2]); acc[3] = fmaf(w, __uint_as_float(a.w), acc[3]);
+                acc[4] = fmaf(w, __uint_as_float(b.x), acc[4]); acc[5] = fmaf(w, __uint_as_float(b.y), acc[5]);
+                acc[6] = fmaf(w, __uint_as_float(b.z), acc[6]); acc[7] = fmaf(w, __uint_as_float(b.w), acc[7]);
+              };
+#pragma unroll
+              for (int i = 0; i < GI_NE; ++i)
+                if (i < n) fma8(va[i], vb[i], __uint_as_float(wb[i]));
+              for (int e = GI_NE; e < n; ++e) {   // bins longer than the staged head
+                const int2 ee = __ldg(entries2 + (int)meta.y + e);
+                const uint4* src = reinterpret_cast<const uint4*>(gcb + (size_t)ee.x * (size_t)(g.Co * sizeof(T)));
+                fma8(__ldg(src), __ldg(src + 1), __int_as_float(ee.y));
+              }
+              uint4 hi, lo;
+              gi_split8(acc, hi, lo);
+              sts128(a_addr + sw128(row0 + pass * 4, chunk), hi);
+              sts128(a_addr + GI_A_BYTES + sw128(row0 + pass * 4, chunk), lo);
+            }
+            ptx::fence_proxy_async_smem();
+            ptx::mbar_arrive_warp(&full_a[s]);
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+            gcb += 64 * sizeof(T);
+          }
+          ptx::mbar_arrive_warp(&plan_empty[ps]);
+          if (++ps == GI_PLAN_SLOTS) { ps = 0; pph ^= 1; }
+          continue;
+        }
         uint4 va[GI_NE], vb[GI_NE];
         // the row offsets are re-read from the plan row at every issue (two LDS.128) rather than held for the
         // tap: two load buffers + both passes' offsets do not fit the gather warps' registers
         auto issue = [&](uint4 (&v)[GI_NE], int pass, const char* base) {
-          const uint32_t pa = plan_addr + pass * 4 * (uint32_t)sizeof(GiPlanRow);
+          const uint32_t pa = plan_addr + pass * 4 * (uint32_t)sizeof(PlanRow);
           const uint4 i0 = lds128(pa), i1 = lds128(pa + 16), meta = lds128(pa + 48);
           const uint32_t idx[GI_NE] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
           const int n = (int)meta.x;
@@ -535,7 +643,7 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const __grid_consta
             if (i < n) v[i] = __ldg(reinterpret_cast<const uint4*>(base + idx[i]));
         };
         auto finish = [&](const uint4 (&v)[GI_NE], int pass, const char* base, uint32_t a_addr) {
-          const uint32_t pa = plan_addr + pass * 4 * (uint32_t)sizeof(GiPlanRow);
+          const uint32_t pa = plan_addr + pass * 4 * (uint32_t)sizeof(PlanRow);
           const uint4 wv = lds128(pa + 32), meta = lds128(pa + 48);
           const T* wh = reinterpret_cast<const T*>(&wv);
           const int n = (int)meta.x;
@@ -555,7 +663,7 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const __grid_consta
         for (int cob = 0; cob < prm.cobs; ++cob) {
           issue(vb, 1, gcb);
           ptx::mbar_wait(&empty[s], ph ^ 1);
-          const uint32_t a_addr = ptx::smem_u32(sA + s * GI_A_BYTES);
+          const uint32_t a_addr = ptx::smem_u32(sA + s * A_STAGE);
           finish(va, 0, gcb, a_addr);
           if (cob + 1 < prm.cobs) issue(va, 0, gcb + 128);
           finish(vb, 1, gcb, a_addr);
@@ -590,24 +698,43 @@ __global__ void k_transpose_weight(const T* __restrict__ w, T* __restrict__ wt, 
   }
 }
 
+// fp32 filters: the same transposition, split into bf16 hi / lo banks
+__global__ void k_transpose_weight_split(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
+                                         __nv_bfloat16* __restrict__ lo, int Co, int Cg, int Cog, int K) {
+  const size_t n = (size_t)Co * Cg * K;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int KC = K * Cog;
+    const int c = (int)(i / KC);
+    const int r = (int)(i % KC);
+    const int tap = r / Cog, col = r - tap * Cog;
+    const int grp = c / Cg, cl = c - grp * Cg;
+    const float v = w[((size_t)(grp * Cog + col) * Cg + cl) * K + tap];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+template <typename T>
 size_t smem_bytes_gi(int stages) {
-  return 1024 + (size_t)stages * (GI_A_BYTES + GI_B_BYTES) + (size_t)GI_PLAN_SLOTS * GI_BM * sizeof(GiPlanRow) +
+  return 1024 + (size_t)stages * (GiCfg<T>::A_STAGE + GI_B_BYTES) +
+         (size_t)GI_PLAN_SLOTS * GI_BM * sizeof(typename GiCfg<T>::Row) +
          (3 * stages + 2 * GI_PLAN_SLOTS + 4) * sizeof(uint64_t) + 16;
 }
 
 template <typename T, bool CL, int STAGES>
-void launch_grad_input(const CUtensorMap& tmap, const CUtensorMap& tmap_gx, const TcGiParams& prm, int grid,
-                       LaunchCtx& ctx) {
-  const size_t smem = smem_bytes_gi(STAGES);
+void launch_grad_input(const CUtensorMap& tmap, const CUtensorMap& tmap_gx, const CUtensorMap& tmap2,
+                       const TcGiParams& prm, int grid, LaunchCtx& ctx) {
+  const size_t smem = smem_bytes_gi<T>(STAGES);
   static std::atomic<unsigned long long> configured{0};
   opt_in_dynamic_smem(k_tc_grad_input<T, CL, STAGES>, smem, configured, ctx);
   ProfScope prof(ctx, "tc_grad_input");
-  k_tc_grad_input<T, CL, STAGES><<<grid, GI_THREADS, smem, ctx.stream>>>(tmap, tmap_gx, prm);
+  k_tc_grad_input<T, CL, STAGES><<<grid, GI_THREADS, smem, ctx.stream>>>(tmap, tmap_gx, tmap2, prm);
   MDCONV_CHECK_LAUNCH(ctx);
 }
 
 int pick_bn_gi(const DevGeom& g) {
-  int bn = GI_MAX_BN;
+  int bn = g.esize == 4 ? GiCfg<float>::MAX_BN_T : GI_MAX_BN;
   while (bn > 64 && (g.Cg % bn != 0 || g.Cdg % bn != 0)) bn >>= 1;
   return bn;
 }
@@ -676,16 +803,18 @@ void build_bins(const DevGeom& g, const void* off, const void* mask, char* ws, c
 bool grad_input_supported(const DevGeom& g) {
   if (g.Cog % 64 != 0 || g.Cg % 64 != 0 || g.Cdg % 64 != 0 || g.Co % 8 != 0) return false;
   if (num_bins(g) + 1 > 2147483647ULL || max_entries(g) > 2147483647ULL) return false;
-  if ((long long)g.B * g.P * g.Co * 2 > 4294967295LL) return false;  // 32-bit byte offsets into grad_output
+  if ((long long)g.B * g.P * g.Co * g.esize > 4294967295LL) return false;  // 32-bit byte offsets into grad_output
   return true;
 }
 
 // channels-last copy of grad_output (NCHW callers only: channels-last callers' grad_output is gathered in place)
-static size_t got_bytes(const DevGeom& g) { return g.cl ? 0 : align256((size_t)g.B * g.Co * g.P * 2); }
+static size_t got_bytes(const DevGeom& g) { return g.cl ? 0 : align256((size_t)g.B * g.Co * g.P * g.esize); }
+// transposed filter bank(s): one 16-bit bank, or bf16 hi + lo for fp32 callers
+static size_t wt_bytes(const DevGeom& g) { return align256((size_t)g.Co * g.Kg * 2) * (g.esize == 4 ? 2 : 1); }
 
 size_t grad_input_workspace(const DevGeom& g) {
   // channels-last grad_output + transposed weight + inverse index
-  return got_bytes(g) + align256((size_t)g.Co * g.Kg * 2) + gi_layout(g).total;
+  return got_bytes(g) + wt_bytes(g) + gi_layout(g).total;
 }
 
 // Stage 1 (can be issued early): the inverse index, on the side stream when there is one.  Returns with
@@ -694,7 +823,7 @@ template <typename T>
 void tensor_grad_input_prepare(const DevGeom& g, const void* off, const void* mask, void* ws, LaunchCtx& ctx) {
   char* base = reinterpret_cast<char*>(ws);
   base += got_bytes(g);
-  base += align256((size_t)g.Co * g.Kg * sizeof(T));
+  base += wt_bytes(g);
   const GiLayout L = gi_layout(g);
   // no fork while the caller's stream is being captured into a CUDA graph: the whole call then stays on that stream
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -725,8 +854,10 @@ void tensor_grad_input(const DevGeom& g, const void* w, const void* go, void* gx
   char* base = reinterpret_cast<char*>(ws);
   const T* got = g.cl ? reinterpret_cast<const T*>(go) : reinterpret_cast<const T*>(base);
   base += got_bytes(g);
-  T* wt = reinterpret_cast<T*>(base);
-  base += align256((size_t)g.Co * g.Kg * sizeof(T));
+  constexpr bool F32 = std::is_same<T, float>::value;
+  using E = typename std::conditional<F32, __nv_bfloat16, T>::type;   // element type of the filter bank(s)
+  char* wt = base;
+  base += wt_bytes(g);
   const GiLayout L = gi_layout(g);
 
   if (!g.cl) launch_to_channels_last<T>((const T*)go, const_cast<T*>(got), g.B, g.Co, g.P, ctx);
@@ -734,7 +865,12 @@ void tensor_grad_input(const DevGeom& g, const void* w, const void* go, void* gx
     ProfScope prof(ctx, "transpose_weight");
     const size_t n = (size_t)g.Co * g.Kg;
     const int blocks = (int)((n + 255) / 256 > 1184 ? 1184 : (n + 255) / 256);
-    k_transpose_weight<T><<<blocks, 256, 0, ctx.stream>>>((const T*)w, wt, g.Co, g.Cg, g.Cog, g.K);
+    if constexpr (F32)
+      k_transpose_weight_split<<<blocks, 256, 0, ctx.stream>>>(
+          (const float*)w, reinterpret_cast<__nv_bfloat16*>(wt), reinterpret_cast<__nv_bfloat16*>(wt + wt_bytes(g) / 2),
+          g.Co, g.Cg, g.Cog, g.K);
+    else
+      k_transpose_weight<T><<<blocks, 256, 0, ctx.stream>>>((const T*)w, reinterpret_cast<T*>(wt), g.Co, g.Cg, g.Cog, g.K);
     MDCONV_CHECK_LAUNCH(ctx);
   }
   if (ctx.side_join != nullptr) {   // inverse index is ready
@@ -761,35 +897,43 @@ void tensor_grad_input(const DevGeom& g, const void* w, const void* go, void* gx
     if (ctx.err == cudaSuccess) ctx.err = cudaErrorNotSupported;
     return;
   }
-  CUtensorMap tmap;
+  CUtensorMap tmap, tmap2, tmap_gx;
+  memset(&tmap2, 0, sizeof(tmap2));
+  memset(&tmap_gx, 0, sizeof(tmap_gx));
   const cuuint64_t dims[2] = {(cuuint64_t)g.K * g.Cog, (cuuint64_t)g.C};
-  const cuuint64_t strides[1] = {(cuuint64_t)g.K * g.Cog * sizeof(T)};
+  const cuuint64_t strides[1] = {(cuuint64_t)g.K * g.Cog * sizeof(E)};
   const cuuint32_t box[2] = {64, (cuuint32_t)prm.BN};
   const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = enc(&tmap, tmap_dtype<T>(), 2, wt, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(&tmap, tmap_dtype<E>(), 2, wt, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_SUCCESS && F32)
+    r = enc(&tmap2, tmap_dtype<E>(), 2, wt + wt_bytes(g) / 2, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    if (ctx.err == cudaSuccess) ctx.err = cudaErrorInvalidValue;
-    return;
-  }
-  CUtensorMap tmap_gx;
-  memset(&tmap_gx, 0, sizeof(tmap_gx));
-  if (g.cl && !encode_rows_by_channels<T>(&tmap_gx, gx, (size_t)g.B * g.IN, g.C)) {
     if (ctx.err == cudaSuccess) ctx.err = cudaErrorInvalidValue;
     return;
   }
   const int sms = sm_count() - ctx.spare_sms > 0 ? sm_count() - ctx.spare_sms : 1;
   const int grid = prm.total_tiles < sms ? prm.total_tiles : sms;
-  if (g.nd == 3) {
-    if (g.cl) launch_grad_input<T, true, 2>(tmap, tmap_gx, prm, grid, ctx);
-    else launch_grad_input<T, false, 2>(tmap, tmap_gx, prm, grid, ctx);
+  if constexpr (F32) {
+    launch_grad_input<T, false, 2>(tmap, tmap_gx, tmap2, prm, grid, ctx);
   } else {
-    if (g.cl) launch_grad_input<T, true, GI_STAGES>(tmap, tmap_gx, prm, grid, ctx);
-    else launch_grad_input<T, false, GI_STAGES>(tmap, tmap_gx, prm, grid, ctx);
+    if (g.cl && !encode_rows_by_channels<T>(&tmap_gx, gx, (size_t)g.B * g.IN, g.C)) {
+      if (ctx.err == cudaSuccess) ctx.err = cudaErrorInvalidValue;
+      return;
+    }
+    if (g.nd == 3) {
+      if (g.cl) launch_grad_input<T, true, 2>(tmap, tmap_gx, tmap2, prm, grid, ctx);
+      else launch_grad_input<T, false, 2>(tmap, tmap_gx, tmap2, prm, grid, ctx);
+    } else {
+      if (g.cl) launch_grad_input<T, true, GI_STAGES>(tmap, tmap_gx, tmap2, prm, grid, ctx);
+      else launch_grad_input<T, false, GI_STAGES>(tmap, tmap_gx, tmap2, prm, grid, ctx);
+    }
   }
 }
 
+template void tensor_grad_input<float>(const DevGeom&, const void*, const void*, void*, void*, LaunchCtx&);
+template void tensor_grad_input_prepare<float>(const DevGeom&, const void*, const void*, void*, LaunchCtx&);
 template void tensor_grad_input<__half>(const DevGeom&, const void*, const void*, void*, void*, LaunchCtx&);
 template void tensor_grad_input<__nv_bfloat16>(const DevGeom&, const void*, const void*, void*, void*, LaunchCtx&);
 template void tensor_grad_input_prepare<__half>(const DevGeom&, const void*, const void*, void*, LaunchCtx&);

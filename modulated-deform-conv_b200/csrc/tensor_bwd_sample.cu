@@ -62,6 +62,23 @@ template <int ND> struct GsRegs {
   static_assert(128 * (CTL + MOVER) + GS_DOT_THREADS * DOT <= GS_THREADS * 80, "setmaxnreg.inc would wait forever");
 };
 
+// fp32 callers: split bf16 operands (hi / lo grad_output tiles and filter slices, three products per K step, see
+// tensor_path.cu FwdCfg); the accumulator goes to shared memory as fp32 (a [128 x 64] block is 32 KB) and the dot
+// products against the fp32 corner values run in fp32.
+template <typename T> struct GsCfg {
+  static constexpr bool F32 = false;
+  static constexpr int A_STAGE = GS_A_BYTES, T_BYTES = GS_T_BYTES, MAX_NB = 4;
+};
+template <> struct GsCfg<float> {
+  static constexpr bool F32 = true;
+  static constexpr int A_STAGE = 2 * GS_A_BYTES, T_BYTES = 2 * GS_T_BYTES, MAX_NB = 2;   // B stage: hi blocks, then lo
+};
+// byte offset of 16-byte chunk `c` (0..15) of row `row` in an fp32 T block: 256-byte rows, each 128-byte half
+// swizzled like sw128
+__device__ __forceinline__ uint32_t t32_off(int row, int c) {
+  return (uint32_t)(row * 256 + ((c & 8) << 4) + (((c & 7) ^ (row & 7)) << 4));
+}
+
 // Offset / mask slab ring (north_star: "TMA bulk loads of ... offset/mask slabs into shared memory"): per work item
 // (128-position tile = two 64-position blocks, one tap) the ND offset rows and the mask row of each block arrive by
 // cp.async.bulk.tensor straight from the caller's NCHW tensors, OM_SLOTS items ahead of the movers, so the sampling
@@ -116,8 +133,11 @@ __device__ __forceinline__ float dot8(const uint4& a, const uint4& b, __nv_bfloa
   const float2 f = __bfloat1622float2(p);
   return f.x + f.y;
 }
+__device__ __forceinline__ float cvt_from_storage(float v) { return v; }
 __device__ __forceinline__ float cvt_from_storage(__half v) { return __half2float(v); }
 __device__ __forceinline__ float cvt_from_storage(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float dot8(const uint4&, const uint4&, float) { return 0.f; }        // (16-bit paths only)
+__device__ __forceinline__ uint32_t pack2(float, float, float) { return 0u; }                   // (16-bit paths only)
 __device__ __forceinline__ uint32_t pack2(float a, float b, __half) {
   const __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
@@ -131,14 +151,18 @@ template <typename T, int ND, bool MOD>
 __global__ void __launch_bounds__(GS_THREADS, 1)
 k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ CUtensorMap tmap_mask,
+                 const __grid_constant__ CUtensorMap tmap_go2, const __grid_constant__ CUtensorMap tmap_w2,
                  const TcGsParams prm) {
   constexpr int NC = 1 << ND;
+  constexpr bool F32 = GsCfg<T>::F32;
+  constexpr int A_STAGE = GsCfg<T>::A_STAGE;
+  constexpr int T_BYTES = GsCfg<T>::T_BYTES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
-  uint8_t* sB = sA + GS_STAGES * GS_A_BYTES;
+  uint8_t* sB = sA + GS_STAGES * A_STAGE;
   uint8_t* sT = sB + GS_STAGES * GS_B_BYTES;
-  SampleEntry<ND>* sPlan = reinterpret_cast<SampleEntry<ND>*>(sT + 2 * GS_T_BYTES);
+  SampleEntry<ND>* sPlan = reinterpret_cast<SampleEntry<ND>*>(sT + 2 * T_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sPlan) + 2 * 128 * sizeof(SampleEntry<ND>));
   uint64_t* full = bars;                    // [GS_STAGES]  TMA -> MMA
   uint64_t* empty = full + GS_STAGES;       // [GS_STAGES]  MMA -> TMA
@@ -160,6 +184,7 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_go);
     ptx::prefetch_tensormap(&tmap_w);
+    if (F32) { ptx::prefetch_tensormap(&tmap_go2); ptx::prefetch_tensormap(&tmap_w2); }
     for (int s = 0; s < GS_STAGES; ++s) {
       ptx::mbar_init(&full[s], 1);
       ptx::mbar_init(&empty[s], 1);
@@ -229,13 +254,21 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
             for (int kb = 0; kb < prm.kblocks; ++kb) {
               const int co0 = grp * g.Cog + kb * GS_KCO;
               ptx::mbar_wait(&empty[s], ph ^ 1);
-              ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)(GS_A_BYTES + nb * GS_KCO * 128));
+              ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)(GS_A_BYTES + nb * GS_KCO * 128) * (F32 ? 2u : 1u));
 #pragma unroll
-              for (int h = 0; h < 2; ++h)
-                ptx::tma_load_3d(sA + s * GS_A_BYTES + h * (GS_KCO * 128), &tmap_go, &full[s], pb_p0[h], co0, pb_b[h]);
-              for (int j = 0; j < nb; ++j)
+              for (int h = 0; h < 2; ++h) {
+                ptx::tma_load_3d(sA + s * A_STAGE + h * (GS_KCO * 128), &tmap_go, &full[s], pb_p0[h], co0, pb_b[h]);
+                if (F32)
+                  ptx::tma_load_3d(sA + s * A_STAGE + GS_A_BYTES + h * (GS_KCO * 128), &tmap_go2, &full[s], pb_p0[h], co0,
+                                   pb_b[h]);
+              }
+              for (int j = 0; j < nb; ++j) {
                 ptx::tma_load_2d(sB + s * GS_B_BYTES + j * (GS_KCO * 128), &tmap_w, &full[s],
                                  ((ccl0 + j) * g.K + tap) * 64, co0);
+                if (F32)
+                  ptx::tma_load_2d(sB + s * GS_B_BYTES + GS_B_BYTES / 2 + j * (GS_KCO * 128), &tmap_w2, &full[s],
+                                   ((ccl0 + j) * g.K + tap) * 64, co0);
+              }
               if (++s == GS_STAGES) { s = 0; ph ^= 1; }
             }
           }
@@ -246,7 +279,7 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = ptx::umma_idesc_f16(umma_fmt<T>(), /*A MN-major*/ 1, /*B MN-major*/ 1, 128, nb * 64);
+      const uint32_t idesc = ptx::umma_idesc_f16(F32 ? 1 : umma_fmt<T>(), /*A MN-major*/ 1, /*B MN-major*/ 1, 128, nb * 64);
       int s = 0;
       uint32_t ph = 0;
       int as = 0;
@@ -259,13 +292,19 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
           for (int kb = 0; kb < prm.kblocks; ++kb) {
             ptx::mbar_wait(&full[s], ph);
             ptx::tc_fence_after_sync();
-            const uint32_t a_addr = ptx::smem_u32(sA + s * GS_A_BYTES);
+            const uint32_t a_addr = ptx::smem_u32(sA + s * A_STAGE);
             const uint32_t b_addr = ptx::smem_u32(sB + s * GS_B_BYTES);
 #pragma unroll
             for (int k = 0; k < GS_KCO / 16; ++k) {  // 16 output channels per MMA
               const uint64_t ad = ptx::umma_smem_desc_sw128(a_addr + k * 2048, GS_KCO * 128, 1024);
               const uint64_t bd = ptx::umma_smem_desc_sw128(b_addr + k * 2048, GS_KCO * 128, 1024);
               ptx::umma_f16(d_tmem, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              if (F32) {   // + hi*lo + lo*hi
+                const uint64_t al = ptx::umma_smem_desc_sw128(a_addr + GS_A_BYTES + k * 2048, GS_KCO * 128, 1024);
+                const uint64_t bl = ptx::umma_smem_desc_sw128(b_addr + GS_B_BYTES / 2 + k * 2048, GS_KCO * 128, 1024);
+                ptx::umma_f16(d_tmem, ad, bl, idesc, 1u);
+                ptx::umma_f16(d_tmem, al, bd, idesc, 1u);
+              }
             }
             ptx::umma_commit(&empty[s]);
             if (++s == GS_STAGES) { s = 0; ph ^= 1; }
@@ -306,7 +345,7 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
     const int row = threadIdx.x - 128;  // TMEM lane == tile row
     const T* __restrict__ off = reinterpret_cast<const T*>(prm.off);
     const T* __restrict__ mask = reinterpret_cast<const T*>(prm.mask);
-    const int C8 = g.C >> 3;
+    const int C8 = F32 ? g.C >> 2 : g.C >> 3;   // 16-byte vectors per position
     const bool rule_b = g.rule != 0;
     int as = 0, ts = 0, ps = 0, os = 0;
     uint32_t aph = 0, tph = 0, pph = 0, oph = 0;
@@ -390,12 +429,18 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
           const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(as * 256);
           for (int j = 0; j < nb; ++j) {
             ptx::mbar_wait(&t_empty[ts], tph ^ 1);
-            const uint32_t tb = ptx::smem_u32(sT + ts * GS_T_BYTES);
+            const uint32_t tb = ptx::smem_u32(sT + ts * T_BYTES);
 #pragma unroll
             for (int hlf = 0; hlf < 2; ++hlf) {
               uint32_t v[32];
               ptx::tmem_ld_32x32(taddr + j * 64 + hlf * 32, v);
               ptx::tmem_ld_wait();
+              if constexpr (F32) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q)   // 4 channels = one 16-byte chunk, kept in fp32
+                  sts128(tb + t32_off(row, hlf * 8 + q), make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+                continue;
+              }
 #pragma unroll
               for (int q = 0; q < 4; ++q) {  // 8 channels = one 16-byte chunk
                 uint4 o;
@@ -455,6 +500,45 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
         // run, the corner loads of the NEXT step are in flight (two register buffers; the corner values do not
         // depend on the accumulator, only their use waits for the T tile).
         const int nblk = nsub * nb;   // 64-channel blocks of this (deformable group, tap)
+        if constexpr (F32) {
+          // fp32: this lane's 8 channels are two 16-byte vectors of the fp32 input and of the fp32 accumulator block;
+          // per block and row: corner loads (4 corners at a time), wait for the block, fp32 dot products
+          for (int blk = 0; blk < nblk; ++blk) {
+            const uint4* xc = xq + (((dgi * bpd + blk) * 64) >> 2) + 2 * j;
+            bool waited = false;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+#pragma unroll
+              for (int c4 = 0; c4 < NC; c4 += 4) {
+                uint4 xa[4], xb[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  const int id = idx[i][c4 + c];
+                  xa[c] = id >= 0 ? __ldg(xc + id) : make_uint4(0u, 0u, 0u, 0u);
+                  xb[c] = id >= 0 ? __ldg(xc + id + 1) : make_uint4(0u, 0u, 0u, 0u);
+                }
+                if (!waited) { ptx::mbar_wait(&t_full[ts], tph); waited = true; }
+                const uint32_t tb = ptx::smem_u32(sT + ts * T_BYTES);
+                const uint4 g0 = lds128(tb + t32_off(row0 + 4 * i, 2 * j));
+                const uint4 g1 = lds128(tb + t32_off(row0 + 4 * i, 2 * j + 1));
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  float d = __uint_as_float(g0.x) * __uint_as_float(xa[c].x);
+                  d = fmaf(__uint_as_float(g0.y), __uint_as_float(xa[c].y), d);
+                  d = fmaf(__uint_as_float(g0.z), __uint_as_float(xa[c].z), d);
+                  d = fmaf(__uint_as_float(g0.w), __uint_as_float(xa[c].w), d);
+                  d = fmaf(__uint_as_float(g1.x), __uint_as_float(xb[c].x), d);
+                  d = fmaf(__uint_as_float(g1.y), __uint_as_float(xb[c].y), d);
+                  d = fmaf(__uint_as_float(g1.z), __uint_as_float(xb[c].z), d);
+                  d = fmaf(__uint_as_float(g1.w), __uint_as_float(xb[c].w), d);
+                  S[i][c4 + c] += d;
+                }
+              }
+            }
+            ptx::mbar_arrive_warp(&t_empty[ts]);
+            if (++ts == 2) { ts = 0; tph ^= 1; }
+          }
+        }
         auto load_row = [&](int blk, int i, uint4 (&v)[NC]) {
           const uint4* xc = xq + (((dgi * bpd + blk) * 64) >> 3) + j;
 #pragma unroll
@@ -463,13 +547,15 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
 #ifndef MDCONV_GS_ROLL3D
 #define MDCONV_GS_ROLL3D 0
 #endif
-        if constexpr (ND == 2 || MDCONV_GS_ROLL3D) {
+        if constexpr (F32) {
+          // (handled above)
+        } else if constexpr (ND == 2 || MDCONV_GS_ROLL3D) {
           uint4 va[NC], vb[NC];
           load_row(0, 0, va);
           for (int blk = 0; blk < nblk; ++blk) {
             load_row(blk, 1, vb);
             ptx::mbar_wait(&t_full[ts], tph);
-            const uint32_t tb = ptx::smem_u32(sT + ts * GS_T_BYTES);
+            const uint32_t tb = ptx::smem_u32(sT + ts * T_BYTES);
             {
               const uint4 gc = lds128(tb + sw128(row0, j));
 #pragma unroll
@@ -492,7 +578,7 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
             load_row(blk, 0, xv[0]);
             load_row(blk, 1, xv[1]);
             ptx::mbar_wait(&t_full[ts], tph);
-            const uint32_t tb = ptx::smem_u32(sT + ts * GS_T_BYTES);
+            const uint32_t tb = ptx::smem_u32(sT + ts * T_BYTES);
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
               const uint4 gc = lds128(tb + sw128(row0 + 4 * i, j));
@@ -579,22 +665,25 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
   if (warp == 2) ptx::tmem_dealloc<512>(tmem_base);
 }
 
-template <int ND>
+template <typename T, int ND>
 size_t gs_smem_bytes() {
-  return 1024 + (size_t)GS_STAGES * (GS_A_BYTES + GS_B_BYTES) + 2 * GS_T_BYTES + 2 * 128 * sizeof(SampleEntry<ND>) +
+  return 1024 + (size_t)GS_STAGES * (GsCfg<T>::A_STAGE + GS_B_BYTES) + 2 * GsCfg<T>::T_BYTES +
+         2 * 128 * sizeof(SampleEntry<ND>) +
          (2 * GS_STAGES + 12 + 2 * GS_OM_SLOTS) * sizeof(uint64_t) + 160 + (size_t)GS_OM_SLOTS * gs_om_slot_bytes<ND>();
 }
 
+struct GsMaps {
+  CUtensorMap go, w, off, mask, go2, w2;   // go2 / w2: the "lo" halves of fp32 callers
+};
 template <typename T, int ND, bool MOD>
-void launch_grad_sample(const CUtensorMap& tmap_go, const CUtensorMap& tmap_w, const CUtensorMap& tmap_off,
-                        const CUtensorMap& tmap_mask, const TcGsParams& prm, LaunchCtx& ctx) {
-  const size_t smem = gs_smem_bytes<ND>();
+void launch_grad_sample(const GsMaps& m, const TcGsParams& prm, LaunchCtx& ctx) {
+  const size_t smem = gs_smem_bytes<T, ND>();
   static std::atomic<unsigned long long> configured{0};
   opt_in_dynamic_smem(k_tc_grad_sample<T, ND, MOD>, smem, configured, ctx);
   const int sms = sm_count() - ctx.spare_sms > 0 ? sm_count() - ctx.spare_sms : 1;
   const int grid = prm.items < sms ? (int)prm.items : sms;
   ProfScope prof(ctx, "tc_grad_sample");
-  k_tc_grad_sample<T, ND, MOD><<<grid, GS_THREADS, smem, ctx.stream>>>(tmap_go, tmap_w, tmap_off, tmap_mask, prm);
+  k_tc_grad_sample<T, ND, MOD><<<grid, GS_THREADS, smem, ctx.stream>>>(m.go, m.w, m.off, m.mask, m.go2, m.w2, prm);
   MDCONV_CHECK_LAUNCH(ctx);
 }
 
@@ -604,16 +693,19 @@ bool grad_sample_supported(const DevGeom& g) {
   return g.Cog % GS_KCO == 0 && g.Cg % 64 == 0 && g.Cdg % 64 == 0;
 }
 
-// xt: channels-last input; wr: weight re-ordered to [Co][(channel-block, tap, 64 channels)]; go: grad_output rows
-// [B][Co][go_ld] (go_ld = P, or P rounded up to 8 elements for the padded copy).
+// xt: channels-last input; wr: weight re-ordered to [Co][(channel-block, tap, 64 channels)] (fp32 callers: the bf16
+// hi bank followed by the lo bank); go: grad_output rows [B][Co][go_ld] (go_ld = P, or P rounded up to 8 elements for
+// the padded copy; fp32 callers: the bf16 hi copy, go_lo the lo copy).
 template <typename T>
-void tensor_grad_sample(const DevGeom& g, const T* xt, const T* wr, const void* off, const void* mask, const void* go,
-                        int go_ld, void* goff, void* gmask, LaunchCtx& ctx) {
+void tensor_grad_sample(const DevGeom& g, const T* xt, const void* wr, const void* off, const void* mask, const void* go,
+                        const void* go_lo, int go_ld, void* goff, void* gmask, LaunchCtx& ctx) {
+  constexpr bool F32 = std::is_same<T, float>::value;
+  using E = typename std::conditional<F32, __nv_bfloat16, T>::type;   // element type of the TMA-read operands
   TcGsParams prm;
   prm.g = g;
   prm.xt = xt; prm.off = off; prm.mask = mask; prm.goff = goff; prm.gmask = gmask;
   const int bpd = g.Cdg / 64, bpg = g.Cg / 64;
-  int nb = 4;
+  int nb = GsCfg<T>::MAX_NB;
   while (nb > 1 && (bpd % nb != 0 || bpg % nb != 0)) nb >>= 1;
   prm.nb = nb;
   prm.nsub = bpd / nb;
@@ -628,69 +720,68 @@ void tensor_grad_sample(const DevGeom& g, const T* xt, const T* wr, const void* 
     if (ctx.err == cudaSuccess) ctx.err = cudaErrorNotSupported;
     return;
   }
-  CUtensorMap tmap_go, tmap_w;
-  {
+  GsMaps m;
+  memset(&m, 0, sizeof(m));
+  auto enc_go = [&](CUtensorMap* tm, const void* base) {
     const cuuint64_t dims[3] = {(cuuint64_t)g.P, (cuuint64_t)g.Co, (cuuint64_t)g.B};
-    const cuuint64_t strides[2] = {(cuuint64_t)go_ld * sizeof(T), (cuuint64_t)g.Co * go_ld * sizeof(T)};
+    const cuuint64_t strides[2] = {(cuuint64_t)go_ld * sizeof(E), (cuuint64_t)g.Co * go_ld * sizeof(E)};
     const cuuint32_t box[3] = {64, GS_KCO, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = enc(&tmap_go, tmap_dtype<T>(), 3, const_cast<void*>(go), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-      if (ctx.err == cudaSuccess) ctx.err = cudaErrorInvalidValue;
-      return;
-    }
-  }
-  {
+    return enc(tm, tmap_dtype<E>(), 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  };
+  auto enc_w = [&](CUtensorMap* tm, const void* base) {
     const cuuint64_t dims[2] = {(cuuint64_t)g.Kg, (cuuint64_t)g.Co};
-    const cuuint64_t strides[1] = {(cuuint64_t)g.Kg * sizeof(T)};
+    const cuuint64_t strides[1] = {(cuuint64_t)g.Kg * sizeof(E)};
     const cuuint32_t box[2] = {64, GS_KCO};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = enc(&tmap_w, tmap_dtype<T>(), 2, const_cast<T*>(wr), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-      if (ctx.err == cudaSuccess) ctx.err = cudaErrorInvalidValue;
-      return;
-    }
+    return enc(tm, tmap_dtype<E>(), 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  };
+  bool ok = enc_go(&m.go, go) && enc_w(&m.w, wr);
+  if (ok && F32) ok = enc_go(&m.go2, go_lo) && enc_w(&m.w2, reinterpret_cast<const char*>(wr) + wr_bytes(g) / 2);
+  if (!ok) {
+    if (ctx.err == cudaSuccess) ctx.err = cudaErrorInvalidValue;
+    return;
   }
   // offset [B][dg*K*nd][P] and mask [B][dg*K][P] as 3D maps, un-swizzled boxes of 64 positions x (nd | 1) channels
-  CUtensorMap tmap_off, tmap_mask;
-  memset(&tmap_off, 0, sizeof(tmap_off));
-  memset(&tmap_mask, 0, sizeof(tmap_mask));
-  prm.om_tma = (g.P % 8 == 0 && ((uintptr_t)off & 15) == 0 && (!g.modulated || ((uintptr_t)mask & 15) == 0)) ? 1 : 0;
+  // (16-bit callers with 16-byte row strides; everything else builds the sampling entries from global loads)
+  prm.om_tma = (!F32 && g.P % 8 == 0 && ((uintptr_t)off & 15) == 0 && (!g.modulated || ((uintptr_t)mask & 15) == 0)) ? 1 : 0;
   if (prm.om_tma) {
     const cuuint32_t estr[3] = {1, 1, 1};
     const cuuint64_t odims[3] = {(cuuint64_t)g.P, (cuuint64_t)g.dg * g.K * g.nd, (cuuint64_t)g.B};
     const cuuint64_t ostr[2] = {(cuuint64_t)g.P * sizeof(T), (cuuint64_t)g.dg * g.K * g.nd * g.P * sizeof(T)};
     const cuuint32_t obox[3] = {64, (cuuint32_t)g.nd, 1};
-    CUresult r = enc(&tmap_off, tmap_dtype<T>(), 3, const_cast<void*>(off), odims, ostr, obox, estr,
+    CUresult r = enc(&m.off, tmap_dtype<E>(), 3, const_cast<void*>(off), odims, ostr, obox, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r == CUDA_SUCCESS && g.modulated) {
       const cuuint64_t mdims[3] = {(cuuint64_t)g.P, (cuuint64_t)g.dg * g.K, (cuuint64_t)g.B};
       const cuuint64_t mstr[2] = {(cuuint64_t)g.P * sizeof(T), (cuuint64_t)g.dg * g.K * g.P * sizeof(T)};
       const cuuint32_t mbox[3] = {64, 1, 1};
-      r = enc(&tmap_mask, tmap_dtype<T>(), 3, const_cast<void*>(mask), mdims, mstr, mbox, estr,
+      r = enc(&m.mask, tmap_dtype<E>(), 3, const_cast<void*>(mask), mdims, mstr, mbox, estr,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }
     if (r != CUDA_SUCCESS) prm.om_tma = 0;   // fall back to global loads
   }
   if (g.nd == 2) {
-    if (g.modulated) launch_grad_sample<T, 2, true>(tmap_go, tmap_w, tmap_off, tmap_mask, prm, ctx);
-    else launch_grad_sample<T, 2, false>(tmap_go, tmap_w, tmap_off, tmap_mask, prm, ctx);
+    if (g.modulated) launch_grad_sample<T, 2, true>(m, prm, ctx);
+    else launch_grad_sample<T, 2, false>(m, prm, ctx);
   } else {
-    if (g.modulated) launch_grad_sample<T, 3, true>(tmap_go, tmap_w, tmap_off, tmap_mask, prm, ctx);
-    else launch_grad_sample<T, 3, false>(tmap_go, tmap_w, tmap_off, tmap_mask, prm, ctx);
+    if (g.modulated) launch_grad_sample<T, 3, true>(m, prm, ctx);
+    else launch_grad_sample<T, 3, false>(m, prm, ctx);
   }
 }
 
-template void tensor_grad_sample<__half>(const DevGeom&, const __half*, const __half*, const void*, const void*,
-                                         const void*, int, void*, void*, LaunchCtx&);
-template void tensor_grad_sample<__nv_bfloat16>(const DevGeom&, const __nv_bfloat16*, const __nv_bfloat16*,
+template void tensor_grad_sample<__half>(const DevGeom&, const __half*, const void*, const void*, const void*,
+                                         const void*, const void*, int, void*, void*, LaunchCtx&);
+template void tensor_grad_sample<__nv_bfloat16>(const DevGeom&, const __nv_bfloat16*, const void*, const void*,
                                                 const void*, const void*, const void*, int, void*, void*, LaunchCtx&);
+template void tensor_grad_sample<float>(const DevGeom&, const float*, const void*, const void*, const void*,
+                                        const void*, const void*, int, void*, void*, LaunchCtx&);
 
 }  // namespace tc
 }  // namespace mdconv
