@@ -116,6 +116,11 @@ __global__ void __launch_bounds__(256) k_bin_entries(const DevGeom g, const T* _
     SamplePos<ND> sp;
     sample_pos<T, ND, MOD>(g, off, mask, rc, dgi, tap, sp);
     if (!sp.in_range) continue;
+    // all corners first, then all atomics, then all stores: the 2^ND (atomic -> store) chains are independent and
+    // this keeps them in flight together (the fill pass is latency-bound: 8 returning atomics per thread in 3D)
+    size_t bin[1 << ND];
+    float wgt[1 << ND];
+    bool okc[1 << ND];
 #pragma unroll
     for (int c = 0; c < (1 << ND); ++c) {
       float w = sp.m;
@@ -131,16 +136,28 @@ __global__ void __launch_bounds__(256) k_bin_entries(const DevGeom g, const T* _
         w *= hi ? sp.fr[a] : (1.f - sp.fr[a]);
         pix = pix * g.in[a] + ia;
       }
-      if (!ok) continue;
-      const size_t bin = (((size_t)b * g.dg + dgi) * g.K + tap) * g.IN + pix;   // tap-major: neighbours in p hit neighbouring bins
-      if (!FILL) {
-        atomicAdd(count + bin, 1);
-      } else {
-        const int slot = start[bin] + atomicSub(count + bin, 1) - 1;
-        BinEntry e;
-        e.row = b * g.P + p;
-        e.w = w;
-        entries[slot] = e;
+      okc[c] = ok;
+      wgt[c] = w;
+      bin[c] = ok ? (((size_t)b * g.dg + dgi) * g.K + tap) * g.IN + pix : 0;   // tap-major: neighbours in p hit neighbouring bins
+    }
+    if (!FILL) {
+#pragma unroll
+      for (int c = 0; c < (1 << ND); ++c)
+        if (okc[c]) atomicAdd(count + bin[c], 1);
+    } else {
+      int slot[1 << ND];
+#pragma unroll
+      for (int c = 0; c < (1 << ND); ++c) slot[c] = okc[c] ? atomicSub(count + bin[c], 1) - 1 : 0;
+#pragma unroll
+      for (int c = 0; c < (1 << ND); ++c) slot[c] += okc[c] ? __ldg(start + bin[c]) : 0;
+#pragma unroll
+      for (int c = 0; c < (1 << ND); ++c) {
+        if (okc[c]) {
+          BinEntry e;
+          e.row = b * g.P + p;
+          e.w = wgt[c];
+          entries[slot[c]] = e;
+        }
       }
     }
   }

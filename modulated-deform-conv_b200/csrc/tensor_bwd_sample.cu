@@ -51,14 +51,9 @@ constexpr int GS_T_BYTES = 128 * 128;     // one [128 pos x 64 ch] block in the 
 // registers after setmaxnreg (the CTA owns GS_THREADS x 80): 3D gives the dot warps all it can (their two rows x 8
 // corner vectors are 64 registers on their own); 2D keeps the movers whole (their TMEM read + sampling entry spill
 // below 80) and hands the dot warps what the control warps free
-#ifndef MDCONV_GS3_CTL
-#define MDCONV_GS3_CTL 24
-#define MDCONV_GS3_MOVER 72
-#define MDCONV_GS3_DOT 96
-#endif
 template <int ND> struct GsRegs {
   static constexpr bool REBALANCE = ND == 3;   // 2D: every warp keeps its launch-time 80 (the split only costs there)
-  static constexpr uint32_t CTL = MDCONV_GS3_CTL, MOVER = MDCONV_GS3_MOVER, DOT = MDCONV_GS3_DOT;
+  static constexpr uint32_t CTL = 24, MOVER = 72, DOT = 96;   // measured at cfg4: 598 us (dot 88: 671 us)
   static_assert(128 * (CTL + MOVER) + GS_DOT_THREADS * DOT <= GS_THREADS * 80, "setmaxnreg.inc would wait forever");
 };
 
@@ -544,12 +539,9 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
 #pragma unroll
           for (int c = 0; c < NC; ++c) v[c] = idx[i][c] >= 0 ? __ldg(xc + idx[i][c]) : make_uint4(0u, 0u, 0u, 0u);
         };
-#ifndef MDCONV_GS_ROLL3D
-#define MDCONV_GS_ROLL3D 0
-#endif
         if constexpr (F32) {
           // (handled above)
-        } else if constexpr (ND == 2 || MDCONV_GS_ROLL3D) {
+        } else if constexpr (ND == 2) {
           uint4 va[NC], vb[NC];
           load_row(0, 0, va);
           for (int blk = 0; blk < nblk; ++blk) {
