@@ -48,9 +48,9 @@ constexpr int GS_KCO = 32;                // output channels per K-block
 constexpr int GS_A_BYTES = 2 * GS_KCO * 128;  // two [32 co x 64 pos] blocks
 constexpr int GS_B_BYTES = 4 * GS_KCO * 128;  // up to four [32 co x 64 kk] blocks
 constexpr int GS_T_BYTES = 128 * 128;     // one [128 pos x 64 ch] block in the storage dtype
-// registers after setmaxnreg (the CTA owns GS_THREADS x 80): 3D gives the dot warps all it can (their two rows x 8
-// corner vectors are 64 registers on their own); 2D keeps the movers whole (their TMEM read + sampling entry spill
-// below 80) and hands the dot warps what the control warps free
+// registers after setmaxnreg (the CTA owns GS_THREADS x 80).  3D: the dot warps get all there is (their two rows x 8
+// corner vectors are 64 registers on their own; at 80 they spill).  2D: nobody is short at 80, and the split costs
+// (control warps spill at 24, movers below 80): every warp keeps its launch-time registers.
 template <int ND> struct GsRegs {
   static constexpr bool REBALANCE = ND == 3;   // 2D: every warp keeps its launch-time 80 (the split only costs there)
   static constexpr uint32_t CTL = 24, MOVER = 72, DOT = 96;   // measured at cfg4: 598 us (dot 88: 671 us)
