@@ -29,6 +29,14 @@ inline size_t wr_bytes(const DevGeom& g) { return align256((size_t)g.Co * g.Kg *
 constexpr int CL_STAGE_BYTES = 128 * 128;
 
 // ---- explicit shared-state-space accesses (generic LD/ST through a computed pointer is slower) ----
+// `loaded & zero` (zero: a run-time 0) as ONE instruction the compiler can neither fold, duplicate nor sink into a branch:
+// the first read of a register some earlier load wrote, i.e. the place where the thread waits for that load's
+// scoreboard.  The result (0) is added to the addresses of whatever must not start before that wait.
+__device__ __forceinline__ uint32_t drain_point(uint32_t loaded, int zero) {
+  uint32_t r;
+  asm volatile("and.b32 %0, %1, %2;" : "=r"(r) : "r"(loaded), "r"(zero));
+  return r;
+}
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));

@@ -75,6 +75,7 @@ struct TcGwParams {
   int S;         // splits of the position reduction
   int pbi;       // 64-position blocks per image
   int total_pb;  // B * pbi
+  int zero;      // always 0 at run time (tc::drain_point)
 };
 
 template <typename T, int ND, bool MOD>
@@ -283,11 +284,11 @@ k_tc_grad_weight(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
     int s = 0, ips = 0, cps = 0;
     uint32_t ph = 0, ipph = 0;
 
-    auto issue = [&](uint4 (&v0)[NC], uint4 (&v1)[NC]) {
+    auto issue = [&](uint4 (&v0)[NC], uint4 (&v1)[NC], uint32_t after) {
       if constexpr (F32) return;
       ptx::mbar_wait(&plan_full[ips], ipph);
       if (active) {
-        const uint32_t pa = plan_row + ips * kSlotBytes;
+        const uint32_t pa = plan_row + ips * kSlotBytes + after;
         int i0[NC], i1[NC];
 #pragma unroll
         for (int q = 0; q < NC / 4; ++q) {
@@ -302,10 +303,10 @@ k_tc_grad_weight(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
       }
       if (++ips == GW_PLAN_SLOTS) { ips = 0; ipph ^= 1; }
     };
-    auto finish = [&](const uint4 (&v0)[NC], const uint4 (&v1)[NC]) {
+    auto finish = [&](const uint4 (&v0)[NC], const uint4 (&v1)[NC], uint32_t after = 0u) {
       ptx::mbar_wait(&empty[s], ph ^ 1);
       if (active) {
-        const uint32_t pa = plan_row + cps * kSlotBytes + 4 * NC;
+        const uint32_t pa = plan_row + cps * kSlotBytes + 4 * NC + after;
         uint32_t w0[NC], w1[NC];
 #pragma unroll
         for (int q = 0; q < NC / 4; ++q) {
@@ -378,19 +379,23 @@ k_tc_grad_weight(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
     } else if (ND == 2) {
       uint4 a0[NC], a1[NC], b0[NC], b1[NC];
       int pb = pb0;
-      if (pb < pb1) issue(a0, a1);
+      // wait for the block about to be interpolated BEFORE the next block's loads are issued: every LDG of the loop
+      // retires through one scoreboard (see the forward kernel's gather loop, tensor_path.cu)
+      if (pb < pb1) issue(a0, a1, 0u);
       while (pb < pb1) {
-        if (pb + 1 < pb1) issue(b0, b1);
-        finish(a0, a1);
+        const uint32_t da = tc::drain_point(a1[NC - 1].w, prm.zero);
+        if (pb + 1 < pb1) issue(b0, b1, da);
+        finish(a0, a1, da);
         if (++pb >= pb1) break;
-        if (pb + 1 < pb1) issue(a0, a1);
-        finish(b0, b1);
+        const uint32_t db = tc::drain_point(b1[NC - 1].w, prm.zero);
+        if (pb + 1 < pb1) issue(a0, a1, db);
+        finish(b0, b1, db);
         ++pb;
       }
     } else {
       uint4 a0[NC], a1[NC];
       for (int pb = pb0; pb < pb1; ++pb) {
-        issue(a0, a1);
+        issue(a0, a1, 0u);
         finish(a0, a1);
       }
     }
@@ -583,6 +588,7 @@ void tensor_backward_t(const DevGeom& g, const void* x, const void* w, const voi
   prm.S = S;
   prm.pbi = (g.P + 63) / 64;
   prm.total_pb = g.B * prm.pbi;
+  prm.zero = 0;
   const int grid = g.g * prm.m_pairs * prm.n_tiles * S;
 
   PFN_encodeTiled enc = get_encode_fn();

@@ -284,6 +284,7 @@ struct TcGiParams {
   int m_tiles, n_tiles, total_tiles;
   int cobs;                  // 64-wide output-channel blocks per group = Cog / 64
   int kblocks;               // K * cobs
+  int zero;                  // always 0 at run time (tc::drain_point)
 };
 
 // 8-channel accumulator of the gather: packed pairs in the storage dtype (one HFMA2 / HFMA2.BF16 per channel pair,
@@ -650,8 +651,8 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const __grid_consta
         uint4 va[GI_NE], vb[GI_NE];
         // the row offsets are re-read from the plan row at every issue (two LDS.128) rather than held for the
         // tap: two load buffers + both passes' offsets do not fit the gather warps' registers
-        auto issue = [&](uint4 (&v)[GI_NE], int pass, const char* base) {
-          const uint32_t pa = plan_addr + pass * 4 * (uint32_t)sizeof(PlanRow);
+        auto issue = [&](uint4 (&v)[GI_NE], int pass, const char* base, uint32_t after) {
+          const uint32_t pa = plan_addr + pass * 4 * (uint32_t)sizeof(PlanRow) + after;
           const uint4 i0 = lds128(pa), i1 = lds128(pa + 16), meta = lds128(pa + 48);
           const uint32_t idx[GI_NE] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
           const int n = (int)meta.x;
@@ -676,14 +677,18 @@ k_tc_grad_input(const __grid_constant__ CUtensorMap tmap_wt, const __grid_consta
           }
           sts128(a_addr + sw128(row0 + pass * 4, chunk), acc.pack());
         };
-        issue(va, 0, gcb);
+        // the wait for the buffer about to be accumulated comes BEFORE the next loads are issued: every LDG of the
+        // loop retires through one scoreboard (see the forward kernel's gather loop, tensor_path.cu)
+        issue(va, 0, gcb, 0u);
         for (int cob = 0; cob < prm.cobs; ++cob) {
-          issue(vb, 1, gcb);
+          const uint32_t da = tc::drain_point(va[0].x, prm.zero);
+          issue(vb, 1, gcb, da);
           ptx::mbar_wait(&empty[s], ph ^ 1);
           const uint32_t a_addr = ptx::smem_u32(sA + s * A_STAGE);
           finish(va, 0, gcb, a_addr);
-          if (cob + 1 < prm.cobs) issue(va, 0, gcb + 128);
-          finish(vb, 1, gcb, a_addr);
+          const uint32_t db = tc::drain_point(vb[0].x, prm.zero);
+          if (cob + 1 < prm.cobs) issue(va, 0, gcb + 128, db);
+          finish(vb, 1, gcb, a_addr + db);
           ptx::fence_proxy_async_smem();
           ptx::mbar_arrive_warp(&full_a[s]);
           if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -902,6 +907,7 @@ void tensor_grad_input(const DevGeom& g, const void* w, const void* go, void* gx
   prm.entries = reinterpret_cast<const BinEntry*>(base + L.entries);
   prm.gx = gx;
   prm.BN = pick_bn_gi(g);
+  prm.zero = 0;
   const long long total_pos = (long long)g.B * g.IN;
   prm.m_tiles = (int)((total_pos + GI_BM - 1) / GI_BM);
   prm.n_tiles = g.C / prm.BN;

@@ -105,6 +105,7 @@ struct TcGsParams {
   int m_tiles;       // ceil(total_pb / 2)
   long long items;   // m_tiles * dg * K (tile, phase) work items, split evenly over the CTAs
   int om_tma;        // 1: offset / mask slabs come by TMA (needs P % 8 == 0: 16-byte global strides), 0: global loads
+  int zero;          // always 0 at run time (tc::drain_point)
 };
 
 // dot product of two 8-element vectors stored in the tensor dtype
@@ -534,18 +535,20 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
             if (++ts == 2) { ts = 0; tph ^= 1; }
           }
         }
-        auto load_row = [&](int blk, int i, uint4 (&v)[NC]) {
-          const uint4* xc = xq + (((dgi * bpd + blk) * 64) >> 3) + j;
+        auto load_row = [&](int blk, int i, uint4 (&v)[NC], uint32_t after = 0u) {
+          const uint4* xc = xq + (((dgi * bpd + blk) * 64) >> 3) + j + after;
 #pragma unroll
           for (int c = 0; c < NC; ++c) v[c] = idx[i][c] >= 0 ? __ldg(xc + idx[i][c]) : make_uint4(0u, 0u, 0u, 0u);
         };
         if constexpr (F32) {
           // (handled above)
         } else if constexpr (ND == 2) {
+          // (the wait for the row about to be used comes BEFORE the next row's loads are issued: every LDG of the loop
+          // retires through one scoreboard, see the forward kernel's gather loop, tensor_path.cu)
           uint4 va[NC], vb[NC];
           load_row(0, 0, va);
           for (int blk = 0; blk < nblk; ++blk) {
-            load_row(blk, 1, vb);
+            load_row(blk, 1, vb, tc::drain_point(va[NC - 1].w, prm.zero));
             ptx::mbar_wait(&t_full[ts], tph);
             const uint32_t tb = ptx::smem_u32(sT + ts * T_BYTES);
             {
@@ -553,9 +556,10 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
 #pragma unroll
               for (int c = 0; c < NC; ++c) S[0][c] += dot8(gc, va[c], T());
             }
-            if (blk + 1 < nblk) load_row(blk + 1, 0, va);
+            const uint32_t db = tc::drain_point(vb[NC - 1].w, prm.zero);
+            if (blk + 1 < nblk) load_row(blk + 1, 0, va, db);
             {
-              const uint4 gc = lds128(tb + sw128(row0 + 4, j));
+              const uint4 gc = lds128(tb + sw128(row0 + 4, j) + db);   // (+ db: the wait stays ahead of the branch)
 #pragma unroll
               for (int c = 0; c < NC; ++c) S[1][c] += dot8(gc, vb[c], T());
             }
@@ -695,6 +699,7 @@ void tensor_grad_sample(const DevGeom& g, const T* xt, const void* wr, const voi
   using E = typename std::conditional<F32, __nv_bfloat16, T>::type;   // element type of the TMA-read operands
   TcGsParams prm;
   prm.g = g;
+  prm.zero = 0;
   prm.xt = xt; prm.off = off; prm.mask = mask; prm.goff = goff; prm.gmask = gmask;
   const int bpd = g.Cdg / 64, bpg = g.Cg / 64;
   int nb = GsCfg<T>::MAX_NB;

@@ -76,6 +76,7 @@ struct TcFwdParams {
   int ccs;           // channel blocks per group (Cg / 64)
   int bpd;           // channel blocks per deformable group (Cdg / 64)
   int kblocks;       // ccs * K
+  int zero;          // always 0 at run time, opaque to the compiler: see the gather loop (load ordering)
 };
 
 // K-block order inside one (tile, group): channel blocks are walked in runs that share a deformable
@@ -270,7 +271,11 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr int fmt = F32 ? 1 : tc::umma_fmt<T>();   // fp32 callers: bf16 halves
+#ifdef MDCONV_EXP_HALFN   // timing experiment only (wrong results): half-width MMAs, everything else unchanged
+      const uint32_t idesc = ptx::umma_idesc_f16(fmt, 0, 0, TC_BM, BN / 2);
+#else
       const uint32_t idesc = ptx::umma_idesc_f16(fmt, 0, 0, TC_BM, BN);
+#endif
       int s = 0;
       uint32_t ph = 0;
       int as = 0;
@@ -286,7 +291,11 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
           const uint32_t a_addr = ptx::smem_u32(sA + s * A_STAGE);
           const uint32_t b_addr = ptx::smem_u32(sB + s * TC_B_BYTES);
 #pragma unroll
+#ifdef MDCONV_EXP_NOMMA    // timing experiment only: no MMAs at all (the commits still run the pipeline)
+          for (int k = 0; k < 0; ++k) {
+#else
           for (int k = 0; k < TC_BK / 16; ++k) {
+#endif
             const uint64_t ad = ptx::umma_smem_desc_sw128(a_addr + k * 32, 0, 1024);
             const uint64_t bd = ptx::umma_smem_desc_sw128(b_addr + k * 32, 0, 1024);
             ptx::umma_f16(d_tmem, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
@@ -426,10 +435,11 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
     // position, a quarter of the L1 wavefronts of a live row, and nothing reads the rows back)
 
     // issue the corner loads of K-block `it` into (v0, v1)
-    auto issue = [&](const KbIter& it, uint4 (&v0)[NC], uint4 (&v1)[NC]) {
+    // `after` (always 0) chains the loads behind a value read from the OTHER register buffer, see the loop below
+    auto issue = [&](const KbIter& it, uint4 (&v0)[NC], uint4 (&v1)[NC], uint32_t after) {
       if constexpr (F32) return;
       if (it.first()) ptx::mbar_wait(&plan_full[ips], ipph);
-      const uint32_t pa = plan_row + ips * kSlotBytes;
+      const uint32_t pa = plan_row + ips * kSlotBytes + after;
       const uint4* xc = xq + ((it.grp * g.Cg + it.cc * TC_BK) >> 3) + chunk;
       int i0[4 * NQ], i1[4 * NQ];
 #pragma unroll
@@ -440,16 +450,18 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
       }
 #pragma unroll
       for (int c = 0; c < NC; ++c) v0[c] = __ldg(xc + i0[c]);
+#ifndef MDCONV_EXP_HALFROWS   // timing experiment only: the second row of every thread is not gathered
 #pragma unroll
       for (int c = 0; c < NC; ++c) v1[c] = __ldg(xc + i1[c]);
+#endif
       if (it.last()) {
         if (++ips == PLAN_SLOTS) { ips = 0; ipph ^= 1; }
       }
     };
     // interpolate K-block `it` from (v0, v1) into the A stage, publish it, release the plan slot
-    auto finish = [&](const KbIter& it, const uint4 (&v0)[NC], const uint4 (&v1)[NC]) {
+    auto finish = [&](const KbIter& it, const uint4 (&v0)[NC], const uint4 (&v1)[NC], uint32_t after = 0u) {
       ptx::mbar_wait(&empty[s], ph ^ 1);            // MMA has finished reading A[s]
-      const uint32_t a_addr = ptx::smem_u32(sA + s * A_STAGE);
+      const uint32_t a_addr = ptx::smem_u32(sA + s * A_STAGE) + after;
       if (GRID) {
         // the loaded vector IS the column value (absent taps were pointed at the all-zero position)
         tc::sts128(a_addr + tc::sw128(row0, chunk), v0[0]);
@@ -465,10 +477,14 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
         }
         if constexpr (!F32) {
           tc::sts128(a_addr + tc::sw128(row0, chunk), tc::interp8(v0, w0, NC, T()));
+#ifndef MDCONV_EXP_HALFROWS
           tc::sts128(a_addr + tc::sw128(row0 + 4, chunk), tc::interp8(v1, w1, NC, T()));
+#endif
         }
       }
+#ifndef MDCONV_EXP_NOFENCE    // timing experiment only
       ptx::fence_proxy_async_smem();
+#endif
       ptx::mbar_arrive_warp(&full_a[s]);
       if (++s == TC_STAGES) { s = 0; ph ^= 1; }
       if (it.last()) {
@@ -533,24 +549,32 @@ k_tc_forward(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
         ka.advance(prm);
       }
     } else if (ND == 2 || GRID) {
+      // All corner loads of a thread retire through ONE hardware scoreboard (ptxas gives every LDG of this loop the
+      // same one), and waiting on a scoreboard means waiting for EVERYTHING outstanding on it: if the loads of K-block
+      // k+1 were issued before the first use of K-block k's registers, that use would also wait for the loads just
+      // issued and the look-ahead would hide nothing.  So the wait comes first: one instruction reads a register of
+      // the buffer about to be interpolated (`& prm.zero`: a run-time 0 the compiler cannot fold), the address of the
+      // next loads depends on its result, and the loads then fly while the current block is interpolated and stored.
       uint4 a0[NC], a1[NC], b0[NC], b1[NC];
-      if (ka.valid) issue(ka, a0, a1);
+      if (ka.valid) issue(ka, a0, a1, 0u);
       while (ka.valid) {
         kb2 = ka;
         kb2.advance(prm);
-        if (kb2.valid) issue(kb2, b0, b1);
-        finish(ka, a0, a1);
+        const uint32_t da = tc::drain_point(a1[NC - 1].w, prm.zero);
+        if (kb2.valid) issue(kb2, b0, b1, da);
+        finish(ka, a0, a1, da);
         if (!kb2.valid) break;
         ka = kb2;
         ka.advance(prm);
-        if (ka.valid) issue(ka, a0, a1);
-        finish(kb2, b0, b1);
+        const uint32_t db = tc::drain_point(b1[NC - 1].w, prm.zero);
+        if (ka.valid) issue(ka, a0, a1, db);
+        finish(kb2, b0, b1, db);
       }
     } else {
       // 3D: 16 corner loads per thread already fill the register budget; no look-ahead
       uint4 a0[NC], a1[NC];
       while (ka.valid) {
-        issue(ka, a0, a1);
+        issue(ka, a0, a1, 0u);
         finish(ka, a0, a1);
         ka.advance(prm);
       }
@@ -740,6 +764,7 @@ void tensor_forward_t(const DevGeom& g, const void* x, const void* w, const void
   prm.ccs = g.Cg / TC_BK;
   prm.bpd = g.Cdg / TC_BK;
   prm.kblocks = prm.ccs * g.K;
+  prm.zero = 0;
   tc::plan_tail_split(prm.total_tiles, tc::sm_count(), !g.cl, prm.full_tiles, prm.tail_tiles, prm.tail_split,
                       prm.tail_rows);
 
