@@ -217,6 +217,14 @@ int mdconv_set_comm_sms(int sms);
  * environment does the same.  Returns the previous setting. */
 int mdconv_set_fp32_tensor_cores(int on);
 
+/* grad_input of 16-bit calls is a col2im GATHER over grad_columns ([samples][P][K*C] in the storage dtype -- the
+ * reference's own buffer, src/mdeformable_conv.cu:396-419) that the grad_offset / grad_mask kernel streams out on its
+ * way; the buffer is part of the backward workspace mdconv_workspace_bytes() reports.  `megabytes` (default 1024, or
+ * MDCONV_B200_GCOL_MAX_MB) caps it: a batch whose grad_columns are larger is walked in chunks of whole samples that
+ * fit (slower: more, smaller launches).  0 -- and fp32 calls -- run grad_input as a third contraction over the inverse
+ * index instead, which needs no such buffer.  Returns the previous cap (-1: default not resolved yet). */
+long long mdconv_set_gcol_budget_mb(long long megabytes);
+
 /* ---- The reference's eight entry points, C ABI form --------------------------------------
  * Argument order follows the reference signatures; tensor handles become device pointers and the
  * sizes the reference read from the tensors are passed explicitly (batch, channels, spatial

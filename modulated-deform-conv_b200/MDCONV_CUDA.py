@@ -140,6 +140,17 @@ def set_fp32_tensor_cores(on: bool) -> bool:
     return bool(_lib.mdconv_set_fp32_tensor_cores(1 if on else 0))
 
 
+_lib.mdconv_set_gcol_budget_mb.restype = ctypes.c_longlong
+_lib.mdconv_set_gcol_budget_mb.argtypes = [ctypes.c_longlong]
+
+
+def set_gcol_budget_mb(megabytes: int) -> int:
+    """Cap (MiB) of the grad_columns buffer behind the col2im-gather grad_input of 16-bit calls (default 1024; larger
+    batches are walked in chunks; 0: always the third contraction).  Returns the previous cap (-1 if the default had
+    not been resolved yet)."""
+    return int(_lib.mdconv_set_gcol_budget_mb(int(megabytes)))
+
+
 def set_comm_sms(sms: int) -> int:
     """SMs the persistent data-gradient kernels leave free for a concurrent collective once the parameter
     gradients are final (see mdconv_set_comm_sms).  Returns the previous value."""

@@ -338,6 +338,7 @@ int mdconv_backward_ex(const mdconv_geom_t* gi, const void* input, const void* w
 
 int mdconv_set_comm_sms(int sms) { return mdconv::set_comm_spare_sms(sms); }
 int mdconv_set_fp32_tensor_cores(int on) { return mdconv::set_fp32_on_tensor_cores(on); }
+long long mdconv_set_gcol_budget_mb(long long megabytes) { return mdconv::tc::set_gcol_budget_mb(megabytes); }
 
 // ---- legacy-named entry points -----------------------------------------------------------------
 static mdconv_geom_t legacy_geom(int nd, int modulated, int batch, int channels, int height, int width, int length,

@@ -227,6 +227,9 @@ struct LaunchCtx {
 int comm_spare_sms();
 int set_comm_spare_sms(int sms);   // returns the previous value
 int set_fp32_on_tensor_cores(int on);   // returns the previous value (tensor_path.cu)
+namespace tc {
+long long set_gcol_budget_mb(long long mb);   // grad_columns budget of the col2im-gather grad_input (tensor_bwd_input.cu)
+}
 inline void signal_weight_ready(LaunchCtx& ctx) {
   if (ctx.weight_ready != nullptr) {
     cudaError_t e = cudaEventRecord(ctx.weight_ready, ctx.stream);

@@ -426,7 +426,8 @@ bool tensor_backward_supported(const DevGeom& g, int dtype);
 bool grad_sample_supported(const DevGeom& g);
 template <typename T>
 void tensor_grad_sample(const DevGeom& g, const T* xt, const void* wr, const void* off, const void* mask, const void* go,
-                        const void* go_lo, int go_ld, void* goff, void* gmask, LaunchCtx& ctx);
+                        const void* go_lo, int go_ld, void* goff, void* gmask, void* gcol, int sample0, int samples,
+                        LaunchCtx& ctx);
 // grad_input (tensor_bwd_input.cu)
 bool grad_input_supported(const DevGeom& g);
 size_t grad_input_workspace(const DevGeom& g);
@@ -434,6 +435,15 @@ template <typename T>
 void tensor_grad_input_prepare(const DevGeom& g, const void* off, const void* mask, void* ws, LaunchCtx& ctx);
 template <typename T>
 void tensor_grad_input(const DevGeom& g, const void* w, const void* go, void* gx, void* ws, LaunchCtx& ctx);
+// col2im-gather path of grad_input (16-bit callers): the batch is walked in chunks of gcol_chunk_samples() samples;
+// per chunk k_tc_grad_sample streams its grad_columns into ONE buffer of the workspace -- small enough to stay in L2,
+// re-used by every chunk -- and a gather over the inverse index turns it into that chunk's grad_input
+bool grad_input_uses_gcol(const DevGeom& g);
+int gcol_chunk_samples(const DevGeom& g);
+void* grad_input_gcol(const DevGeom& g, void* ws);            // the grad_columns buffer (or nullptr: contraction path)
+long long set_gcol_budget_mb(long long mb);                   // returns the previous budget (-1: not set yet)
+template <typename T>
+void tensor_grad_input_from_gcol(const DevGeom& g, void* gx, void* ws, int sample0, int samples, LaunchCtx& ctx);
 
 }  // namespace tc
 }  // namespace mdconv

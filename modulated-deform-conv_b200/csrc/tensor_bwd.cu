@@ -637,7 +637,19 @@ void tensor_backward_t(const DevGeom& g, const void* x, const void* w, const voi
 
   // ---- grad_offset / grad_mask / grad_input ----
   if (data_tc) {
-    tensor_grad_sample<T>(g, xt, wr, off, mask, go_tma, go_tma_lo, ld, goff, gmask, ctx);
+    // 16-bit callers: chunk by chunk, grad_sample also streams grad_columns into an L2-sized buffer and grad_input is
+    // a gather over it; otherwise grad_input runs its own contraction (tensor_bwd_input.cu)
+    void* gcol = grad_input_gcol(g, data_ws);
+    if (gcol != nullptr) {
+      const int step = gcol_chunk_samples(g);
+      for (int b0 = 0; b0 < g.B; b0 += step) {
+        const int nb = g.B - b0 < step ? g.B - b0 : step;
+        tensor_grad_sample<T>(g, xt, wr, off, mask, go_tma, go_tma_lo, ld, goff, gmask, gcol, b0, nb, ctx);
+        tensor_grad_input_from_gcol<T>(g, gx, data_ws, b0, nb, ctx);
+      }
+      return;
+    }
+    tensor_grad_sample<T>(g, xt, wr, off, mask, go_tma, go_tma_lo, ld, goff, gmask, nullptr, 0, g.B, ctx);
     tensor_grad_input<T>(g, w, go, gx, data_ws, ctx);
     return;
   }

@@ -100,10 +100,25 @@ struct BinEntry {
 // ---- inverse index ----------------------------------------------------------------------------
 // One thread per (sample, deformable group, output position, tap).  FILL == false: count the entries
 // of each bin; FILL == true: place them (slot taken from the remaining count).
+// pos_major: the layout the col2im gather reads -- the K bins of one input position are neighbours (bin =
+// ((sample, deformable group), input position, tap)), so its entries of ALL taps are one contiguous run, and an entry
+// is ready to use: `row` = element offset of the grad_columns block it scales, ((b * P + output position) * K + tap) * C,
+// `w` = the weight as a packed pair in the storage dtype.  Otherwise tap-major (bin = ((sample, deformable group),
+// tap, input position), row = b * P + output position, fp32 weight), what k_tc_grad_input walks.
+__device__ __forceinline__ float pack_weight(float w, __half) {
+  const __half2 h = __float2half2_rn(w);
+  return __uint_as_float(*reinterpret_cast<const uint32_t*>(&h));
+}
+__device__ __forceinline__ float pack_weight(float w, __nv_bfloat16) {
+  const __nv_bfloat162 h = __float2bfloat162_rn(w);
+  return __uint_as_float(*reinterpret_cast<const uint32_t*>(&h));
+}
+__device__ __forceinline__ float pack_weight(float w, float) { return w; }
 template <typename T, int ND, bool MOD, bool FILL>
 __global__ void __launch_bounds__(256) k_bin_entries(const DevGeom g, const T* __restrict__ off,
                                                      const T* __restrict__ mask, int* __restrict__ count,
-                                                     const int* __restrict__ start, BinEntry* __restrict__ entries) {
+                                                     const int* __restrict__ start, BinEntry* __restrict__ entries,
+                                                     int pos_major) {
   const long long n = (long long)g.B * g.dg * g.K * g.P;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int p = (int)(i % g.P);
@@ -138,7 +153,9 @@ __global__ void __launch_bounds__(256) k_bin_entries(const DevGeom g, const T* _
       }
       okc[c] = ok;
       wgt[c] = w;
-      bin[c] = ok ? (((size_t)b * g.dg + dgi) * g.K + tap) * g.IN + pix : 0;   // tap-major: neighbours in p hit neighbouring bins
+      const size_t bd = (size_t)b * g.dg + dgi;
+      bin[c] = !ok ? 0 : pos_major ? (bd * g.IN + pix) * g.K + tap
+                                   : (bd * g.K + tap) * g.IN + pix;   // tap-major: neighbours in p hit neighbouring bins
     }
     if (!FILL) {
 #pragma unroll
@@ -154,8 +171,8 @@ __global__ void __launch_bounds__(256) k_bin_entries(const DevGeom g, const T* _
       for (int c = 0; c < (1 << ND); ++c) {
         if (okc[c]) {
           BinEntry e;
-          e.row = b * g.P + p;
-          e.w = wgt[c];
+          e.row = pos_major ? ((b * g.P + p) * g.K + tap) * g.C : b * g.P + p;
+          e.w = pos_major ? pack_weight(wgt[c], T()) : wgt[c];
           entries[slot[c]] = e;
         }
       }
@@ -338,6 +355,181 @@ template <> struct Acc8<float> {   // placeholder: the fp32 gather has its own a
   __device__ __forceinline__ void fma(const uint4&, float) {}
   __device__ __forceinline__ uint4 pack() const { return make_uint4(0u, 0u, 0u, 0u); }
 };
+
+// ---- grad_input as a col2im GATHER over grad_columns (16-bit callers, default) --------------------
+// k_tc_grad_sample already holds gcol[pos, (tap, c)] = sum_co go[pos, co] * W[co, c, tap] block by block in shared
+// memory for its dot products; with save_gcol it also streams those blocks to HBM ([B][P][K*C], the reference's
+// grad_columns buffer, src/mdeformable_conv.cu:396-419).  grad_input is then
+//     gx[ipos, c] = sum over taps, over the entries e of bin (sample, deformable group of c, tap, ipos):  w_e * gcol[row_e, (tap, c)]
+// -- the reference's col2im (:282-293) read through the inverse index instead of scattered with atomics: no third
+// contraction, no channels-last copy of grad_output, no transposed filter bank, and still one write per element in a
+// fixed order.  One thread = 8 channels of one input position; its entries (all taps: one contiguous run of the
+// position-major index) are walked C2I_B at a time, so that many 16-byte loads are in flight per thread; fp32
+// accumulation.  NCHW callers: a [64 positions x C] tile is turned
+// through shared memory so the stores run along the positions; channels-last callers store their rows directly.
+constexpr int C2I_MAX_POS = 64;    // input positions per tile: ~512 (position, 8-channel chunk) pairs, 8 .. 64 positions
+constexpr int C2I_CS = 512;        // channels per tile (wider layers take several channel slabs per position tile)
+constexpr int C2I_THREADS = 256;
+#ifndef MDCONV_C2I_B
+#define MDCONV_C2I_B 8
+#endif
+#ifndef MDCONV_C2I_MINB
+#define MDCONV_C2I_MINB 4
+#endif
+constexpr int C2I_B = MDCONV_C2I_B;        // entries per batch of the gather loop (16-byte loads in flight per thread)
+constexpr int C2I_MINB = MDCONV_C2I_MINB;  // blocks per SM the register allocation aims at
+
+// packed 8-channel partial sum of one batch: sum_k w_k * v_k with w_k already a packed pair (entry.y)
+template <int NB, typename H2>
+__device__ __forceinline__ void c2i_batch_t(const uint4 (&v)[NB], const int2 (&ee)[NB], H2 (&a)[4]) {
+#pragma unroll
+  for (int k = 0; k < NB; ++k) {
+    const uint32_t wb = (uint32_t)ee[k].y;
+    const H2 w = *reinterpret_cast<const H2*>(&wb);
+    const H2* h = reinterpret_cast<const H2*>(&v[k]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = k == 0 ? __hmul2(w, h[i]) : __hfma2(w, h[i], a[i]);
+  }
+}
+template <int NB>
+__device__ __forceinline__ uint4 c2i_batch(const uint4 (&v)[NB], const int2 (&ee)[NB], __half) {
+  __half2 a[4];
+  c2i_batch_t<NB, __half2>(v, ee, a);
+  return *reinterpret_cast<const uint4*>(a);
+}
+template <int NB>
+__device__ __forceinline__ uint4 c2i_batch(const uint4 (&v)[NB], const int2 (&ee)[NB], __nv_bfloat16) {
+  __nv_bfloat162 a[4];
+  c2i_batch_t<NB, __nv_bfloat162>(v, ee, a);
+  return *reinterpret_cast<const uint4*>(a);
+}
+// fp32 += a packed partial sum
+__device__ __forceinline__ void c2i_flush_t(float (&acc)[8], const uint4& p, __half) {
+  const __half2* h = reinterpret_cast<const __half2*>(&p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(h[i]);
+    acc[2 * i] += f.x;
+    acc[2 * i + 1] += f.y;
+  }
+}
+__device__ __forceinline__ void c2i_flush_t(float (&acc)[8], const uint4& p, __nv_bfloat16) {
+  const uint32_t* u = reinterpret_cast<const uint32_t*>(&p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {   // bf16 -> fp32 is a shift
+    acc[2 * i] += __uint_as_float(u[i] << 16);
+    acc[2 * i + 1] += __uint_as_float(u[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint4 c2i_pack(const float (&acc)[8], __half) {
+  uint4 r;
+  uint32_t* o = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 h = __floats2half2_rn(acc[2 * i], acc[2 * i + 1]);
+    o[i] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  return r;
+}
+__device__ __forceinline__ uint4 c2i_pack(const float (&acc)[8], __nv_bfloat16) {
+  uint4 r;
+  uint32_t* o = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(acc[2 * i], acc[2 * i + 1]);
+    o[i] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  return r;
+}
+
+template <typename T, bool CL>
+__global__ void __launch_bounds__(C2I_THREADS, C2I_MINB) k_col2im_gather(const DevGeom g, const T* __restrict__ gcol,
+                                                                  const int* __restrict__ bin_start,
+                                                                  const BinEntry* __restrict__ entries,
+                                                                  T* __restrict__ gx, long long pos_base,
+                                                                  long long total_pos, int n_tiles, int slabs,
+                                                                  int tile_pos) {
+  extern __shared__ __align__(16) uint8_t c2i_smem[];   // NCHW: [tile_pos][slab channels + 8] elements
+  const int2* __restrict__ ent2 = reinterpret_cast<const int2*>(entries);
+  T* tile = reinterpret_cast<T*>(c2i_smem);
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const long long pos0 = pos_base + (long long)(t / slabs) * tile_pos;   // [pos_base, total_pos): this launch's samples
+    const int c_base = (t % slabs) * C2I_CS;      // first channel of this tile's slab
+    const int cs = min(C2I_CS, g.C - c_base);     // channels in it
+    const int ldt = cs + 8;                       // padded row of the staging tile (elements)
+    const int CH = cs >> 3;                       // 8-channel chunks per position
+    const int items = tile_pos * CH;              // (position, chunk) pairs per tile
+    for (int it = threadIdx.x; it < items; it += C2I_THREADS) {
+      const int chunk = it % CH, pl = it / CH;    // a warp = consecutive chunks of one position (>= 256 channels), or of a few
+      const long long gpos = pos0 + pl;
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      if (gpos < total_pos) {
+        const int b = (int)(gpos / g.IN), ipos = (int)(gpos - (long long)b * g.IN);
+        const int dgi = (c_base + chunk * 8) / g.Cdg;
+        // position-major bins: the entries of all K taps of this input position are one run [e0, e1) (~4 * K long)
+        const size_t bin0 = (((size_t)b * g.dg + dgi) * g.IN + ipos) * g.K;
+        const int e0 = __ldg(bin_start + bin0), e1 = __ldg(bin_start + bin0 + g.K);
+        const T* colc = gcol + c_base + chunk * 8;   // an entry's block: colc + entry.x
+        // C2I_B entries at a time: their (L1-resident) records, then their grad_columns vectors all in flight
+        // together; the products of a batch are summed in packed pairs of the storage dtype, as the gather of
+        // k_tc_grad_input does, and batches are folded in fp32.
+        int e = e0;
+        for (; e + C2I_B <= e1; e += C2I_B) {
+          int2 ee[C2I_B];
+          uint4 v[C2I_B];
+#pragma unroll
+          for (int k = 0; k < C2I_B; ++k) ee[k] = __ldg(ent2 + e + k);
+#pragma unroll
+          for (int k = 0; k < C2I_B; ++k) v[k] = __ldg(reinterpret_cast<const uint4*>(colc + ee[k].x));
+          c2i_flush_t(acc, c2i_batch<C2I_B>(v, ee, T()), T());
+        }
+        if (e < e1) {                             // the last, partial batch
+          int2 ee[C2I_B];
+          uint4 v[C2I_B];
+#pragma unroll
+          for (int k = 0; k < C2I_B; ++k) ee[k] = e + k < e1 ? __ldg(ent2 + e + k) : make_int2(0, 0);   // weight 0
+#pragma unroll
+          for (int k = 0; k < C2I_B; ++k) v[k] = e + k < e1 ? __ldg(reinterpret_cast<const uint4*>(colc + ee[k].x)) : make_uint4(0u, 0u, 0u, 0u);
+          c2i_flush_t(acc, c2i_batch<C2I_B>(v, ee, T()), T());
+        }
+      }
+      const uint4 out = c2i_pack(acc, T());
+      if (CL) {
+        if (gpos < total_pos) *reinterpret_cast<uint4*>(gx + (size_t)gpos * g.C + c_base + chunk * 8) = out;
+      } else {
+        *reinterpret_cast<uint4*>(tile + (size_t)pl * ldt + chunk * 8) = out;   // 16-byte rows-of-channels store
+      }
+    }
+    if (!CL) {
+      __syncthreads();
+      // store: thread -> (8-position chunk, channel), lanes along the channels (conflict-free 2-byte reads of the
+      // staging tile); a tile may straddle samples, and IN need not be a multiple of 8
+      const int vec_ok = (g.IN % 8 == 0) && ((reinterpret_cast<uintptr_t>(gx) & 15) == 0);
+      for (int q = threadIdx.x; q < cs * (tile_pos / 8); q += C2I_THREADS) {
+        const int cl = q % cs, pc = (q / cs) * 8;
+        const int c = c_base + cl;
+        const long long gp = pos0 + pc;
+        if (gp >= total_pos) continue;
+        T vals[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) vals[k] = tile[(size_t)(pc + k) * ldt + cl];
+        const int b = (int)(gp / g.IN), ipos = (int)(gp - (long long)b * g.IN);
+        if (vec_ok && gp + 8 <= total_pos) {      // (IN % 8 == 0: the 8 positions are in one sample, 16-byte aligned)
+          *reinterpret_cast<uint4*>(gx + ((size_t)b * g.C + c) * g.IN + ipos) = *reinterpret_cast<const uint4*>(vals);
+        } else {
+          for (int k = 0; k < 8 && gp + k < total_pos; ++k) {
+            const long long gk = gp + k;
+            const int bk = (int)(gk / g.IN), ik = (int)(gk - (long long)bk * g.IN);
+            gx[((size_t)bk * g.C + c) * g.IN + ik] = vals[k];
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
 
 // CL: the caller's activations are channels-last (grad_output is gathered in place, grad_input leaves through TMA
 // stores); a compile-time switch so the NCHW instantiation carries none of that epilogue's registers or code.
@@ -783,7 +975,8 @@ GiLayout gi_layout(const DevGeom& g) {
 }
 
 template <typename T, int ND, bool MOD>
-void build_bins(const DevGeom& g, const void* off, const void* mask, char* ws, const GiLayout& L, LaunchCtx& ctx) {
+void build_bins(const DevGeom& g, const void* off, const void* mask, char* ws, const GiLayout& L, int pos_major,
+                LaunchCtx& ctx) {
   int* count = reinterpret_cast<int*>(ws + L.count);
   int* start = reinterpret_cast<int*>(ws + L.start);
   BinEntry* entries = reinterpret_cast<BinEntry*>(ws + L.entries);
@@ -794,7 +987,8 @@ void build_bins(const DevGeom& g, const void* off, const void* mask, char* ws, c
   const int blocks = (int)((n + 255) / 256 > 148 * 16 ? 148 * 16 : (n + 255) / 256);
   {
     ProfScope prof(ctx, "bin_count");
-    k_bin_entries<T, ND, MOD, false><<<blocks, 256, 0, ctx.stream>>>(g, (const T*)off, (const T*)mask, count, start, entries);
+    k_bin_entries<T, ND, MOD, false><<<blocks, 256, 0, ctx.stream>>>(g, (const T*)off, (const T*)mask, count, start, entries,
+                                                                     pos_major);
     MDCONV_CHECK_LAUNCH(ctx);
   }
   {
@@ -806,7 +1000,8 @@ void build_bins(const DevGeom& g, const void* off, const void* mask, char* ws, c
   }
   {
     ProfScope prof(ctx, "bin_fill");
-    k_bin_entries<T, ND, MOD, true><<<blocks, 256, 0, ctx.stream>>>(g, (const T*)off, (const T*)mask, count, start, entries);
+    k_bin_entries<T, ND, MOD, true><<<blocks, 256, 0, ctx.stream>>>(g, (const T*)off, (const T*)mask, count, start, entries,
+                                                                    pos_major);
     MDCONV_CHECK_LAUNCH(ctx);
   }
   {
@@ -834,18 +1029,107 @@ static size_t got_bytes(const DevGeom& g) { return g.cl ? 0 : align256((size_t)g
 // transposed filter bank(s): one 16-bit bank, or bf16 hi + lo for fp32 callers
 static size_t wt_bytes(const DevGeom& g) { return align256((size_t)g.Co * g.Kg * 2) * (g.esize == 4 ? 2 : 1); }
 
+// ---- col2im-gather path ---------------------------------------------------------------------------
+// grad_columns ([samples][P][K*C], storage dtype) live in ONE workspace buffer capped by the budget
+// (MDCONV_B200_GCOL_MAX_MB / mdconv_set_gcol_budget_mb(), default 1024 MiB).  A batch that fits goes through in one
+// (k_tc_grad_sample, k_col2im_gather) pair; a larger one is walked in chunks of whole samples that fit, re-using the
+// buffer (measured at cfg2: 4 / 8 chunks cost +9 % / +27 % of the pair -- smaller launches fill the machine worse, and
+// keeping the buffer L2-resident buys nothing).  Budget 0 -- and fp32 callers, and batches whose offsets do not fit 31
+// bits -- take the contraction path (k_tc_grad_input), which needs no buffer.
+static std::atomic<long long> g_gcol_budget_mb{-1};
+long long set_gcol_budget_mb(long long mb) {
+  const long long prev = g_gcol_budget_mb.load();
+  g_gcol_budget_mb.store(mb < 0 ? 0 : mb);
+  return prev;
+}
+static long long gcol_budget_bytes() {
+  long long mb = g_gcol_budget_mb.load();
+  if (mb < 0) {
+    const char* e = getenv("MDCONV_B200_GCOL_MAX_MB");
+    mb = e ? atoll(e) : 1024;
+    if (mb < 0) mb = 0;
+    g_gcol_budget_mb.store(mb);
+  }
+  return mb << 20;
+}
+static long long gcol_sample_bytes(const DevGeom& g) { return (long long)g.P * g.K * g.C * 2; }
+bool grad_input_uses_gcol(const DevGeom& g) {
+  if (g.esize != 2 || gcol_budget_bytes() <= 0) return false;
+  if ((long long)g.B * g.P * g.K * g.C > 2147483647LL) return false;   // an entry holds a 31-bit element offset
+  return gcol_sample_bytes(g) <= (512LL << 20);                        // (one sample is the smallest chunk)
+}
+int gcol_chunk_samples(const DevGeom& g) {
+  long long n = gcol_budget_bytes() / gcol_sample_bytes(g);
+  if (n < 1) n = 1;
+  if (n > g.B) n = g.B;
+  return (int)n;
+}
+size_t gcol_bytes(const DevGeom& g) { return align256((size_t)gcol_chunk_samples(g) * (size_t)gcol_sample_bytes(g)); }
+
 size_t grad_input_workspace(const DevGeom& g) {
-  // channels-last grad_output + transposed weight + inverse index
+  // gather path: grad_columns buffer + inverse index;  contraction path: channels-last grad_output + transposed weight + index
+  if (grad_input_uses_gcol(g)) return gcol_bytes(g) + gi_layout(g).total;
   return got_bytes(g) + wt_bytes(g) + gi_layout(g).total;
 }
+// offset of the inverse index inside the grad_input workspace
+static size_t gi_index_offset(const DevGeom& g) { return grad_input_uses_gcol(g) ? gcol_bytes(g) : got_bytes(g) + wt_bytes(g); }
+void* grad_input_gcol(const DevGeom& g, void* ws) { return grad_input_uses_gcol(g) ? ws : nullptr; }
+
+// grad_input of samples [sample0, sample0 + samples) from the buffer k_tc_grad_sample has just filled for them
+template <typename T>
+void tensor_grad_input_from_gcol(const DevGeom& g, void* gx, void* ws, int sample0, int samples, LaunchCtx& ctx) {
+  if constexpr (std::is_same<T, float>::value) {
+    (void)g; (void)gx; (void)ws; (void)sample0; (void)samples;
+    if (ctx.err == cudaSuccess) ctx.err = cudaErrorNotSupported;
+    return;
+  } else {
+    char* base = reinterpret_cast<char*>(ws);
+    // entries hold offsets from the start of the WHOLE batch's grad_columns; the buffer holds this chunk's part
+    const T* gcol = reinterpret_cast<const T*>(base) - (size_t)sample0 * g.P * g.K * g.C;
+    base += gcol_bytes(g);
+    const GiLayout L = gi_layout(g);
+    if (ctx.side_join != nullptr) {   // inverse index is ready
+      cudaStreamWaitEvent(ctx.stream, ctx.side_join, 0);
+      ctx.side_join = nullptr;
+    }
+    const long long pos_base = (long long)sample0 * g.IN, total_pos = (long long)(sample0 + samples) * g.IN;
+    const int slabs = (g.C + C2I_CS - 1) / C2I_CS;
+    const int cs = g.C < C2I_CS ? g.C : C2I_CS;
+    int tile_pos = (512 / (cs >> 3)) & ~7;          // ~512 (position, chunk) pairs per tile: two per thread
+    if (tile_pos < 8) tile_pos = 8;
+    if (tile_pos > C2I_MAX_POS) tile_pos = C2I_MAX_POS;
+    const int n_tiles = (int)((total_pos - pos_base + tile_pos - 1) / tile_pos) * slabs;
+    const size_t smem_max = (size_t)C2I_MAX_POS * (C2I_CS + 8) * sizeof(T);
+    const size_t smem = g.cl ? 0 : (size_t)tile_pos * (cs + 8) * sizeof(T);
+    const int sms = sm_count() - ctx.spare_sms > 0 ? sm_count() - ctx.spare_sms : 1;
+    int per_sm = smem > 0 ? (int)((200 * 1024) / smem) : C2I_MINB;   // (blocks per SM by registers: __launch_bounds__)
+    if (per_sm > C2I_MINB) per_sm = C2I_MINB;
+    if (per_sm < 1) per_sm = 1;
+    const int grid = n_tiles < sms * per_sm ? n_tiles : sms * per_sm;
+    const int* start = reinterpret_cast<const int*>(base + L.start);
+    const BinEntry* entries = reinterpret_cast<const BinEntry*>(base + L.entries);
+    ProfScope prof(ctx, "col2im_gather");
+    if (g.cl) {
+      k_col2im_gather<T, true><<<grid, C2I_THREADS, 0, ctx.stream>>>(g, gcol, start, entries, (T*)gx, pos_base, total_pos,
+                                                                     n_tiles, slabs, tile_pos);
+    } else {
+      static std::atomic<unsigned long long> configured{0};
+      opt_in_dynamic_smem(k_col2im_gather<T, false>, smem_max, configured, ctx);
+      k_col2im_gather<T, false><<<grid, C2I_THREADS, smem, ctx.stream>>>(g, gcol, start, entries, (T*)gx, pos_base,
+                                                                         total_pos, n_tiles, slabs, tile_pos);
+    }
+    MDCONV_CHECK_LAUNCH(ctx);
+  }
+}
+template void tensor_grad_input_from_gcol<float>(const DevGeom&, void*, void*, int, int, LaunchCtx&);
+template void tensor_grad_input_from_gcol<__half>(const DevGeom&, void*, void*, int, int, LaunchCtx&);
+template void tensor_grad_input_from_gcol<__nv_bfloat16>(const DevGeom&, void*, void*, int, int, LaunchCtx&);
 
 // Stage 1 (can be issued early): the inverse index, on the side stream when there is one.  Returns with
 // the side stream forked from ctx.stream; tensor_grad_input() joins it before the GEMM kernel.
 template <typename T>
 void tensor_grad_input_prepare(const DevGeom& g, const void* off, const void* mask, void* ws, LaunchCtx& ctx) {
-  char* base = reinterpret_cast<char*>(ws);
-  base += got_bytes(g);
-  base += wt_bytes(g);
+  char* base = reinterpret_cast<char*>(ws) + gi_index_offset(g);
   const GiLayout L = gi_layout(g);
   // no fork while the caller's stream is being captured into a CUDA graph: the whole call then stays on that stream
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -857,12 +1141,13 @@ void tensor_grad_input_prepare(const DevGeom& g, const void* off, const void* ma
     cudaStreamWaitEvent(ss->stream, ss->fork, 0);
     ctx.stream = ss->stream;
   }
+  const int pos_major = grad_input_uses_gcol(g) ? 1 : 0;   // the layout the consumer of this call reads
   if (g.nd == 2) {
-    if (g.modulated) build_bins<T, 2, true>(g, off, mask, base, L, ctx);
-    else build_bins<T, 2, false>(g, off, mask, base, L, ctx);
+    if (g.modulated) build_bins<T, 2, true>(g, off, mask, base, L, pos_major, ctx);
+    else build_bins<T, 2, false>(g, off, mask, base, L, pos_major, ctx);
   } else {
-    if (g.modulated) build_bins<T, 3, true>(g, off, mask, base, L, ctx);
-    else build_bins<T, 3, false>(g, off, mask, base, L, ctx);
+    if (g.modulated) build_bins<T, 3, true>(g, off, mask, base, L, pos_major, ctx);
+    else build_bins<T, 3, false>(g, off, mask, base, L, pos_major, ctx);
   }
   if (ss) {
     cudaEventRecord(ss->join, ss->stream);

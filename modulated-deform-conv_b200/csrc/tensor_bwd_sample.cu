@@ -63,10 +63,14 @@ template <int ND> struct GsRegs {
 template <typename T> struct GsCfg {
   static constexpr bool F32 = false;
   static constexpr int A_STAGE = GS_A_BYTES, T_BYTES = GS_T_BYTES, MAX_NB = 4;
+  // slots of the T ring (accumulator blocks in shared memory): 4, so a block can wait for its grad_columns store
+  // (save_gcol: the TMA engine reads it ~1 us after the dot warps are done with it) without stalling the movers
+  static constexpr int T_SLOTS = 4;
 };
 template <> struct GsCfg<float> {
   static constexpr bool F32 = true;
   static constexpr int A_STAGE = 2 * GS_A_BYTES, T_BYTES = 2 * GS_T_BYTES, MAX_NB = 2;   // B stage: hi blocks, then lo
+  static constexpr int T_SLOTS = 2;
 };
 // byte offset of 16-byte chunk `c` (0..15) of row `row` in an fp32 T block: 256-byte rows, each 128-byte half
 // swizzled like sw128
@@ -101,11 +105,13 @@ struct TcGsParams {
   int nsub;          // stages per (deformable group, tap) = Cdg / 64 / nb
   int kblocks;       // K blocks per stage = Cog / 32
   int pbi;           // 64-position blocks per sample
-  int total_pb;      // B * pbi
-  int m_tiles;       // ceil(total_pb / 2)
+  int pb_base;       // first 64-position block of this launch (a whole number of samples: sample0 * pbi)
+  int total_pb;      // one past its last block: (sample0 + samples) * pbi
+  int m_tiles;       // ceil((total_pb - pb_base) / 2)
   long long items;   // m_tiles * dg * K (tile, phase) work items, split evenly over the CTAs
   int om_tma;        // 1: offset / mask slabs come by TMA (needs P % 8 == 0: 16-byte global strides), 0: global loads
   int zero;          // always 0 at run time (tc::drain_point)
+  int save_gcol;     // 1: every gcol block also goes to HBM ([B][P][K*C], tmap_gcol) for the col2im gather of grad_input
 };
 
 // dot product of two 8-element vectors stored in the tensor dtype
@@ -148,25 +154,26 @@ __global__ void __launch_bounds__(GS_THREADS, 1)
 k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ CUtensorMap tmap_mask,
                  const __grid_constant__ CUtensorMap tmap_go2, const __grid_constant__ CUtensorMap tmap_w2,
-                 const TcGsParams prm) {
+                 const __grid_constant__ CUtensorMap tmap_gcol, const TcGsParams prm) {
   constexpr int NC = 1 << ND;
   constexpr bool F32 = GsCfg<T>::F32;
   constexpr int A_STAGE = GsCfg<T>::A_STAGE;
   constexpr int T_BYTES = GsCfg<T>::T_BYTES;
+  constexpr int T_SLOTS = GsCfg<T>::T_SLOTS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = sA + GS_STAGES * A_STAGE;
   uint8_t* sT = sB + GS_STAGES * GS_B_BYTES;
-  SampleEntry<ND>* sPlan = reinterpret_cast<SampleEntry<ND>*>(sT + 2 * T_BYTES);
+  SampleEntry<ND>* sPlan = reinterpret_cast<SampleEntry<ND>*>(sT + T_SLOTS * T_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sPlan) + 2 * 128 * sizeof(SampleEntry<ND>));
   uint64_t* full = bars;                    // [GS_STAGES]  TMA -> MMA
   uint64_t* empty = full + GS_STAGES;       // [GS_STAGES]  MMA -> TMA
   uint64_t* tmem_full = empty + GS_STAGES;  // [2]          MMA -> movers
   uint64_t* tmem_empty = tmem_full + 2;     // [2]          movers -> MMA
-  uint64_t* t_full = tmem_empty + 2;        // [2]          movers -> dot warps
-  uint64_t* t_empty = t_full + 2;           // [2]          dot warps -> movers
-  uint64_t* plan_full = t_empty + 2;        // [2]          movers -> dot warps
+  uint64_t* t_full = tmem_empty + 2;        // [T_SLOTS]    movers -> dot warps (and the gcol storer)
+  uint64_t* t_empty = t_full + T_SLOTS;     // [T_SLOTS]    dot warps (and the gcol storer) -> movers
+  uint64_t* plan_full = t_empty + T_SLOTS;  // [2]          movers -> dot warps
   uint64_t* plan_empty = plan_full + 2;     // [2]          dot warps -> movers
   uint64_t* om_full = plan_empty + 2;       // [GS_OM_SLOTS] TMA -> movers (offset / mask slabs)
   uint64_t* om_empty = om_full + GS_OM_SLOTS;
@@ -188,10 +195,12 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tmem_full[s], 1);
       ptx::mbar_init(&tmem_empty[s], ptx::arrivals(128));
-      ptx::mbar_init(&t_full[s], ptx::arrivals(128));
-      ptx::mbar_init(&t_empty[s], ptx::arrivals(GS_DOT_THREADS));
       ptx::mbar_init(&plan_full[s], ptx::arrivals(128));
       ptx::mbar_init(&plan_empty[s], ptx::arrivals(GS_DOT_THREADS));
+    }
+    for (int s = 0; s < T_SLOTS; ++s) {
+      ptx::mbar_init(&t_full[s], ptx::arrivals(128));
+      ptx::mbar_init(&t_empty[s], ptx::arrivals(GS_DOT_THREADS) + (prm.save_gcol ? 1u : 0u));   // (+ the gcol storer)
     }
     for (int s = 0; s < GS_OM_SLOTS; ++s) {
       ptx::mbar_init(&om_full[s], 1);
@@ -201,6 +210,7 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
       ptx::prefetch_tensormap(&tmap_off);
       if (MOD) ptx::prefetch_tensormap(&tmap_mask);
     }
+    if (prm.save_gcol) ptx::prefetch_tensormap(&tmap_gcol);
     ptx::fence_barrier_init();
   }
   if (warp == 2) ptx::tmem_alloc<512>(tmem_ptr);
@@ -235,7 +245,7 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
         if (new_tile) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            const int pb = 2 * t + h;
+            const int pb = prm.pb_base + 2 * t + h;
             pb_b[h] = pb < prm.total_pb ? pb / prm.pbi : g.B;  // b == B: fully out of bounds -> zero fill
             pb_p0[h] = pb < prm.total_pb ? (pb % prm.pbi) * 64 : 0;
           }
@@ -310,6 +320,55 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
         }
       }
     }
+  } else if (warp == 2) {
+    // ===================== gcol storer =====================
+    // grad_columns for the col2im gather of grad_input (reference src/mdeformable_conv.cu:396-419 materialises the
+    // same buffer through a GEMM): every [128 positions x 64 channels] block the movers lay out for the dot warps also
+    // leaves for HBM, straight from that shared-memory tile by TMA (two 64-position boxes; rows past the end of a
+    // sample are clipped by the tensor map).  The storer is one more reader of the T ring.
+    if (lane == 0 && prm.save_gcol && !F32) {
+      int ts = 0, prev = -1;                    // prev: slot whose store may still be reading shared memory
+      const uint64_t pol = ptx::l2_policy_evict_first();   // a write-once stream: it should not displace the operands
+      uint32_t tph = 0;
+      int t = t_first, phs = phs_first;
+      for (int it = 0; it < n_items; ++it) {
+        const int dgi = phs / g.K, tap = phs - dgi * g.K;
+        int sb[2], sp0[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int pb = prm.pb_base + 2 * t + h;
+          sb[h] = pb < prm.total_pb ? pb / prm.pbi - prm.pb_base / prm.pbi : -1;   // sample inside this launch's buffer
+          sp0[h] = pb < prm.total_pb ? (pb % prm.pbi) * 64 : 0;
+        }
+        for (int sub = 0; sub < nsub; ++sub) {
+          for (int j = 0; j < nb; ++j) {
+            const int col = tap * g.C + (dgi * bpd + sub * nb + j) * 64;
+            ptx::mbar_wait(&t_full[ts], tph);
+            const uint8_t* src = sT + ts * T_BYTES;
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#ifdef MDCONV_EXP_NOSTORE   // timing experiment only (wrong grad_input): the ring protocol without the stores
+              if (false) ptx::tma_store_3d_hint(&tmap_gcol, src + h * 8192, col, sp0[h], sb[h], pol);
+#else
+              if (sb[h] >= 0) ptx::tma_store_3d_hint(&tmap_gcol, src + h * 8192, col, sp0[h], sb[h], pol);
+#endif
+            ptx::bulk_commit_group();
+            if (prev >= 0) {                    // the store before this one has read its tile: the movers may overwrite it
+              ptx::bulk_wait_group_read<1>();
+              ptx::mbar_arrive(&t_empty[prev]);
+            }
+            prev = ts;
+            if (++ts == T_SLOTS) { ts = 0; tph ^= 1; }
+          }
+        }
+        if (++phs == phases) { phs = 0; ++t; }
+      }
+      if (prev >= 0) {
+        ptx::bulk_wait_group_read<0>();
+        ptx::mbar_arrive(&t_empty[prev]);
+      }
+      ptx::bulk_wait_group<0>();                // all stores complete before the CTA retires
+    }
   } else if (warp == 3) {
     // ===================== TMA producer: offset / mask slabs =====================
     if (lane == 0 && prm.om_tma) {
@@ -323,7 +382,7 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
         uint8_t* slot = sOM + os * gs_om_slot_bytes<ND>();
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const int pb = 2 * t + h;
+          const int pb = prm.pb_base + 2 * t + h;
           const int b = pb < prm.total_pb ? pb / prm.pbi : g.B;        // b == B: out of bounds -> zero fill
           const int p0 = pb < prm.total_pb ? (pb % prm.pbi) * 64 : 0;
           uint8_t* dst = slot + h * (ND + 1) * GS_OM_ROW_BYTES;
@@ -351,7 +410,7 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
     RowCoord<ND> rc;
     for (int it = 0; it < n_items; ++it) {
       if (new_tile) {
-        const int pb = 2 * t + (row >> 6);
+        const int pb = prm.pb_base + 2 * t + (row >> 6);
         const int p = (pb % prm.pbi) * 64 + (row & 63);
         valid = pb < prm.total_pb && p < g.P;
         decode_row<ND>(g, valid ? pb / prm.pbi : 0, p, valid, rc);
@@ -447,8 +506,9 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
                 sts128(tb + sw128(row, hlf * 4 + q), o);
               }
             }
+            if (prm.save_gcol) ptx::fence_proxy_async_smem();   // the TMA store reads the tile through the async proxy
             ptx::mbar_arrive_warp(&t_full[ts]);
-            if (++ts == 2) { ts = 0; tph ^= 1; }
+            if (++ts == T_SLOTS) { ts = 0; tph ^= 1; }
           }
           ptx::tc_fence_before_sync();
           ptx::mbar_arrive_warp(&tmem_empty[as]);
@@ -532,7 +592,7 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
               }
             }
             ptx::mbar_arrive_warp(&t_empty[ts]);
-            if (++ts == 2) { ts = 0; tph ^= 1; }
+            if (++ts == T_SLOTS) { ts = 0; tph ^= 1; }
           }
         }
         auto load_row = [&](int blk, int i, uint4 (&v)[NC], uint32_t after = 0u) {
@@ -564,7 +624,7 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
               for (int c = 0; c < NC; ++c) S[1][c] += dot8(gc, vb[c], T());
             }
             ptx::mbar_arrive_warp(&t_empty[ts]);
-            if (++ts == 2) { ts = 0; tph ^= 1; }
+            if (++ts == T_SLOTS) { ts = 0; tph ^= 1; }
           }
         } else {
           // 3D: 8 corners per row -- the rolling form needs more live registers than the dot warps have (it
@@ -582,7 +642,7 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
               for (int c = 0; c < NC; ++c) S[i][c] += dot8(gc, xv[i][c], T());
             }
             ptx::mbar_arrive_warp(&t_empty[ts]);
-            if (++ts == 2) { ts = 0; tph ^= 1; }
+            if (++ts == T_SLOTS) { ts = 0; tph ^= 1; }
           }
         }
         // ---- reduce over the 8 lanes of each row, combine, store ----
@@ -620,7 +680,7 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
             flags = tail2.x;
           }
           if (flags & 2u) {
-            const int pb = 2 * t + (row >> 6);
+            const int pb = prm.pb_base + 2 * t + (row >> 6);
             const int b = pb / prm.pbi;
             const int p = (pb % prm.pbi) * 64 + (row & 63);
             float gm = 0.f;
@@ -663,13 +723,14 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
 
 template <typename T, int ND>
 size_t gs_smem_bytes() {
-  return 1024 + (size_t)GS_STAGES * (GsCfg<T>::A_STAGE + GS_B_BYTES) + 2 * GsCfg<T>::T_BYTES +
+  return 1024 + (size_t)GS_STAGES * (GsCfg<T>::A_STAGE + GS_B_BYTES) + GsCfg<T>::T_SLOTS * GsCfg<T>::T_BYTES +
          2 * 128 * sizeof(SampleEntry<ND>) +
-         (2 * GS_STAGES + 12 + 2 * GS_OM_SLOTS) * sizeof(uint64_t) + 160 + (size_t)GS_OM_SLOTS * gs_om_slot_bytes<ND>();
+         (2 * GS_STAGES + 8 + 2 * GsCfg<T>::T_SLOTS + 2 * GS_OM_SLOTS) * sizeof(uint64_t) + 160 + (size_t)GS_OM_SLOTS * gs_om_slot_bytes<ND>();
 }
 
 struct GsMaps {
   CUtensorMap go, w, off, mask, go2, w2;   // go2 / w2: the "lo" halves of fp32 callers
+  CUtensorMap gcol;                        // grad_columns [B][P][K*C] (save_gcol)
 };
 template <typename T, int ND, bool MOD>
 void launch_grad_sample(const GsMaps& m, const TcGsParams& prm, LaunchCtx& ctx) {
@@ -679,7 +740,8 @@ void launch_grad_sample(const GsMaps& m, const TcGsParams& prm, LaunchCtx& ctx) 
   const int sms = sm_count() - ctx.spare_sms > 0 ? sm_count() - ctx.spare_sms : 1;
   const int grid = prm.items < sms ? (int)prm.items : sms;
   ProfScope prof(ctx, "tc_grad_sample");
-  k_tc_grad_sample<T, ND, MOD><<<grid, GS_THREADS, smem, ctx.stream>>>(m.go, m.w, m.off, m.mask, m.go2, m.w2, prm);
+  k_tc_grad_sample<T, ND, MOD><<<grid, GS_THREADS, smem, ctx.stream>>>(m.go, m.w, m.off, m.mask, m.go2, m.w2, m.gcol,
+                                                                       prm);
   MDCONV_CHECK_LAUNCH(ctx);
 }
 
@@ -691,10 +753,12 @@ bool grad_sample_supported(const DevGeom& g) {
 
 // xt: channels-last input; wr: weight re-ordered to [Co][(channel-block, tap, 64 channels)] (fp32 callers: the bf16
 // hi bank followed by the lo bank); go: grad_output rows [B][Co][go_ld] (go_ld = P, or P rounded up to 8 elements for
-// the padded copy; fp32 callers: the bf16 hi copy, go_lo the lo copy).
+// the padded copy; fp32 callers: the bf16 hi copy, go_lo the lo copy).  One launch covers samples [sample0, sample0 +
+// samples); gcol (16-bit callers, may be NULL) receives their grad_columns as [samples][P][K*C].
 template <typename T>
 void tensor_grad_sample(const DevGeom& g, const T* xt, const void* wr, const void* off, const void* mask, const void* go,
-                        const void* go_lo, int go_ld, void* goff, void* gmask, LaunchCtx& ctx) {
+                        const void* go_lo, int go_ld, void* goff, void* gmask, void* gcol, int sample0, int samples,
+                        LaunchCtx& ctx) {
   constexpr bool F32 = std::is_same<T, float>::value;
   using E = typename std::conditional<F32, __nv_bfloat16, T>::type;   // element type of the TMA-read operands
   TcGsParams prm;
@@ -708,8 +772,9 @@ void tensor_grad_sample(const DevGeom& g, const T* xt, const void* wr, const voi
   prm.nsub = bpd / nb;
   prm.kblocks = g.Cog / GS_KCO;
   prm.pbi = (g.P + 63) / 64;
-  prm.total_pb = g.B * prm.pbi;
-  prm.m_tiles = (prm.total_pb + 1) / 2;
+  prm.pb_base = sample0 * prm.pbi;
+  prm.total_pb = (sample0 + samples) * prm.pbi;
+  prm.m_tiles = (prm.total_pb - prm.pb_base + 1) / 2;
   prm.items = (long long)prm.m_tiles * g.dg * g.K;
 
   PFN_encodeTiled enc = get_encode_fn();
@@ -764,6 +829,19 @@ void tensor_grad_sample(const DevGeom& g, const T* xt, const void* wr, const voi
     }
     if (r != CUDA_SUCCESS) prm.om_tma = 0;   // fall back to global loads
   }
+  // grad_columns [B][P][K*C] in the storage dtype: boxes of 64 positions x 64 channels, written from the swizzled T tile
+  prm.save_gcol = (gcol != nullptr && !F32) ? 1 : 0;
+  if (prm.save_gcol) {
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const cuuint64_t cdims[3] = {(cuuint64_t)g.K * g.C, (cuuint64_t)g.P, (cuuint64_t)samples};
+    const cuuint64_t cstr[2] = {(cuuint64_t)g.K * g.C * sizeof(T), (cuuint64_t)g.P * g.K * g.C * sizeof(T)};
+    const cuuint32_t cbox[3] = {64, 64, 1};
+    if (enc(&m.gcol, tmap_dtype<E>(), 3, gcol, cdims, cstr, cbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+      if (ctx.err == cudaSuccess) ctx.err = cudaErrorInvalidValue;
+      return;
+    }
+  }
   if (g.nd == 2) {
     if (g.modulated) launch_grad_sample<T, 2, true>(m, prm, ctx);
     else launch_grad_sample<T, 2, false>(m, prm, ctx);
@@ -774,11 +852,12 @@ void tensor_grad_sample(const DevGeom& g, const T* xt, const void* wr, const voi
 }
 
 template void tensor_grad_sample<__half>(const DevGeom&, const __half*, const void*, const void*, const void*,
-                                         const void*, const void*, int, void*, void*, LaunchCtx&);
+                                         const void*, const void*, int, void*, void*, void*, int, int, LaunchCtx&);
 template void tensor_grad_sample<__nv_bfloat16>(const DevGeom&, const __nv_bfloat16*, const void*, const void*,
-                                                const void*, const void*, const void*, int, void*, void*, LaunchCtx&);
+                                                const void*, const void*, const void*, int, void*, void*, void*, int, int,
+                                                LaunchCtx&);
 template void tensor_grad_sample<float>(const DevGeom&, const float*, const void*, const void*, const void*,
-                                        const void*, const void*, int, void*, void*, LaunchCtx&);
+                                        const void*, const void*, int, void*, void*, void*, int, int, LaunchCtx&);
 
 }  // namespace tc
 }  // namespace mdconv

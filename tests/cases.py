@@ -127,10 +127,13 @@ TENSOR_CASES = [
     Case("tc_m2d_co32", 2, True, B=2, C=64, Co=32, size=(8, 8), seed=77),
     # ragged tails: B*P not a multiple of the 128-row tile, P not a multiple of 64
     Case("tc_m2d_ragged", 2, True, B=3, C=64, Co=64, size=(10, 12), seed=78),
+    Case("tc_m2d_ragged_3chunks", 2, True, B=3, C=128, Co=64, size=(22, 19), seed=86),   # P = 418: not a multiple of 8
     Case("tc_m2d_sigma8", 2, True, B=1, C=64, Co=64, size=(16, 16), sigma=8.0, seed=79),
     # more than one output-channel tile (Co = 512 > 256) and eight channel blocks (C = 512)
     Case("tc_m2d_co512", 2, True, B=1, C=64, Co=512, size=(8, 8), seed=81),
     Case("tc_d2d_c512_dg2", 2, False, B=1, C=512, Co=64, size=(8, 8), dg=2, seed=82),
+    # 1024 input channels: two 512-channel slabs per position tile in the col2im gather of grad_input
+    Case("tc_m2d_c1024_slabs", 2, True, B=2, C=1024, Co=64, size=(6, 7), dg=2, seed=85),
     # 1x1 kernel with stride 2 (a single tap), and a 5x5 kernel (25 taps, dilation 1, pad 2)
     Case("tc_m2d_k1_s2", 2, True, B=2, C=64, Co=64, size=(9, 10), k=(1, 1), s=(2, 2), p=(0, 0), seed=83),
     Case("tc_m2d_k5", 2, True, B=1, C=64, Co=64, size=(8, 8), k=(5, 5), p=(2, 2), seed=84),

@@ -206,6 +206,53 @@ def test_tensor_path_matches_oracle(case, dtype):
     _compare(ours, _oracle(case, t), TOL[dtype], f"{case.name}/{dtype} (bwd path {bwd})")
 
 
+def _data_grad_kernels(case, t, budget_mb=None):
+    """Run one forced-tensor-path fwd+bwd with kernel profiling on -> (results, launched kernel names)."""
+    import MDCONV_CUDA
+    prev = None if budget_mb is None else MDCONV_CUDA.set_gcol_budget_mb(budget_mb)
+    MDCONV_CUDA.profile_enable(True)
+    try:
+        ours = _run_ours(case, t, fwd_path=2, bwd_path=2)
+        names = [n for n, _ in MDCONV_CUDA.profile_read()]
+    finally:
+        MDCONV_CUDA.profile_enable(False)
+        MDCONV_CUDA.set_path(0)
+        if prev is not None:
+            MDCONV_CUDA.set_gcol_budget_mb(prev if prev >= 0 else 1024)
+    return ours, names
+
+
+_GCOL_CASES = ["tc_m2d_c64", "tc_m2d_stride2_dg2", "tc_m2d_g4_dg2", "tc_d2d_c192_dg3", "tc_m2d_c256_multi_tile",
+               "tc_m2d_ragged", "tc_m2d_ragged_3chunks", "tc_d2d_c512_dg2", "tc_m2d_c1024_slabs", "tc_m3d_dg2_stride2", "tc_m2d_all_oob"]
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16], ids=["f16", "bf16"])
+@pytest.mark.parametrize("name", _GCOL_CASES)
+def test_grad_input_paths_col2im_gather_and_contraction(name, dtype):
+    """16-bit grad_input has two routes over the same inverse index: the default col2im GATHER over the grad_columns
+    k_tc_grad_sample streams out (reference src/mdeformable_conv.cu:282-293 + :396-419), and the third contraction
+    (k_tc_grad_input, budget 0).  Both must hold the oracle's bar, and the chunked gather (a budget of 1 MiB: one
+    sample per (grad_sample, gather) pair) must reproduce the one-pass gather bit for bit."""
+    case = {c.name: c for c in TENSOR_CASES}[name]
+    t = make_inputs(case, dtype)
+    ref = _oracle(case, t)
+    one, names = _data_grad_kernels(case, t, budget_mb=1024)
+    assert "col2im_gather" in names and "tc_grad_input" not in names, names
+    assert names.count("col2im_gather") == 1 and names.count("tc_grad_sample") == 1, names
+    assert "transpose_weight" not in names, names          # no transposed filter bank, no channels-last grad_output
+    _compare(one, ref, TOL[dtype], f"{name}/{dtype} col2im gather")
+    chunked, names_c = _data_grad_kernels(case, t, budget_mb=1)
+    per_sample = case.taps * case.C * 2 * int(np.prod(case.out_size))      # bytes of one sample's grad_columns
+    step = min(case.B, max(1, 2 ** 20 // per_sample))
+    chunks = -(-case.B // step)
+    assert names_c.count("col2im_gather") == chunks == names_c.count("tc_grad_sample"), (names_c, chunks)
+    for k in one:
+        assert np.array_equal(one[k], chunked[k]), f"{name}: chunked gather changed {k}"
+    old, names_o = _data_grad_kernels(case, t, budget_mb=0)
+    assert "tc_grad_input" in names_o and "col2im_gather" not in names_o, names_o
+    _compare(old, ref, TOL[dtype], f"{name}/{dtype} contraction")
+
+
 @pytest.mark.parametrize("case", TENSOR_CASES, ids=lambda c: c.name)
 def test_fp32_tensor_path_matches_oracle(case):
     """fp32 on the tensor cores (operands split into bf16 hi / lo, three products per K step, fp32 accumulation):

@@ -101,7 +101,8 @@ def test_second_device_in_the_same_process():
 @pytest.mark.parametrize("hw", [(14, 14), (7, 7), (9, 5)], ids=["14x14", "7x7", "9x5"])
 def test_tensor_backward_takes_maps_with_any_position_count(hw):
     """Output maps whose position count is not a multiple of 8 (14x14 -> 196, 7x7 -> 49, 9x5 -> 45) stay on the
-    tcgen05 backward (grad_weight / grad_sample / grad_input), and match the oracle."""
+    tcgen05 backward (grad_weight / grad_sample, grad_input as the col2im gather over grad_sample's grad_columns), and
+    match the oracle."""
     import ctypes
     import MDCONV_CUDA as M
     case = Case(f"p_{hw[0]}x{hw[1]}", 2, True, B=3, C=64, Co=64, size=hw, seed=304)
@@ -115,7 +116,8 @@ def test_tensor_backward_takes_maps_with_any_position_count(hw):
         names = {n for n, _ in M.profile_read()}
     finally:
         M.profile_enable(False)
-    assert {"tc_forward", "tc_grad_weight", "tc_grad_sample", "tc_grad_input"} <= names, names
+    assert {"tc_forward", "tc_grad_weight", "tc_grad_sample", "col2im_gather"} <= names, names
+    assert "generic_bwd_data" not in names, names
     ref = _oracle(case, t)
     for k, r in ref.items():
         assert rel_err(out[k], r) < 1e-2, (k, rel_err(out[k], r))
