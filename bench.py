@@ -632,6 +632,23 @@ def main():
         dur = v / max(1, calls[k]) * 1e-3
         roofline_kernels[k] = {"launch_ms": dur * 1e3, "tflops": gemm_kernels[k] / dur / 1e12,
                                "frac_of_tensor_peak": gemm_kernels[k] / dur / 1e12 / tpeak}
+    if "col2im_gather" in kernels:
+        # grad_input as a gather over grad_columns (HBM / L1-bound, no contraction): bytes it must move once --
+        # grad_columns (B*P*K*C), the inverse-index entries (8 bytes per corner) and grad_input itself
+        P_out = 1
+        for o in out_size(w):
+            P_out *= o
+        n_in = 1
+        for o in w["size"]:
+            n_in *= o
+        taps = 1
+        for o in w["k"]:
+            taps *= o
+        gbytes = B * P_out * taps * w["C"] * es + 8 * B * w["dg"] * taps * P_out * (2 ** w["nd"]) + B * w["C"] * n_in * es
+        dur = kernels["col2im_gather"] / max(1, calls["col2im_gather"]) * 1e-3
+        roofline_kernels["col2im_gather"] = {"launch_ms": dur * 1e3, "bound": "hbm", "algorithmic_bytes": gbytes,
+                                             "gbs": gbytes / dur / 1e9, "frac_of_hbm_peak": gbytes / dur / 1e9 / peaks["hbm_gbs"],
+                                             "traffic": traffic.get("col2im_gather")}
     if dom is not None and tensor_path:
         dur = kernels[dom] / max(1, calls[dom]) * 1e-3
         ach = gemm_kernels.get(dom, flops_fwd) / dur / 1e12

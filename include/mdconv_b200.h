@@ -217,7 +217,7 @@ int mdconv_set_comm_sms(int sms);
  * environment does the same.  Returns the previous setting. */
 int mdconv_set_fp32_tensor_cores(int on);
 
-/* grad_input of 16-bit calls is a col2im GATHER over grad_columns ([samples][P][K*C] in the storage dtype -- the
+/* grad_input of 16-bit calls is a col2im GATHER over grad_columns ([samples][K][P][C] in the storage dtype -- the
  * reference's own buffer, src/mdeformable_conv.cu:396-419) that the grad_offset / grad_mask kernel streams out on its
  * way; the buffer is part of the backward workspace mdconv_workspace_bytes() reports.  `megabytes` (default 1024, or
  * MDCONV_B200_GCOL_MAX_MB) caps it: a batch whose grad_columns are larger is walked in chunks of whole samples that

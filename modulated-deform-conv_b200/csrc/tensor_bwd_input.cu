@@ -102,7 +102,7 @@ struct BinEntry {
 // of each bin; FILL == true: place them (slot taken from the remaining count).
 // pos_major: the layout the col2im gather reads -- the K bins of one input position are neighbours (bin =
 // ((sample, deformable group), input position, tap)), so its entries of ALL taps are one contiguous run, and an entry
-// is ready to use: `row` = element offset of the grad_columns block it scales, ((b * P + output position) * K + tap) * C,
+// is ready to use: `row` = element offset of the grad_columns block it scales, ((b * K + tap) * P + output position) * C,
 // `w` = the weight as a packed pair in the storage dtype.  Otherwise tap-major (bin = ((sample, deformable group),
 // tap, input position), row = b * P + output position, fp32 weight), what k_tc_grad_input walks.
 __device__ __forceinline__ float pack_weight(float w, __half) {
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(256) k_bin_entries(const DevGeom g, const T* _
       for (int c = 0; c < (1 << ND); ++c) {
         if (okc[c]) {
           BinEntry e;
-          e.row = pos_major ? ((b * g.P + p) * g.K + tap) * g.C : b * g.P + p;
+          e.row = pos_major ? ((b * g.K + tap) * g.P + p) * g.C : b * g.P + p;
           e.w = pos_major ? pack_weight(wgt[c], T()) : wgt[c];
           entries[slot[c]] = e;
         }
@@ -358,7 +358,7 @@ template <> struct Acc8<float> {   // placeholder: the fp32 gather has its own a
 
 // ---- grad_input as a col2im GATHER over grad_columns (16-bit callers, default) --------------------
 // k_tc_grad_sample already holds gcol[pos, (tap, c)] = sum_co go[pos, co] * W[co, c, tap] block by block in shared
-// memory for its dot products; with save_gcol it also streams those blocks to HBM ([B][P][K*C], the reference's
+// memory for its dot products; with save_gcol it also streams those blocks to HBM ([samples][K][P][C], the reference's
 // grad_columns buffer, src/mdeformable_conv.cu:396-419).  grad_input is then
 //     gx[ipos, c] = sum over taps, over the entries e of bin (sample, deformable group of c, tap, ipos):  w_e * gcol[row_e, (tap, c)]
 // -- the reference's col2im (:282-293) read through the inverse index instead of scattered with atomics: no third
@@ -459,18 +459,33 @@ __global__ void __launch_bounds__(C2I_THREADS, C2I_MINB) k_col2im_gather(const D
     const int ldt = cs + 8;                       // padded row of the staging tile (elements)
     const int CH = cs >> 3;                       // 8-channel chunks per position
     const int items = tile_pos * CH;              // (position, chunk) pairs per tile
+    // bounds [e0, e1) of a (position, chunk) pair's run of entries: position-major bins, so the entries of all K taps
+    // of the input position are contiguous (~4 * K of them)
+    auto run_bounds = [&](int it, int& e0, int& e1) {
+      const int chunk = it % CH, pl = it / CH;
+      const long long gpos = pos0 + pl;
+      e0 = 0; e1 = 0;
+      if (it < items && gpos < total_pos) {
+        const int b = (int)(gpos / g.IN), ipos = (int)(gpos - (long long)b * g.IN);
+        const int dgi = (c_base + chunk * 8) / g.Cdg;
+        const size_t bin0 = (((size_t)b * g.dg + dgi) * g.IN + ipos) * g.K;
+        e0 = __ldg(bin_start + bin0);
+        e1 = __ldg(bin_start + bin0 + g.K);
+      }
+    };
+    int e0, e1;
+    run_bounds(threadIdx.x, e0, e1);
     for (int it = threadIdx.x; it < items; it += C2I_THREADS) {
       const int chunk = it % CH, pl = it / CH;    // a warp = consecutive chunks of one position (>= 256 channels), or of a few
       const long long gpos = pos0 + pl;
+      // the bounds of this thread's NEXT pair are fetched now, and the head of its run is pulled into L1 once they
+      // are here, so the next pair starts on its grad_columns loads instead of behind three dependent misses
+      int n0, n1;
+      run_bounds(it + C2I_THREADS, n0, n1);
       float acc[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-      if (gpos < total_pos) {
-        const int b = (int)(gpos / g.IN), ipos = (int)(gpos - (long long)b * g.IN);
-        const int dgi = (c_base + chunk * 8) / g.Cdg;
-        // position-major bins: the entries of all K taps of this input position are one run [e0, e1) (~4 * K long)
-        const size_t bin0 = (((size_t)b * g.dg + dgi) * g.IN + ipos) * g.K;
-        const int e0 = __ldg(bin_start + bin0), e1 = __ldg(bin_start + bin0 + g.K);
+      {
         const T* colc = gcol + c_base + chunk * 8;   // an entry's block: colc + entry.x
         // C2I_B entries at a time: their (L1-resident) records, then their grad_columns vectors all in flight
         // together; the products of a batch are summed in packed pairs of the storage dtype, as the gather of
@@ -485,6 +500,10 @@ __global__ void __launch_bounds__(C2I_THREADS, C2I_MINB) k_col2im_gather(const D
           for (int k = 0; k < C2I_B; ++k) v[k] = __ldg(reinterpret_cast<const uint4*>(colc + ee[k].x));
           c2i_flush_t(acc, c2i_batch<C2I_B>(v, ee, T()), T());
         }
+        if (n1 > n0) {
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(ent2 + n0));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(ent2 + n0 + 16));
+        }
         if (e < e1) {                             // the last, partial batch
           int2 ee[C2I_B];
           uint4 v[C2I_B];
@@ -495,6 +514,7 @@ __global__ void __launch_bounds__(C2I_THREADS, C2I_MINB) k_col2im_gather(const D
           c2i_flush_t(acc, c2i_batch<C2I_B>(v, ee, T()), T());
         }
       }
+      e0 = n0; e1 = n1;
       const uint4 out = c2i_pack(acc, T());
       if (CL) {
         if (gpos < total_pos) *reinterpret_cast<uint4*>(gx + (size_t)gpos * g.C + c_base + chunk * 8) = out;
@@ -1030,7 +1050,7 @@ static size_t got_bytes(const DevGeom& g) { return g.cl ? 0 : align256((size_t)g
 static size_t wt_bytes(const DevGeom& g) { return align256((size_t)g.Co * g.Kg * 2) * (g.esize == 4 ? 2 : 1); }
 
 // ---- col2im-gather path ---------------------------------------------------------------------------
-// grad_columns ([samples][P][K*C], storage dtype) live in ONE workspace buffer capped by the budget
+// grad_columns ([samples][K][P][C], storage dtype) live in ONE workspace buffer capped by the budget
 // (MDCONV_B200_GCOL_MAX_MB / mdconv_set_gcol_budget_mb(), default 1024 MiB).  A batch that fits goes through in one
 // (k_tc_grad_sample, k_col2im_gather) pair; a larger one is walked in chunks of whole samples that fit, re-using the
 // buffer (measured at cfg2: 4 / 8 chunks cost +9 % / +27 % of the pair -- smaller launches fill the machine worse, and

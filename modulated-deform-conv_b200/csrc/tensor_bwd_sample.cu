@@ -111,7 +111,7 @@ struct TcGsParams {
   long long items;   // m_tiles * dg * K (tile, phase) work items, split evenly over the CTAs
   int om_tma;        // 1: offset / mask slabs come by TMA (needs P % 8 == 0: 16-byte global strides), 0: global loads
   int zero;          // always 0 at run time (tc::drain_point)
-  int save_gcol;     // 1: every gcol block also goes to HBM ([B][P][K*C], tmap_gcol) for the col2im gather of grad_input
+  int save_gcol;     // 1: every gcol block also goes to HBM ([samples][K][P][C], tmap_gcol) for the col2im gather of grad_input
 };
 
 // dot product of two 8-element vectors stored in the tensor dtype
@@ -342,15 +342,15 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
         }
         for (int sub = 0; sub < nsub; ++sub) {
           for (int j = 0; j < nb; ++j) {
-            const int col = tap * g.C + (dgi * bpd + sub * nb + j) * 64;
+            const int c0 = (dgi * bpd + sub * nb + j) * 64;   // grad_columns plane of this tap: [P][C]
             ptx::mbar_wait(&t_full[ts], tph);
             const uint8_t* src = sT + ts * T_BYTES;
 #pragma unroll
             for (int h = 0; h < 2; ++h)
 #ifdef MDCONV_EXP_NOSTORE   // timing experiment only (wrong grad_input): the ring protocol without the stores
-              if (false) ptx::tma_store_3d_hint(&tmap_gcol, src + h * 8192, col, sp0[h], sb[h], pol);
+              if (false) ptx::tma_store_4d_hint(&tmap_gcol, src + h * 8192, c0, sp0[h], tap, sb[h], pol);
 #else
-              if (sb[h] >= 0) ptx::tma_store_3d_hint(&tmap_gcol, src + h * 8192, col, sp0[h], sb[h], pol);
+              if (sb[h] >= 0) ptx::tma_store_4d_hint(&tmap_gcol, src + h * 8192, c0, sp0[h], tap, sb[h], pol);
 #endif
             ptx::bulk_commit_group();
             if (prev >= 0) {                    // the store before this one has read its tile: the movers may overwrite it
@@ -730,7 +730,7 @@ size_t gs_smem_bytes() {
 
 struct GsMaps {
   CUtensorMap go, w, off, mask, go2, w2;   // go2 / w2: the "lo" halves of fp32 callers
-  CUtensorMap gcol;                        // grad_columns [B][P][K*C] (save_gcol)
+  CUtensorMap gcol;                        // grad_columns [samples][K][P][C] (save_gcol)
 };
 template <typename T, int ND, bool MOD>
 void launch_grad_sample(const GsMaps& m, const TcGsParams& prm, LaunchCtx& ctx) {
@@ -754,7 +754,7 @@ bool grad_sample_supported(const DevGeom& g) {
 // xt: channels-last input; wr: weight re-ordered to [Co][(channel-block, tap, 64 channels)] (fp32 callers: the bf16
 // hi bank followed by the lo bank); go: grad_output rows [B][Co][go_ld] (go_ld = P, or P rounded up to 8 elements for
 // the padded copy; fp32 callers: the bf16 hi copy, go_lo the lo copy).  One launch covers samples [sample0, sample0 +
-// samples); gcol (16-bit callers, may be NULL) receives their grad_columns as [samples][P][K*C].
+// samples); gcol (16-bit callers, may be NULL) receives their grad_columns as [samples][K][P][C].
 template <typename T>
 void tensor_grad_sample(const DevGeom& g, const T* xt, const void* wr, const void* off, const void* mask, const void* go,
                         const void* go_lo, int go_ld, void* goff, void* gmask, void* gcol, int sample0, int samples,
@@ -829,14 +829,17 @@ void tensor_grad_sample(const DevGeom& g, const T* xt, const void* wr, const voi
     }
     if (r != CUDA_SUCCESS) prm.om_tma = 0;   // fall back to global loads
   }
-  // grad_columns [B][P][K*C] in the storage dtype: boxes of 64 positions x 64 channels, written from the swizzled T tile
+  // grad_columns [samples][K][P][C] in the storage dtype (one [P][C] plane per tap: neighbouring positions of a tap
+  // are neighbouring 2*C-byte rows, for the stores here and for the gather that follows): boxes of 64 positions x 64
+  // channels, written from the swizzled T tile
   prm.save_gcol = (gcol != nullptr && !F32) ? 1 : 0;
   if (prm.save_gcol) {
-    const cuuint32_t estr[3] = {1, 1, 1};
-    const cuuint64_t cdims[3] = {(cuuint64_t)g.K * g.C, (cuuint64_t)g.P, (cuuint64_t)samples};
-    const cuuint64_t cstr[2] = {(cuuint64_t)g.K * g.C * sizeof(T), (cuuint64_t)g.P * g.K * g.C * sizeof(T)};
-    const cuuint32_t cbox[3] = {64, 64, 1};
-    if (enc(&m.gcol, tmap_dtype<E>(), 3, gcol, cdims, cstr, cbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const cuuint64_t cdims[4] = {(cuuint64_t)g.C, (cuuint64_t)g.P, (cuuint64_t)g.K, (cuuint64_t)samples};
+    const cuuint64_t cstr[3] = {(cuuint64_t)g.C * sizeof(T), (cuuint64_t)g.P * g.C * sizeof(T),
+                                (cuuint64_t)g.K * g.P * g.C * sizeof(T)};
+    const cuuint32_t cbox[4] = {64, 64, 1, 1};
+    if (enc(&m.gcol, tmap_dtype<E>(), 4, gcol, cdims, cstr, cbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
       if (ctx.err == cudaSuccess) ctx.err = cudaErrorInvalidValue;
       return;

@@ -10,5 +10,5 @@ done
 timeout 300 python bench.py --channels-last --steps 20 --warmup 5 --no-cpu-baseline --no-ref-cuda > gpurun_out/bench_cfg2_cl_$TAG.json 2> gpurun_out/bench_cfg2_cl_$TAG.err; echo "bench channels-last rc=$?"
 timeout 300 python bench.py --steps 2000 --warmup 20 --no-cpu-baseline --no-ref-cuda > gpurun_out/bench_cfg2_sustained_$TAG.json 2> gpurun_out/bench_cfg2_sustained_$TAG.err; echo "bench sustained rc=$?"
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_smoke_$TAG.csv python __graft_entry__.py smoke > gpurun_out/ncu_smoke_$TAG.log 2>&1; echo "ncu smoke rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_tc_ -s 8 -c 4 -f -o gpurun_out/prof_$TAG python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-ref-cuda > gpurun_out/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:k_tc_|k_col2im" -s 8 -c 4 -f -o gpurun_out/prof_$TAG python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-ref-cuda > gpurun_out/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
 ls -la gpurun_out/prof_$TAG.ncu-rep

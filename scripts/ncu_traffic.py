@@ -9,7 +9,7 @@ hdr, units = rows[0], rows[1]
 ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
 scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 names = {"k_tc_forward": "tc_forward", "k_tc_grad_weight": "tc_grad_weight", "k_tc_grad_sample": "tc_grad_sample",
-         "k_tc_grad_input": "tc_grad_input", "k_generic_forward": "generic_forward",
+         "k_tc_grad_input": "tc_grad_input", "k_col2im_gather": "col2im_gather", "k_generic_forward": "generic_forward",
          "k_generic_bwd_data": "generic_bwd_data", "k_generic_bwd_weight": "generic_bwd_weight"}
 out = {}
 for r in rows[2:]:
