@@ -12,3 +12,4 @@ timeout 300 python bench.py --steps 2000 --warmup 20 --no-cpu-baseline --no-ref-
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_smoke_$TAG.csv python __graft_entry__.py smoke > gpurun_out/ncu_smoke_$TAG.log 2>&1; echo "ncu smoke rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k "regex:k_tc_|k_col2im" -s 8 -c 4 -f -o gpurun_out/prof_$TAG python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-ref-cuda > gpurun_out/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
 ls -la gpurun_out/prof_$TAG.ncu-rep
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:k_tc_|k_col2im" -s 8 -c 4 -f -o gpurun_out/prof_cfg4_$TAG python bench.py --workload cfg4 --steps 1 --warmup 3 --no-cpu-baseline --no-ref-cuda > gpurun_out/ncu_full_cfg4_$TAG.log 2>&1; echo "ncu full cfg4 rc=$?"
