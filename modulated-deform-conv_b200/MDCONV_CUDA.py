@@ -194,6 +194,31 @@ def _check(rc: int, what: str) -> None:
         raise RuntimeError(f"{what}: {msg}")
 
 
+def _raw_stream() -> int:
+    """cudaStream_t of the current device's current stream (the cheap form of torch.cuda.current_stream().cuda_stream:
+    this sits on the launch path of every call)."""
+    return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
+
+
+class _NoCtx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+_NO_CTX = _NoCtx()
+
+
+def _on_device(device):
+    """Context that makes ``device`` current -- nothing at all when it already is (the usual case: a device-guard
+    context manager costs ~10 us of host time per call)."""
+    if device.index is None or device.index == torch.cuda.current_device():
+        return _NO_CTX
+    return torch.cuda.device(device)
+
+
 def _ptr(t):
     return None if t is None or t.numel() == 0 else ctypes.c_void_p(t.data_ptr())
 
@@ -328,13 +353,13 @@ def _forward(input, weight, bias, offset, mask, output, kernel, stride, pad, dil
         _expect(mask, (input.shape[0], dgroup * K) + shape[2:], "mask")
     if with_bias:
         _expect(bias, (weight.shape[0],), "bias")
-    with torch.cuda.device(input.device):
+    with _on_device(input.device):
         if output is None:
             output = torch.empty(shape, dtype=input.dtype, device=input.device,
                                  memory_format=_cl_format(nd) if cl else torch.contiguous_format)
         else:
             _expect(output, shape, "output")
-        stream = torch.cuda.current_stream().cuda_stream
+        stream = _raw_stream()
         ex = None
         if prelaid is not None and not cl and prelaid.device == input.device and \
                 prelaid.numel() >= int(_lib.mdconv_workspace_bytes(ctypes.byref(g), 0)) > 0 and \
@@ -386,7 +411,7 @@ def _backward(input, weight, bias, offset, mask, grad_output, grads, kernel, str
     _validate(named, weight, kernel, group, nd, cl)
     g = _geom(input, weight, kernel, stride, pad, dil, group, dgroup, modulated, with_bias, cl)
     _expect(grad_output, _out_shape(g, input, weight), "grad_output")
-    with torch.cuda.device(input.device):
+    with _on_device(input.device):
         if grads is None:
             grads = {"grad_input": torch.empty_like(input, memory_format=torch.preserve_format),
                      "grad_offset": torch.empty_like(offset),
@@ -400,7 +425,7 @@ def _backward(input, weight, bias, offset, mask, grad_output, grads, kernel, str
             if modulated:
                 _expect(grads["grad_mask"], mask.shape, "grad_mask")
         ws, n = _workspace(g, True, input.device)
-        stream = torch.cuda.current_stream().cuda_stream
+        stream = _raw_stream()
         sv_ptr, sv_n = None, 0
         if saved is not None and saved[2] == g.path and saved[0].device == input.device and \
                 (len(saved) < 4 or saved[3] == cl) and int(_lib.mdconv_saved_bytes(ctypes.byref(g))) == saved[1]:
@@ -443,10 +468,10 @@ def to_channels_last(input, weight, kernel, stride, pad, dil, group, deformable_
               with_bias)
     if int(_lib.mdconv_channels_last_bytes(ctypes.byref(g))) == 0:
         return None
-    with torch.cuda.device(input.device):
+    with _on_device(input.device):
         ws, n = _workspace(g, False, input.device)
         rc = _lib.mdconv_to_channels_last(ctypes.byref(g), _ptr(input), _ptr(ws),
-                                          ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+                                          ctypes.c_void_p(_raw_stream()))
     _check(rc, "mdconv_to_channels_last")
     return ws
 
@@ -467,7 +492,7 @@ def producer_conv(input, weight, bias, n_first, kernel, stride, pad, prelaid=Non
     g = _geom(input, weight, kernel, stride, pad, (1,) * nd, 1, 1, False, True)
     g.path = 2
     shape = _out_shape(g, input, weight)
-    with torch.cuda.device(input.device):
+    with _on_device(input.device):
         out1 = torch.empty((shape[0], n_first) + shape[2:], dtype=input.dtype, device=input.device)
         out2 = torch.empty((shape[0], n - n_first) + shape[2:], dtype=input.dtype, device=input.device) \
             if n_first < n else None
@@ -485,7 +510,7 @@ def producer_conv(input, weight, bias, n_first, kernel, stride, pad, prelaid=Non
         ws = torch.empty(need, dtype=torch.uint8, device=input.device)
         rc = _lib.mdconv_forward_ex(ctypes.byref(g), _ptr(input), _ptr(weight), _ptr(bias), None, None, _ptr(out1),
                                     _ptr(ws), need, ctypes.byref(ex),
-                                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+                                    ctypes.c_void_p(_raw_stream()))
     _check(rc, "mdconv_forward_ex(regular_grid)")
     return out1, out2
 
