@@ -1,18 +1,26 @@
-// tensor_bwd_input.cu -- tcgen05 kernel for grad_input (fp16 / bf16), atomics-free.
+// tensor_bwd_input.cu -- grad_input, atomics-free, two routes over one inverse index.
 //
 // Reference: the col2im half of the fused gradient kernels (src/mdeformable_conv.cu:282-293 and
 // twins): one thread per column element, 4 (2D) / 8 (3D) atomicAdd into grad_input each, fed by a
 // materialised grad_columns buffer (G2, :417-419).
 //
 // Here the scatter is turned into a gather.  A small inverse index (CSR) is built per call:
-//     bin (sample, deformable group, tap, input position)  ->  list of (output position, weight)
-// with weight = interpolation weight x mask of the corner that touches that input position.  Then
+//     bin (sample, deformable group, input position, tap)  ->  list of (output position, weight)
+// with weight = interpolation weight x mask of the corner that touches that input position.
+//
+// Route 1 (16-bit callers, default): k_col2im_gather.  k_tc_grad_sample has streamed grad_columns
+//     gcol[pos, (tap, c)] = sum_co go[pos, co] * W[co, c, tap]
+// into the workspace; grad_input[ipos, c] = sum over the entries of ipos's bins of weight * gcol[entry, c] is a
+// plain gather-reduce (no contraction).  Bins are position-major here, so one input position owns one run of entries.
+//
+// Route 2 (fp32 callers, or a grad_columns budget of 0): k_tc_grad_input, a third contraction:
 //     G[pos, (tap, co)] = sum over the bin's entries of weight * go[entry position, co]
 //     grad_input[pos, c] = sum over (tap, co) of G[pos, (tap, co)] * W[co, c, tap]
 // is one implicit GEMM: G tiles are gathered straight into the swizzled UMMA A operand (never in
-// HBM), W^T slices come by TMA, the accumulator lives in TMEM and every grad_input element is
-// written exactly once (deterministic: bin entries are sorted).
+// HBM), W^T slices come by TMA, the accumulator lives in TMEM.  Bins are tap-major for this route.
+// Either way every grad_input element is written exactly once (deterministic: bin entries are sorted).
 //
+// Warp roles of k_tc_grad_input:
 //   warp 0      TMA producer: transposed-weight slices [BN channels x 64 co] -> smem ring
 //   warp 1      MMA issuer (M = 128 input positions, N = BN channels, K = 64 co per block)
 //   warp 2      TMEM allocator

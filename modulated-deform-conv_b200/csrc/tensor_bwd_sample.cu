@@ -9,8 +9,9 @@
 //         S_c[pos, tap] = sum_ch gcol[pos, (ch, tap)] * x[corner_c(pos, tap), ch]
 //         grad_mask     = sum_c w_c * S_c
 //         grad_offset_a = mask * sum_c (d w_c / d p_a) * S_c
-// so neither gcol nor the columns exist in HBM, there are no atomics, and every output element is
-// written exactly once in a fixed summation order (deterministic).
+// so the columns never exist in HBM, there are no atomics, and every output element is written exactly
+// once in a fixed summation order (deterministic).  gcol is consumed from shared memory here; for 16-bit
+// callers it is ALSO streamed to HBM once (the reference's grad_columns), for the col2im gather of grad_input.
 //
 // Work decomposition: one item = (tile of 128 positions, (deformable group, tap) phase); every phase writes its
 // own outputs, so the m_tiles * dg * K items are dealt to the persistent CTAs as equal contiguous ranges (a whole
@@ -19,7 +20,9 @@
 //   warp 0       TMA producer: grad_output tile (MN-major A operand, straight from NCHW) and weight
 //                slices (MN-major B operand), 32 output channels per K-block -> 4-slot smem ring
 //   warp 1       MMA issuer, M=128 positions x N=64*nb channels of one tap, K = output channels
-//   warp 2       TMEM allocator (2 accumulator stages x 256 columns)
+//   warp 2       TMEM allocator (2 accumulator stages x 256 columns); 16-bit callers: also the grad_columns storer
+//                (every [128 positions x 64 channels] block the movers lay out leaves for HBM by cp.async.bulk.tensor,
+//                what k_col2im_gather turns into grad_input: tensor_bwd_input.cu)
 //   warps 4-7    "movers": compute the per-(position, tap) sampling entry (corner indices, fractions,
 //                mask) for the next phase; tcgen05.ld the accumulator, round it to the storage dtype and
 //                re-lay it out in shared memory as [position][64 channels] (128B-swizzled rows)
