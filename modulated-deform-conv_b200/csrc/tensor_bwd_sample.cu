@@ -66,14 +66,16 @@ template <int ND> struct GsRegs {
 template <typename T> struct GsCfg {
   static constexpr bool F32 = false;
   static constexpr int A_STAGE = GS_A_BYTES, T_BYTES = GS_T_BYTES, MAX_NB = 4;
-  // slots of the T ring (accumulator blocks in shared memory): 4, so a block can wait for its grad_columns store
-  // (save_gcol: the TMA engine reads it ~1 us after the dot warps are done with it) without stalling the movers
-  static constexpr int T_SLOTS = 4;
+  // slots of the T ring (accumulator blocks in shared memory, 16 KB each): deep enough that a block can wait for its
+  // grad_columns store (save_gcol: the TMA engine reads it ~1 us after the dot warps are done with it) without stalling
+  // the movers.  Measured: 2D 3 / 4 / 5 / 6 / 7 / 8 slots = 287 / 283 / 277 / 274 / 277 / 277 us at cfg2; 3D wants the
+  // shared memory as L1 instead (4 / 5 / 6 / 8 slots = 603 / 618 / 617 / 632 us at cfg4)
+  static constexpr int t_slots(int nd) { return nd == 2 ? 6 : 4; }
 };
 template <> struct GsCfg<float> {
   static constexpr bool F32 = true;
   static constexpr int A_STAGE = 2 * GS_A_BYTES, T_BYTES = 2 * GS_T_BYTES, MAX_NB = 2;   // B stage: hi blocks, then lo
-  static constexpr int T_SLOTS = 2;
+  static constexpr int t_slots(int) { return 2; }
 };
 // byte offset of 16-byte chunk `c` (0..15) of row `row` in an fp32 T block: 256-byte rows, each 128-byte half
 // swizzled like sw128
@@ -162,7 +164,7 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
   constexpr bool F32 = GsCfg<T>::F32;
   constexpr int A_STAGE = GsCfg<T>::A_STAGE;
   constexpr int T_BYTES = GsCfg<T>::T_BYTES;
-  constexpr int T_SLOTS = GsCfg<T>::T_SLOTS;
+  constexpr int T_SLOTS = GsCfg<T>::t_slots(ND);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
@@ -726,9 +728,9 @@ k_tc_grad_sample(const __grid_constant__ CUtensorMap tmap_go, const __grid_const
 
 template <typename T, int ND>
 size_t gs_smem_bytes() {
-  return 1024 + (size_t)GS_STAGES * (GsCfg<T>::A_STAGE + GS_B_BYTES) + GsCfg<T>::T_SLOTS * GsCfg<T>::T_BYTES +
+  return 1024 + (size_t)GS_STAGES * (GsCfg<T>::A_STAGE + GS_B_BYTES) + GsCfg<T>::t_slots(ND) * GsCfg<T>::T_BYTES +
          2 * 128 * sizeof(SampleEntry<ND>) +
-         (2 * GS_STAGES + 8 + 2 * GsCfg<T>::T_SLOTS + 2 * GS_OM_SLOTS) * sizeof(uint64_t) + 160 + (size_t)GS_OM_SLOTS * gs_om_slot_bytes<ND>();
+         (2 * GS_STAGES + 8 + 2 * GsCfg<T>::t_slots(ND) + 2 * GS_OM_SLOTS) * sizeof(uint64_t) + 160 + (size_t)GS_OM_SLOTS * gs_om_slot_bytes<ND>();
 }
 
 struct GsMaps {
