@@ -1132,7 +1132,7 @@ void tensor_grad_input_from_gcol(const DevGeom& g, void* gx, void* ws, int sampl
     const long long pos_base = (long long)sample0 * g.IN, total_pos = (long long)(sample0 + samples) * g.IN;
     const int slabs = (g.C + C2I_CS - 1) / C2I_CS;
     const int cs = g.C < C2I_CS ? g.C : C2I_CS;
-    int tile_pos = (512 / (cs >> 3)) & ~7;          // ~512 (position, chunk) pairs per tile: two per thread
+    int tile_pos = (512 / (cs >> 3)) & ~7;          // ~512 (position, chunk) pairs per tile, two per thread (256 / 1024: +5 %)
     if (tile_pos < 8) tile_pos = 8;
     if (tile_pos > C2I_MAX_POS) tile_pos = C2I_MAX_POS;
     const int n_tiles = (int)((total_pos - pos_base + tile_pos - 1) / tile_pos) * slabs;
