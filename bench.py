@@ -459,6 +459,7 @@ def main():
     dbuf = [{k: torch.empty_like(host[k], device=dev) for k in keys} for _ in range(NBUF)]
     ev_h2d = [torch.cuda.Event() for _ in range(NBUF)]
     ev_comp = [torch.cuda.Event() for _ in range(NBUF)]
+    ev_d2h = [torch.cuda.Event() for _ in range(NBUF)]
     out_host = [None] * NBUF
     keep = [None] * NBUF
     d2h_bytes = [0]
@@ -474,6 +475,11 @@ def main():
     def issue_step(i):
         b = i % NBUF
         main.wait_event(ev_h2d[b])
+        # the results of the step that used this slot last (two steps ago) have been read back: only now may their
+        # device memory go back to the allocator (explicit events instead of Tensor.record_stream, whose deferred
+        # frees make the caching allocator grow -- cudaMalloc inside the timed region -- on an unlucky interleaving)
+        main.wait_event(ev_d2h[b])
+        keep[b] = None
         lv = {k: dbuf[b][k].detach().requires_grad_() for k in keys if k != "grad_output"}
         mod.weight.grad = None
         y = fwd_bwd(lv["x"], lv["offset"], lv.get("mask"), dbuf[b]["grad_output"])
@@ -484,8 +490,8 @@ def main():
         with torch.cuda.stream(s_d2h):
             s_d2h.wait_event(ev_comp[b])
             for hbuf, r in zip(out_host[b], res):
-                r.record_stream(s_d2h)
                 hbuf.copy_(r, non_blocking=True)
+            ev_d2h[b].record(s_d2h)
         keep[b] = res
         d2h_bytes[0] = sum(r.numel() * r.element_size() for r in res)
 
@@ -502,10 +508,12 @@ def main():
     d2h = d2h_bytes[0]
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ke = max(3, K_steps)
+    seg0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
     e2.record()
     run_e2e(ke)
     e3.record()
     sync_all()
+    e2e_device_allocs = torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - seg0   # cudaMalloc calls inside the region
     ms_e2e = e2.elapsed_time(e3)
     if world > 1:
         tmax = torch.tensor([ms_e2e], device=dev)
@@ -695,7 +703,7 @@ def main():
                            "collective": "1 NCCL all-reduce(sum) of [grad_weight||grad_bias] per step, issued inside the backward on a "
                                          "side stream once the weight-gradient kernels finish" if world > 1 else "none"},
                 "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": ms_e2e / ke, "steps": ke,
+                        "ms_per_step": ms_e2e / ke, "steps": ke, "cuda_mallocs_in_region": e2e_device_allocs,
                         "achieved_h2d_gbs": h2d / (ms_e2e / ke * 1e-3) / 1e9,
                         "achieved_d2h_gbs": d2h / (ms_e2e / ke * 1e-3) / 1e9,
                         "copy_only_probe": copy_probe,
