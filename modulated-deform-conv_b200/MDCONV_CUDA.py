@@ -415,9 +415,18 @@ def _backward(input, weight, bias, offset, mask, grad_output, grads, kernel, str
         if grads is None:
             grads = {"grad_input": torch.empty_like(input, memory_format=torch.preserve_format),
                      "grad_offset": torch.empty_like(offset),
-                     "grad_mask": torch.empty_like(mask) if modulated else None,
-                     "grad_weight": torch.empty_like(weight),
-                     "grad_bias": torch.empty_like(bias) if with_bias else torch.zeros_like(bias)}
+                     "grad_mask": torch.empty_like(mask) if modulated else None}
+            if want_f32 and with_bias and input.dtype != torch.float64:
+                # the two parameter gradients as views of ONE buffer, [grad_weight || grad_bias] like flat_f32: a
+                # batch-sharded caller rounds the reduced fp32 sum into both with a single copy
+                nw = weight.numel()
+                both = torch.empty(nw + bias.numel(), dtype=weight.dtype, device=input.device)
+                grads["grad_weight"] = both[:nw].view(weight.shape)
+                grads["grad_bias"] = both[nw:]
+                grads["flat_storage"] = both
+            else:
+                grads["grad_weight"] = torch.empty_like(weight)
+                grads["grad_bias"] = torch.empty_like(bias) if with_bias else torch.zeros_like(bias)
         else:
             _expect(grads["grad_input"], input.shape, "grad_input")
             _expect(grads["grad_offset"], offset.shape, "grad_offset")

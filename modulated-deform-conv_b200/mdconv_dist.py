@@ -145,20 +145,29 @@ class GradSync:
                 dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
                 self._scale(t)
             return
+        # Host cost matters here (this runs inside every backward, once per rank, and eight launch loops share one
+        # host): set_stream instead of the torch.cuda.stream context manager, one rounding copy when the gradients
+        # are views of one buffer, and no Tensor.record_stream -- the main stream re-joins the communication stream
+        # below, before this call returns, so whatever frees or re-uses these tensors afterwards is already ordered
+        # behind the collective and the copies.
         main = torch.cuda.current_stream(outs[0].device)
         self._stream.wait_event(self.event)          # only grad_weight / grad_bias, not the whole backward
-        with torch.cuda.stream(self._stream):
+        torch.cuda.set_stream(self._stream)
+        try:
             if self.trace is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(self._stream)
             if flat32 is not None:
                 dist.all_reduce(flat32, op=dist.ReduceOp.SUM, group=self.group)
                 self._scale(flat32)
-                off = 0
-                for t in outs:                       # the single rounding to the storage dtype
-                    t.copy_(flat32[off:off + t.numel()].view(t.shape))
-                    off += t.numel()
-                flat32.record_stream(self._stream)
+                both = grads.get("flat_storage")
+                if both is not None and both.numel() == flat32.numel():
+                    both.copy_(flat32)               # the single rounding to the storage dtype, both gradients at once
+                else:
+                    off = 0
+                    for t in outs:
+                        t.copy_(flat32[off:off + t.numel()].view(t.shape))
+                        off += t.numel()
                 if self.keep_last:
                     self.last_flat32 = flat32
             else:
@@ -173,8 +182,8 @@ class GradSync:
             if self.trace is not None:
                 e1.record(self._stream)
                 self.trace.append((e0, e1))
-            for t in outs:
-                t.record_stream(self._stream)
+        finally:
+            torch.cuda.set_stream(main)
         main.wait_stream(self._stream)
 
 
