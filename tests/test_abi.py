@@ -65,6 +65,35 @@ def test_geometry_validation_and_sizes():
     assert M._lib.mdconv_forward(ctypes.byref(g3), None, None, None, None, None, None, None, 0, None) == 2
 
 
+def test_grad_columns_budget_shapes_the_backward_workspace():
+    """Host logic of the col2im-gather grad_input (no GPU needed): the backward workspace of a 16-bit tensor-path call
+    holds ONE grad_columns buffer -- the whole batch's when it fits the cap, a whole number of samples otherwise -- and
+    none at all with a cap of 0 (grad_input as a contraction) or for fp32 callers."""
+    import MDCONV_CUDA as M
+    x = torch.empty(32, 256, 56, 56, dtype=torch.float16)
+    w = torch.empty(256, 256, 3, 3, dtype=torch.float16)
+    g = M._geom(x, w, (3, 3), (1, 1), (1, 1), (1, 1), 1, 1, True, False)
+    g.path = 2
+    if M._lib.mdconv_selected_path(ctypes.byref(g), 1) != 2:
+        pytest.skip("tensor path not selectable on this host")
+    sample = 3136 * 9 * 256 * 2                       # bytes of one sample's grad_columns [K][P][C]
+    prev = M.set_gcol_budget_mb(1024)
+    try:
+        full = M._lib.mdconv_workspace_bytes(ctypes.byref(g), 1)
+        assert M.set_gcol_budget_mb(64) == 1024       # the setter returns the previous cap
+        chunked = M._lib.mdconv_workspace_bytes(ctypes.byref(g), 1)
+        M.set_gcol_budget_mb(0)
+        none = M._lib.mdconv_workspace_bytes(ctypes.byref(g), 1)
+        fwd = M._lib.mdconv_workspace_bytes(ctypes.byref(g), 0)
+    finally:
+        M.set_gcol_budget_mb(prev if prev >= 0 else 1024)
+    assert full - chunked == (32 - (64 * 2 ** 20) // sample) * sample      # 32 samples vs the 4 that fit 64 MiB
+    assert 0 < none < chunked < full
+    got_wt = 32 * 256 * 3136 * 2 + 256 * 2304 * 2     # what the contraction route needs instead: got + wt
+    assert abs((full - 32 * sample) - (none - got_wt)) < 4096              # same index / partials either way
+    assert fwd < none                                  # the forward needs neither
+
+
 def test_python_surface_matches_reference_names():
     import MDCONV_CUDA
     import modulated_deform_conv as mdc
